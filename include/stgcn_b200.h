@@ -1,0 +1,179 @@
+/*
+ * stgcn_b200.h -- C ABI of the B200-native ST-GCN / RT-ST-GCN forward path.
+ *
+ * The reference (maximyudayev/Realtime-ST-GCN) has no FFI layer: its hot path is
+ * a set of torch.nn.Module.forward methods.  Each entry point below replaces the
+ * body of one of them; the Python modules under realtime-st-gcn_b200/models/
+ * keep the reference constructor/forward signatures and call these through
+ * ctypes (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors use the reference layout (N, C, T, V), fp32, contiguous, unless
+ *     stated otherwise; parameter tensors use the reference state_dict layouts;
+ *   - the library never allocates or frees memory: the caller (torch) owns all
+ *     inputs, outputs, parameters, workspaces and FIFO state;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - return value 0 = success, non-zero = error; stgcn_last_error() returns a
+ *     thread-local message.  There is no CPU fallback: a non-sm_100 device or a
+ *     missing GPU is an error.
+ */
+#ifndef STGCN_B200_H
+#define STGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STGCN_ABI_VERSION 1
+
+enum { STGCN_NORM_LAYERNORM = 0, STGCN_NORM_BATCHNORM = 1 };
+enum { STGCN_RES_NONE = 0, STGCN_RES_IDENTITY = 1, STGCN_RES_CONV = 2 };
+/* arithmetic of the GEMM stages */
+enum {
+  STGCN_MATH_FP32 = 0,      /* fp32 CUDA-core FMA (exact reference arithmetic)          */
+  STGCN_MATH_BF16X3 = 1,    /* tcgen05 bf16 hi/lo split, 3 MMAs, fp32 accumulate (1e-4) */
+  STGCN_MATH_BF16 = 2       /* tcgen05 single bf16 MMA, fp32 accumulate                 */
+};
+
+/* One st_gcn block.  Replaces StgcnLayer.forward (reference
+ * models/stgcn/stgcn.py:181-193) when `rt == 0` and OnlineLayer.forward
+ * (models/rtstgcn/rtstgcn.py:528-553 + AggregateStgcn.forward :591-627) when
+ * `rt == 1`.  Parameter pointers use the reference layouts:
+ *   gcn_w  (K*c_out, c_in)      gcn.conv.weight / conv.weight        (1x1)
+ *   gcn_b  (K*c_out)            gcn.conv.bias   / conv.bias
+ *   a_eff  (K, V, V)            A * edge_importance (or per-sample (N,K,V,V))
+ *   n1_w/b (c_out, V) | (c_out) tcn.0 / bn_relu.0   LayerNorm | BatchNorm
+ *   tcn_w  (c_out, c_out, G)    tcn.2.weight  (G x 1 temporal conv; ST-GCN only)
+ *   tcn_b  (c_out)              tcn.2.bias
+ *   n2_w/b                      tcn.3         (ST-GCN only)
+ *   res_w  (c_out, c_in)        residual.0.weight
+ *   res_b  (c_out) or NULL      residual.0.bias (NULL for RT: conv has no bias)
+ *   nr_w/b                      residual.1
+ */
+typedef struct stgcn_layer_desc {
+  int32_t c_in, c_out;
+  int32_t kernel;        /* temporal kernel Gamma (odd) */
+  int32_t stride;
+  int32_t residual;      /* STGCN_RES_* */
+  int32_t norm;          /* STGCN_NORM_* */
+  int32_t rt;            /* 0: ST-GCN layer, 1: RT-ST-GCN online layer */
+  int32_t a_per_sample;  /* 0: a_eff is (K,V,V); 1: (N,K,V,V) */
+  const float *gcn_w, *gcn_b, *a_eff;
+  const float *n1_w, *n1_b;
+  const float *tcn_w, *tcn_b;
+  const float *n2_w, *n2_b;
+  const float *res_w, *res_b;
+  const float *nr_w, *nr_b;
+} stgcn_layer_desc;
+
+/* Whole model.  Replaces models.stgcn.Model.forward (stgcn.py:80-97) and
+ * models.rtstgcn.Model.forward with online layers (rtstgcn.py:137-157).
+ *   norm_in_w/b : LayerNorm (c_in, V) | BatchNorm1d (V*c_in) (batchnorm.py:13-23)
+ *   fcn_in_w (c0, c_in), fcn_in_b (c0); fcn_out_w (classes, c_last), fcn_out_b
+ */
+typedef struct stgcn_model_desc {
+  int32_t in_feat, num_joints, partitions, num_classes, num_layers;
+  int32_t norm;          /* STGCN_NORM_* */
+  int32_t math;          /* STGCN_MATH_* */
+  int32_t reserved;
+  const float *norm_in_w, *norm_in_b;
+  const float *fcn_in_w, *fcn_in_b;
+  const float *fcn_out_w, *fcn_out_b;
+  const stgcn_layer_desc *layers;   /* HOST pointer to num_layers descriptors */
+} stgcn_model_desc;
+
+/* ---- library ------------------------------------------------------------- */
+int stgcn_abi_version(void);
+const char *stgcn_last_error(void);
+/* 0 if `device` is an sm_100 GPU this build can run on. */
+int stgcn_device_check(int device);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long stgcn_launch_count(void);
+/* Measurement aid: between begin/end every kernel launch is bracketed by CUDA events on its
+ * stream; end() synchronises and returns summed milliseconds and launch counts per kernel class:
+ * 0 layout, 1 gemm_1x1, 2 gemm_tcn, 3 frame(adjacency/norm/residual), 4 batchnorm, 5 embed,
+ * 6 pool+classifier, 7 misc.  Not re-entrant; single device. */
+#define STGCN_KERNEL_CLASSES 8
+int stgcn_profile_begin(void);
+int stgcn_profile_end(float *ms_per_class_host, long long *launches_per_class_host, int n_classes);
+
+/* ---- primitives (models/utils) -------------------------------------------- */
+/* LayerNorm over (C,V) per (n,t), unbiased variance, affine (C,V).
+ * Replaces LayerNorm.forward, models/utils/layernorm.py:22-28. */
+int stgcn_layernorm_forward(const float *x, const float *w, const float *b, float *y,
+                            int N, int C, int T, int V, float eps, void *stream);
+/* Batch-statistics BatchNorm.  mode 0: per channel over (N,T,V)
+ * (nn.BatchNorm2d(track_running_stats=False), stgcn.py:152); mode 1: per (v,c)
+ * feature over (N,T), weight index v*C+c (BatchNorm1d.forward,
+ * models/utils/batchnorm.py:13-23).  workspace >= stgcn_batchnorm_workspace_bytes. */
+size_t stgcn_batchnorm_workspace_bytes(int C, int V, int mode);
+int stgcn_batchnorm_forward(const float *x, const float *w, const float *b, float *y,
+                            int N, int C, int T, int V, float eps, int mode,
+                            void *workspace, size_t workspace_bytes, void *stream);
+/* Gamma x 1 convolution over time with stride and zero padding (kernel-1)/2,
+ * weight (c_out, c_in, kernel), optional bias.  Replaces the nn.Conv2d calls at
+ * stgcn.py:85,95,154-159,166-170 and tgcn.py:71. */
+size_t stgcn_conv_workspace_bytes(int N, int c_in, int c_out, int T, int V, int kernel, int stride);
+int stgcn_conv_forward(const float *x, const float *w, const float *bias, float *y,
+                       int N, int c_in, int c_out, int T, int V, int kernel, int stride,
+                       void *workspace, size_t workspace_bytes, void *stream);
+/* Graph convolution: 1x1 conv c_in -> K*c_out, contraction with A over (k,v).
+ * Replaces ConvTemporalGraphical.forward, models/utils/tgcn.py:58-79. */
+size_t stgcn_graphconv_workspace_bytes(int N, int c_in, int c_out, int K, int T, int V);
+int stgcn_graphconv_forward(const float *x, const float *w, const float *bias, const float *A,
+                            int a_per_sample, float *y, int N, int c_in, int c_out, int K,
+                            int T, int V, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- ST-GCN layer / model --------------------------------------------------- */
+size_t stgcn_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int N, int T);
+/* x (N,c_in,T,V) -> y (N,c_out,T_out,V), T_out = (T-1)/stride + 1. */
+int stgcn_layer_forward(const stgcn_layer_desc *d, int K, int V, int math, const float *x,
+                        float *y, int N, int T, void *workspace, size_t workspace_bytes,
+                        void *stream);
+size_t stgcn_model_workspace_bytes(const stgcn_model_desc *m, int N, int T);
+/* x (N,in_feat,T,V) -> logits (N,num_classes); features (optional, may be NULL):
+ * pre-pool trunk output in the reference layout (N,c_last,T_final,V).
+ * t_halo_left/right: T-split support -- see stgcn_model_forward_tsplit. */
+int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits,
+                        float *features, int N, int T, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* ---- RT-ST-GCN continual step ----------------------------------------------- */
+/* Per-stream FIFO/accumulator state for B concurrent streams (fp32):
+ * per layer fifo[F][B][V][c_out] (F = stride*(kernel-1)+1) and acc[stride][B][V][c_out],
+ * plus one int32 frame counter per stream.  Replaces the Python attributes
+ * fifo/accumulator/fifo_idx/accumulator_idx of AggregateStgcn (rtstgcn.py:576-579). */
+size_t rtstgcn_state_bytes(const stgcn_model_desc *m, int B);
+/* Zero the state of streams [first, first+count) (all layers). */
+int rtstgcn_state_reset(const stgcn_model_desc *m, void *state, int B, int first, int count,
+                        void *stream);
+size_t rtstgcn_step_workspace_bytes(const stgcn_model_desc *m, int B);
+/* One frame for every stream: x (B,in_feat,1,V) -> logits (B,num_classes). */
+int rtstgcn_step(const stgcn_model_desc *m, const float *x, void *state, float *logits, int B,
+                 void *workspace, size_t workspace_bytes, void *stream);
+/* One OnlineLayer.forward on x (B,c_in,1,V) -> y (B,c_out,1,V); layer_state is the
+ * slice for this layer laid out as rtstgcn_layer_state_bytes describes. */
+size_t rtstgcn_layer_state_bytes(const stgcn_layer_desc *d, int V, int B);
+size_t rtstgcn_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int B);
+int rtstgcn_layer_step(const stgcn_layer_desc *d, int K, int V, int math, const float *x,
+                       float *y, void *layer_state, int32_t *frame_counter, int B,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- host-buffer entry points (processor.py:367,380 / :418 equivalents) ----- */
+/* x_host/logits_host are HOST buffers (pinned for async copies); device_io must
+ * hold N*in_feat*T*V + N*num_classes floats.  H2D, forward, D2H on `stream`. */
+int stgcn_model_forward_host(const stgcn_model_desc *m, const float *x_host, float *logits_host,
+                             int N, int T, void *device_io, void *workspace,
+                             size_t workspace_bytes, void *stream);
+int rtstgcn_step_host(const stgcn_model_desc *m, const float *x_host, void *state,
+                      float *logits_host, int B, void *device_io, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STGCN_B200_H */

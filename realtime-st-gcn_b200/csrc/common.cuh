@@ -1,0 +1,124 @@
+// Shared helpers for the stgcn_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+namespace stgcn {
+
+// thread-local last-error message (the library is re-entrant across devices/streams)
+inline char *err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define STGCN_CUDA_OK(expr)                                                               \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return ::stgcn::fail("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- launch accounting / optional per-kernel-class event timing ---------------------
+// Classes used by bench.py's roofline leg (stgcn_profile_*).
+enum KernelClass {
+  KC_LAYOUT = 0,   // NCTV <-> NTVC transposes
+  KC_GEMM_1X1,     // feature transform / residual 1x1 GEMMs
+  KC_GEMM_TCN,     // Gamma x 1 temporal implicit GEMM
+  KC_FRAME,        // adjacency + norm + residual epilogue kernels
+  KC_BN,           // batch-statistics kernels
+  KC_EMBED,        // norm_in + fcn_in
+  KC_POOL,         // pooling + classifier
+  KC_MISC,         // weight packing, CSR build, counters
+  KC_COUNT
+};
+
+struct Profiler {
+  std::atomic<long long> launches{0};
+  bool on = false;
+  static constexpr int kMax = 4096;
+  cudaEvent_t ev[kMax][2];
+  int cls[kMax];
+  int n = 0;       // events in flight
+  int created = 0; // events created so far
+  float ms[KC_COUNT] = {0};
+  long long count[KC_COUNT] = {0};
+};
+inline Profiler &prof() {
+  static Profiler p;
+  return p;
+}
+// RAII: brackets one kernel launch with events when profiling is on.
+struct ProfScope {
+  cudaStream_t st;
+  int slot = -1;
+  ProfScope(int cls, cudaStream_t s) : st(s) {
+    Profiler &p = prof();
+    if (!p.on || p.n >= Profiler::kMax) return;
+    slot = p.n++;
+    if (slot >= p.created) {
+      cudaEventCreate(&p.ev[slot][0]);
+      cudaEventCreate(&p.ev[slot][1]);
+      p.created = slot + 1;
+    }
+    p.cls[slot] = cls;
+    cudaEventRecord(p.ev[slot][0], st);
+  }
+  ~ProfScope() {
+    if (slot >= 0) cudaEventRecord(prof().ev[slot][1], st);
+  }
+};
+
+#define STGCN_LAUNCH_OK()                                                                 \
+  do {                                                                                    \
+    ::stgcn::prof().launches.fetch_add(1, std::memory_order_relaxed);                     \
+    cudaError_t e_ = cudaGetLastError();                                                  \
+    if (e_ != cudaSuccess)                                                                \
+      return ::stgcn::fail("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define STGCN_REQUIRE(cond, ...)                                                          \
+  do {                                                                                    \
+    if (!(cond)) return ::stgcn::fail(__VA_ARGS__);                                       \
+  } while (0)
+
+// Bump allocator over a caller-owned workspace.  With base == nullptr it only
+// measures, so *_workspace_bytes() and the forward share one code path.
+struct Bump {
+  char *base;
+  size_t cap;
+  size_t off = 0;
+  size_t peak = 0;
+  bool overflow = false;
+  Bump(void *b, size_t c) : base(static_cast<char *>(b)), cap(c) {}
+  template <typename T>
+  T *take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    size_t at = off;
+    off += bytes;
+    if (off > peak) peak = off;
+    if (!base) return nullptr;
+    if (off > cap) {
+      overflow = true;
+      return nullptr;
+    }
+    return reinterpret_cast<T *>(base + at);
+  }
+  bool measuring() const { return base == nullptr; }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace stgcn

@@ -1,0 +1,706 @@
+// fp32 CUDA-core kernels of the ST-GCN / RT-ST-GCN forward path (sm_100a).
+//
+// Internal activation layout is channels-last: rows r = (n*T + t)*V + v, each row
+// holding C contiguous fp32 channels ("NTVC").  The reference layout (N,C,T,V) is
+// converted only at API entry/exit.
+//
+// These kernels are the STGCN_MATH_FP32 arithmetic (exact reference arithmetic,
+// also the path for shapes the tcgen05 kernels do not cover: C % 64 != 0, tiny
+// batches).  The tensor-core kernels live in kernels_tc.cuh.
+#pragma once
+#include "common.cuh"
+
+namespace stgcn {
+
+// --------------------------------------------------------------------------- //
+// layout conversion  x[n][c][p] <-> y[n][p][c]   (p = t*V + v)
+// --------------------------------------------------------------------------- //
+// The channels-last side may be padded to `ld >= C` channels (zero filled / ignored).
+__global__ void k_cp_to_pc(const float *__restrict__ x, float *__restrict__ y, int C, long long P, int ld) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float *xs = x + n * C * P;
+  float *ys = y + n * ld * P;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    long long p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < P) ? xs[(long long)c * P + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long long p = p0 + i;
+    int c = c0 + threadIdx.x;
+    if (c < ld && p < P) ys[p * ld + c] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void k_pc_to_cp(const float *__restrict__ x, float *__restrict__ y, int C, long long P, int ld) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float *xs = x + n * ld * P;
+  float *ys = y + n * C * P;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long long p = p0 + i;
+    int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < P) ? xs[p * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    long long p = p0 + threadIdx.x;
+    if (c < C && p < P) ys[(long long)c * P + p] = tile[threadIdx.x][i];
+  }
+}
+
+// --------------------------------------------------------------------------- //
+// weight repack: temporal conv weight (c_out, c_in, G) -> (c_out, G, c_in) so the
+// implicit-GEMM K index is (tap, channel) with channels contiguous.
+// --------------------------------------------------------------------------- //
+__global__ void k_pack_tcn_w(const float *__restrict__ w, float *__restrict__ wp, int c_out, int c_in,
+                             int G, int c_out_p, int c_in_p) {
+  // destination (c_out_p, G, c_in_p), zero padded
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)c_out_p * c_in_p * G;
+  if (i >= total) return;
+  int ci = i % c_in_p;
+  long long r = i / c_in_p;
+  int j = r % G;
+  int co = r / G;
+  wp[i] = (co < c_out && ci < c_in) ? w[((long long)co * c_in + ci) * G + j] : 0.f;
+}
+
+__global__ void k_pad_vec(const float *__restrict__ src, float *__restrict__ dst, int n, int n_p) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_p) dst[i] = (i < n) ? src[i] : 0.f;
+}
+
+// --------------------------------------------------------------------------- //
+// implicit GEMM over time taps:
+//   Y[m, co] = bias[co] + sum_{j<G} sum_{c<C_in} X[src(m,j), c] * Wp[co, j*C_in + c]
+//   m = (n, tau, w),  src = (n, stride*tau + j - pad, w), zero outside [0, T_in)
+// G = 1 gives the 1x1 convs (gcn feature transform, strided residual conv).
+// --------------------------------------------------------------------------- //
+struct ConvGeom {
+  int M;  // N * T_out * V
+  int T_in, T_out, V, C_in, C_out, G, stride, pad, Ktot;
+};
+
+template <int BM, int BN, int BK>
+__global__ void __launch_bounds__(256)
+    k_gemm_conv(const float *__restrict__ X, const float *__restrict__ Wp, const float *__restrict__ bias,
+                float *__restrict__ Y, ConvGeom g) {
+  static_assert(BM == 128 && BN == 64 && BK == 16, "tile shape is tied to the thread mapping");
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  // A-load assignment: two float4 per thread (row = idx>>2, kq = idx&3)
+  int a_row[2], a_n[2], a_tau[2], a_w[2];
+  bool a_ok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int idx = tid + i * 256;
+    a_row[i] = idx >> 2;
+    int m = m0 + a_row[i];
+    a_ok[i] = m < g.M;
+    int mm = a_ok[i] ? m : 0;
+    a_w[i] = mm % g.V;
+    int tmp = mm / g.V;
+    a_tau[i] = tmp % g.T_out;
+    a_n[i] = tmp / g.T_out;
+  }
+  const int kq = tid & 3;
+  const int b_col = tid >> 2;
+  const bool b_ok = (n0 + b_col) < g.C_out;
+
+  float4 ra[2], rb;
+  auto load_tile = [&](int k0) {
+    int kk = k0 + kq * 4;
+    int j = kk / g.C_in;
+    int c = kk - j * g.C_in;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int ts = g.stride * a_tau[i] + j - g.pad;
+      bool ok = a_ok[i] && kk < g.Ktot && ts >= 0 && ts < g.T_in;
+      if (ok) {
+        long long src = (((long long)a_n[i] * g.T_in + ts) * g.V + a_w[i]) * g.C_in + c;
+        ra[i] = *reinterpret_cast<const float4 *>(X + src);
+      } else {
+        ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (b_ok && kk < g.Ktot)
+      rb = *reinterpret_cast<const float4 *>(Wp + (long long)(n0 + b_col) * g.Ktot + kk);
+    else
+      rb = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      As[buf][kq * 4 + 0][a_row[i]] = ra[i].x;
+      As[buf][kq * 4 + 1][a_row[i]] = ra[i].y;
+      As[buf][kq * 4 + 2][a_row[i]] = ra[i].z;
+      As[buf][kq * 4 + 3][a_row[i]] = ra[i].w;
+    }
+    Bs[buf][kq * 4 + 0][b_col] = rb.x;
+    Bs[buf][kq * 4 + 1][b_col] = rb.y;
+    Bs[buf][kq * 4 + 2][b_col] = rb.z;
+    Bs[buf][kq * 4 + 3][b_col] = rb.w;
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = (g.Ktot + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tile((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store_tile(buf ^ 1);
+    __syncthreads();
+  }
+
+  const int co = n0 + tx * 4;
+  if (co < g.C_out) {
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = *reinterpret_cast<const float4 *>(bias + co);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m = m0 + ty * 8 + i;
+      if (m < g.M) {
+        float4 o = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+        *reinterpret_cast<float4 *>(Y + (long long)m * g.C_out + co) = o;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- //
+// adjacency in CSR-by-output-joint form.  A[k][v][w] (already A*importance):
+//   ptr[w] .. ptr[w+1]  ->  (yoff = v*K*C + k*C, val) in (k,v) order.
+// Dense A (e.g. AA-GCN's A+B+C) simply yields K*V entries per joint.
+// One block per sample (blockIdx.x) when A is per-sample.
+// --------------------------------------------------------------------------- //
+__global__ void k_build_adj_csr(const float *__restrict__ A, int K, int V, int C, int *__restrict__ ptr,
+                                int *__restrict__ yoff, float *__restrict__ val) {
+  extern __shared__ int s_cnt[];  // V + 1
+  const int n = blockIdx.x;
+  const float *a = A + (long long)n * K * V * V;
+  int *p = ptr + (long long)n * (V + 1);
+  int *yo = yoff + (long long)n * K * V * V;
+  float *va = val + (long long)n * K * V * V;
+  for (int w = threadIdx.x; w < V; w += blockDim.x) {
+    int c = 0;
+    for (int kv = 0; kv < K * V; ++kv) c += (a[(long long)kv * V + w] != 0.f);
+    s_cnt[w] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < V; ++w) {
+      int c = s_cnt[w];
+      s_cnt[w] = run;
+      run += c;
+    }
+    s_cnt[V] = run;
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w <= V; w += blockDim.x) p[w] = s_cnt[w];
+  for (int w = threadIdx.x; w < V; w += blockDim.x) {
+    int at = s_cnt[w];
+    for (int kv = 0; kv < K * V; ++kv) {
+      float x = a[(long long)kv * V + w];
+      if (x != 0.f) {
+        int k = kv / V, v = kv - k * V;
+        yo[at] = v * K * C + k * C;
+        va[at] = x;
+        ++at;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- //
+// block reduction helper (sum), all threads get the result
+// --------------------------------------------------------------------------- //
+__device__ __forceinline__ float block_sum(float v, float *s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // protect s_red reuse
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (lane < nw) ? s_red[lane] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+// --------------------------------------------------------------------------- //
+// per-frame fused kernel.  One frame = V rows x C channels (all statistics of the
+// reference LayerNorm live inside one frame).
+//   producer: a = load | adjacency(y) | RT aggregate (adjacency + FIFO/accumulator)
+//   a' = LN(a) (optional), relu_mid (optional)
+//   out = relu_out( a' + [ b | LN(b) ] )
+// --------------------------------------------------------------------------- //
+enum { FRAME_LOAD = 0, FRAME_ADJ = 1, FRAME_RT = 2 };
+enum { B_NONE = 0, B_RAW = 1, B_LN = 2 };
+
+struct FrameArgs {
+  int producer;
+  long long frames;       // N*T (RT: B)
+  int frames_per_sample;  // T, to pick the per-sample adjacency
+  int K, V, C;
+  const float *a;  // FRAME_LOAD: [frames*V, C]
+  const float *y;  // FRAME_ADJ/RT: [frames*V, K*C]
+  const int *adj_ptr;
+  const int *adj_yoff;
+  const float *adj_val;
+  int adj_per_sample;
+  int norm_a;  // 1: LayerNorm(C,V) on a
+  const float *na_w, *na_b;
+  int relu_mid;
+  int b_mode;
+  const float *b;
+  const float *nb_w, *nb_b;
+  int relu_out;
+  float eps;
+  float *out;
+  // RT state
+  float *fifo, *acc;
+  const int *counter;
+  int F, S;
+};
+
+__global__ void __launch_bounds__(256) k_frame(FrameArgs p) {
+  extern __shared__ __align__(16) float s_buf[];
+  __shared__ float s_red[32];
+  const int VC = p.V * p.C;
+  float *za = s_buf;
+  float *zb = s_buf + VC;
+  const float inv_n = 1.f / (float)VC;
+  const float inv_nm1 = 1.f / (float)(VC - 1);
+
+  for (long long f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    const long long row0 = f * p.V;
+    // ---- producer ----
+    if (p.producer == FRAME_LOAD) {
+      const float *src = p.a + row0 * p.C;
+      for (int i = threadIdx.x; i < VC; i += blockDim.x) za[i] = src[i];
+    } else {
+      const long long smp = p.adj_per_sample ? (f / p.frames_per_sample) : 0;
+      const int *ptr = p.adj_ptr + smp * (p.V + 1);
+      const int *yo = p.adj_yoff + smp * (long long)p.K * p.V * p.V;
+      const float *va = p.adj_val + smp * (long long)p.K * p.V * p.V;
+      const float *ysrc = p.y + row0 * (long long)p.K * p.C;
+      int fi = 0, ai = 0;
+      if (p.producer == FRAME_RT) {
+        int t = p.counter[f];
+        fi = t % p.F;
+        ai = t % p.S;
+      }
+      for (int i = threadIdx.x; i < VC; i += blockDim.x) {
+        const int w = i / p.C, c = i - w * p.C;
+        float z = 0.f;
+        const int e1 = ptr[w + 1];
+        for (int e = ptr[w]; e < e1; ++e) z = fmaf(ysrc[yo[e] + c], va[e], z);
+        if (p.producer == FRAME_RT) {
+          // acc <- (acc + z) + (-fifo[fi]);  fifo[fi] <- z   (rtstgcn.py:611-621)
+          const long long so = (f * p.V + w) * (long long)p.C + c;
+          const long long per = p.frames * (long long)VC;
+          float *fp = p.fifo + (long long)fi * per + so;
+          float *ap = p.acc + (long long)ai * per + so;
+          float a = *ap + z;
+          a = a + (-*fp);
+          *ap = a;
+          *fp = z;
+          z = a;
+        }
+        za[i] = z;
+      }
+    }
+    if (p.b_mode == B_LN) {
+      const float *src = p.b + row0 * p.C;
+      for (int i = threadIdx.x; i < VC; i += blockDim.x) zb[i] = src[i];
+    }
+    __syncthreads();
+
+    // ---- statistics ----
+    float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f;
+    if (p.norm_a) {
+      float s = 0.f;
+      for (int i = threadIdx.x; i < VC; i += blockDim.x) s += za[i];
+      mean_a = block_sum(s, s_red) * inv_n;
+      float q = 0.f;
+      for (int i = threadIdx.x; i < VC; i += blockDim.x) {
+        float d = za[i] - mean_a;
+        q = fmaf(d, d, q);
+      }
+      rstd_a = 1.f / sqrtf(block_sum(q, s_red) * inv_nm1 + p.eps);
+    }
+    if (p.b_mode == B_LN) {
+      float s = 0.f;
+      for (int i = threadIdx.x; i < VC; i += blockDim.x) s += zb[i];
+      mean_b = block_sum(s, s_red) * inv_n;
+      float q = 0.f;
+      for (int i = threadIdx.x; i < VC; i += blockDim.x) {
+        float d = zb[i] - mean_b;
+        q = fmaf(d, d, q);
+      }
+      rstd_b = 1.f / sqrtf(block_sum(q, s_red) * inv_nm1 + p.eps);
+    }
+
+    // ---- epilogue ----
+    float *dst = p.out + row0 * p.C;
+    for (int i = threadIdx.x; i < VC; i += blockDim.x) {
+      const int w = i / p.C, c = i - w * p.C;
+      const int pi = c * p.V + w;  // reference affine layout (C, 1, V)
+      float v = za[i];
+      if (p.norm_a) v = (v - mean_a) * rstd_a * p.na_w[pi] + p.na_b[pi];
+      if (p.relu_mid) v = fmaxf(v, 0.f);
+      if (p.b_mode == B_RAW) {
+        v += p.b[row0 * p.C + i];
+      } else if (p.b_mode == B_LN) {
+        v += (zb[i] - mean_b) * rstd_b * p.nb_w[pi] + p.nb_b[pi];
+      }
+      if (p.relu_out) v = fmaxf(v, 0.f);
+      dst[i] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------- //
+// stand-alone module kernels working directly on the reference layout (N,C,T,V)
+// --------------------------------------------------------------------------- //
+// LayerNorm over (C,V) per (n,t), unbiased variance (layernorm.py:22-28).
+__global__ void __launch_bounds__(256)
+    k_layernorm_nctv(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
+                     float *__restrict__ y, int N, int C, int T, int V, float eps) {
+  extern __shared__ __align__(16) float s_buf[];
+  __shared__ float s_red[32];
+  const int CV = C * V;
+  const float inv_n = 1.f / (float)CV, inv_nm1 = 1.f / (float)(CV - 1);
+  const long long frames = (long long)N * T;
+  for (long long f = blockIdx.x; f < frames; f += gridDim.x) {
+    const long long n = f / T, t = f - n * T;
+    for (int i = threadIdx.x; i < CV; i += blockDim.x) {
+      int c = i / V, v = i - c * V;
+      s_buf[i] = x[((n * C + c) * T + t) * V + v];
+    }
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < CV; i += blockDim.x) s += s_buf[i];
+    const float mean = block_sum(s, s_red) * inv_n;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < CV; i += blockDim.x) {
+      float d = s_buf[i] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = 1.f / sqrtf(block_sum(q, s_red) * inv_nm1 + eps);
+    for (int i = threadIdx.x; i < CV; i += blockDim.x) {
+      int c = i / V, v = i - c * V;
+      y[((n * C + c) * T + t) * V + v] = (s_buf[i] - mean) * rstd * w[i] + b[i];
+    }
+    __syncthreads();
+  }
+}
+
+// Batch statistics on (N,C,T,V).  mode 0: per channel; mode 1: per (v,c) feature v*C+c.
+__global__ void __launch_bounds__(256)
+    k_bn_stats_nctv(const float *__restrict__ x, int C, int T, int V, int mode, int chunk,
+                    double *__restrict__ sum, double *__restrict__ sumsq) {
+  extern __shared__ double s_d[];  // mode 1: 2*V
+  __shared__ double s_w[2][8];
+  const int c = blockIdx.y;
+  const long long n = blockIdx.z;
+  const long long plane = (long long)T * V;
+  const float *xs = x + (n * C + c) * plane;
+  long long i0 = (long long)blockIdx.x * chunk, i1 = i0 + chunk;
+  if (i1 > plane) i1 = plane;
+  if (mode == 1) {
+    for (int v = threadIdx.x; v < 2 * V; v += blockDim.x) s_d[v] = 0.0;
+    __syncthreads();
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+      float val = xs[i];
+      int v = (int)(i % V);
+      atomicAdd(&s_d[v], (double)val);
+      atomicAdd(&s_d[V + v], (double)val * val);
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      atomicAdd(&sum[v * C + c], s_d[v]);
+      atomicAdd(&sumsq[v * C + c], s_d[V + v]);
+    }
+  } else {
+    double s = 0.0, q = 0.0;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+      float val = xs[i];
+      s += val;
+      q += (double)val * val;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_w[0][threadIdx.x >> 5] = s;
+      s_w[1][threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double ts = 0, tq = 0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+        ts += s_w[0][k];
+        tq += s_w[1][k];
+      }
+      atomicAdd(&sum[c], ts);
+      atomicAdd(&sumsq[c], tq);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_bn_apply_nctv(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
+                    const double *__restrict__ sum, const double *__restrict__ sumsq, float *__restrict__ y,
+                    int N, int C, int T, int V, int mode, double inv_count, float eps) {
+  const long long plane = (long long)T * V;
+  const long long total = (long long)N * C * plane;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    const int c = (int)((i / plane) % C);
+    const int f = mode == 1 ? v * C + c : c;
+    double mean = sum[f] * inv_count;
+    double var = sumsq[f] * inv_count - mean * mean;
+    if (var < 0) var = 0;
+    y[i] = (float)(((double)x[i] - mean) / sqrt(var + (double)eps)) * w[f] + b[f];
+  }
+}
+
+__global__ void k_advance_counters(int *counter, int first, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) counter[first + i] += 1;
+}
+
+// --------------------------------------------------------------------------- //
+// batch-statistics BatchNorm (two phase).  x is [rows, C]; sums are double.
+// --------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(256)
+    k_channel_stats(const float *__restrict__ x, long long rows, int C, long long rows_per_block,
+                    double *__restrict__ sum, double *__restrict__ sumsq) {
+  __shared__ double s_s[256], s_q[256];
+  const int cpt = C < 256 ? C : 256;
+  const int rsplit = 256 / cpt;
+  const int c0 = threadIdx.x % cpt, rs = threadIdx.x / cpt;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (int cg = 0; cg < C; cg += cpt) {
+    const int c = cg + c0;
+    double s = 0.0, q = 0.0;
+    if (rs < rsplit && c < C) {
+      for (long long r = r0 + rs; r < r1; r += rsplit) {
+        float v = x[r * C + c];
+        s += v;
+        q += (double)v * v;
+      }
+    }
+    s_s[threadIdx.x] = s;
+    s_q[threadIdx.x] = q;
+    __syncthreads();
+    if (rs == 0 && c < C) {
+      for (int k = 1; k < rsplit; ++k) {
+        s += s_s[k * cpt + c0];
+        q += s_q[k * cpt + c0];
+      }
+      atomicAdd(&sum[c], s);
+      atomicAdd(&sumsq[c], q);
+    }
+    __syncthreads();
+  }
+}
+
+// out = relu_out( bn_a(a) [relu_mid] + [ b | bn_b(b) ] ), per-channel batch statistics.
+struct BnApplyArgs {
+  const float *a;
+  const double *a_sum, *a_sumsq;
+  const float *a_w, *a_b;
+  int relu_mid;
+  int b_mode;  // B_NONE / B_RAW / B_LN (here: BN of b)
+  const float *b;
+  const double *b_sum, *b_sumsq;
+  const float *b_w, *b_b;
+  int relu_out;
+  long long rows;
+  int C;
+  double inv_count;
+  float eps;
+  float *out;
+};
+
+__global__ void __launch_bounds__(256) k_bn_apply(BnApplyArgs p) {
+  const long long total = p.rows * p.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % p.C);
+    double mean = p.a_sum[c] * p.inv_count;
+    double var = p.a_sumsq[c] * p.inv_count - mean * mean;
+    if (var < 0) var = 0;
+    float v = (float)(((double)p.a[i] - mean) / sqrt(var + (double)p.eps)) * p.a_w[c] + p.a_b[c];
+    if (p.relu_mid) v = fmaxf(v, 0.f);
+    if (p.b_mode == B_RAW) {
+      v += p.b[i];
+    } else if (p.b_mode == B_LN) {
+      double mb = p.b_sum[c] * p.inv_count;
+      double vb = p.b_sumsq[c] * p.inv_count - mb * mb;
+      if (vb < 0) vb = 0;
+      v += (float)(((double)p.b[i] - mb) / sqrt(vb + (double)p.eps)) * p.b_w[c] + p.b_b[c];
+    }
+    if (p.relu_out) v = fmaxf(v, 0.f);
+    p.out[i] = v;
+  }
+}
+
+// --------------------------------------------------------------------------- //
+// input stage: norm_in + fcn_in (stgcn.py:82-85).  x is [frames, V, C_in] (NTVC).
+//   LN mode: per-frame LayerNorm over (C_in, V), affine (C_in, V)
+//   BN mode: per-feature (v*C_in + c) batch statistics, precomputed sums
+// out[frame, v, co] = b[co] + sum_c W[co][c] * xn[v][c]
+// --------------------------------------------------------------------------- //
+struct EmbedArgs {
+  const float *x;
+  long long frames;
+  int V, C_in, C0;
+  int norm;  // STGCN_NORM_*
+  const float *n_w, *n_b;
+  const double *bn_sum, *bn_sumsq;
+  double bn_inv_count;
+  float eps;
+  const float *W, *bias;
+  float *out;
+};
+
+__global__ void __launch_bounds__(256) k_embed(EmbedArgs p) {
+  extern __shared__ __align__(16) float s_buf[];
+  __shared__ float s_red[32];
+  const int VCi = p.V * p.C_in;
+  float *xn = s_buf;                  // V*C_in
+  float *sw = s_buf + VCi;            // C0*C_in
+  float *sb = sw + p.C0 * p.C_in;     // C0
+  float *sc = sb + p.C0;              // BN: scale[V*C_in], shift[V*C_in]
+  for (int i = threadIdx.x; i < p.C0 * p.C_in; i += blockDim.x) sw[i] = p.W[i];
+  for (int i = threadIdx.x; i < p.C0; i += blockDim.x) sb[i] = p.bias[i];
+  if (p.norm == 1) {
+    for (int i = threadIdx.x; i < VCi; i += blockDim.x) {
+      double mean = p.bn_sum[i] * p.bn_inv_count;
+      double var = p.bn_sumsq[i] * p.bn_inv_count - mean * mean;
+      if (var < 0) var = 0;
+      double rstd = 1.0 / sqrt(var + (double)p.eps);
+      sc[i] = (float)rstd * p.n_w[i];
+      sc[VCi + i] = p.n_b[i] - (float)(mean * rstd) * p.n_w[i];
+    }
+  }
+  __syncthreads();
+  const float inv_n = 1.f / (float)VCi, inv_nm1 = 1.f / (float)(VCi - 1);
+  for (long long f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    const float *src = p.x + f * VCi;
+    for (int i = threadIdx.x; i < VCi; i += blockDim.x) xn[i] = src[i];
+    __syncthreads();
+    if (p.norm == 0) {
+      float s = 0.f;
+      for (int i = threadIdx.x; i < VCi; i += blockDim.x) s += xn[i];
+      float mean = block_sum(s, s_red) * inv_n;
+      float q = 0.f;
+      for (int i = threadIdx.x; i < VCi; i += blockDim.x) {
+        float d = xn[i] - mean;
+        q = fmaf(d, d, q);
+      }
+      float rstd = 1.f / sqrtf(block_sum(q, s_red) * inv_nm1 + p.eps);
+      for (int i = threadIdx.x; i < VCi; i += blockDim.x) {
+        int v = i / p.C_in, c = i - v * p.C_in;
+        int pi = c * p.V + v;
+        xn[i] = (xn[i] - mean) * rstd * p.n_w[pi] + p.n_b[pi];
+      }
+    } else {
+      for (int i = threadIdx.x; i < VCi; i += blockDim.x) xn[i] = xn[i] * sc[i] + sc[VCi + i];
+    }
+    __syncthreads();
+    float *dst = p.out + f * (long long)p.V * p.C0;
+    for (int i = threadIdx.x; i < p.V * p.C0; i += blockDim.x) {
+      int v = i / p.C0, co = i - v * p.C0;
+      float acc = sb[co];
+      for (int c = 0; c < p.C_in; ++c) acc = fmaf(sw[co * p.C_in + c], xn[v * p.C_in + c], acc);
+      dst[i] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------- //
+// pooling + classifier (stgcn.py:92-95, rtstgcn.py:149-152)
+//   part[n][chunk][c] = sum over the chunk's rows;  logits = Wo * mean + bo
+// --------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(256)
+    k_pool_partial(const float *__restrict__ x, long long R, int C, int rows_per_chunk, int nchunk,
+                   float *__restrict__ part) {
+  const long long n = blockIdx.y;
+  const int ch = blockIdx.x;
+  long long r0 = (long long)ch * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > R) r1 = R;
+  const float *xs = x + n * R * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += xs[r * C + c];
+    part[(n * nchunk + ch) * C + c] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_pool_fc(const float *__restrict__ part, int nchunk, int C, float inv_R, const float *__restrict__ W,
+              const float *__restrict__ bias, int classes, float *__restrict__ logits) {
+  extern __shared__ float s_pool[];  // C
+  const long long n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nchunk; ++k) s += part[(n * nchunk + k) * C + c];
+    s_pool[c] = s * inv_R;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int m = warp; m < classes; m += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(W[(long long)m * C + c], s_pool[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) logits[n * classes + m] = s + bias[m];
+  }
+}
+
+}  // namespace stgcn

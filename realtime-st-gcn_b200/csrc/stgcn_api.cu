@@ -1,0 +1,759 @@
+// C ABI of the B200-native ST-GCN / RT-ST-GCN forward path (see include/stgcn_b200.h).
+#include "../../include/stgcn_b200.h"
+
+#include "common.cuh"
+#include "kernels_simt.cuh"
+
+using namespace stgcn;
+
+namespace {
+
+constexpr float kEps = 1e-5f;  // reference LayerNorm / BatchNorm eps (layernorm.py:8)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int round4(int x) { return (x + 3) & ~3; }
+
+// ---- launch helpers ---------------------------------------------------------
+int to_ntvc(const float *x, float *y, int N, int C, long long P, int ld, cudaStream_t st) {
+  dim3 grid(cdiv(P, 32), cdiv(ld, 32), N), block(32, 8);
+  ProfScope ps(KC_LAYOUT, st);
+  k_cp_to_pc<<<grid, block, 0, st>>>(x, y, C, P, ld);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+int to_nctv(const float *x, float *y, int N, int C, long long P, int ld, cudaStream_t st) {
+  dim3 grid(cdiv(P, 32), cdiv(C, 32), N), block(32, 8);
+  ProfScope ps(KC_LAYOUT, st);
+  k_pc_to_cp<<<grid, block, 0, st>>>(x, y, C, P, ld);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+// Y[M, C_out] = conv over taps of X (NTVC), weights packed (C_out, G, C_in)
+int launch_gemm(const float *X, const float *Wp, const float *bias, float *Y, int N, int T_in, int V,
+                int C_in, int C_out, int G, int stride, cudaStream_t st) {
+  STGCN_REQUIRE(C_in % 4 == 0 && C_out % 4 == 0, "gemm: channels must be multiples of 4 (got %d -> %d)",
+                C_in, C_out);
+  ConvGeom g;
+  g.T_in = T_in;
+  g.T_out = (T_in - 1) / stride + 1;
+  g.V = V;
+  g.C_in = C_in;
+  g.C_out = C_out;
+  g.G = G;
+  g.stride = stride;
+  g.pad = (G - 1) / 2;
+  g.Ktot = G * C_in;
+  long long M = (long long)N * g.T_out * V;
+  STGCN_REQUIRE(M < (1ll << 31) - 256, "gemm: too many rows (%lld)", M);
+  g.M = (int)M;
+  dim3 grid(cdiv(M, 128), cdiv(C_out, 64));
+  ProfScope ps(G > 1 ? KC_GEMM_TCN : KC_GEMM_1X1, st);
+  k_gemm_conv<128, 64, 16><<<grid, 256, 0, st>>>(X, Wp, bias, Y, g);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+int launch_frame(const FrameArgs &a, cudaStream_t st) {
+  size_t smem = (size_t)a.V * a.C * sizeof(float) * (a.b_mode == B_LN ? 2 : 1);
+  STGCN_REQUIRE(smem <= 200 * 1024, "frame kernel: V*C too large for shared memory (%zu B)", smem);
+  if (smem > 48 * 1024)
+    STGCN_CUDA_OK(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = a.frames < 148 * 8 ? a.frames : 148 * 8;
+  ProfScope ps(KC_FRAME, st);
+  k_frame<<<(unsigned)blocks, 256, smem, st>>>(a);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+struct AdjCsr {
+  int *ptr;
+  int *yoff;
+  float *val;
+};
+
+int build_csr(const float *A, int a_per_sample, int N, int K, int V, int C, Bump &ws, AdjCsr &csr,
+              cudaStream_t st) {
+  const int nA = a_per_sample ? N : 1;
+  csr.ptr = ws.take<int>((size_t)nA * (V + 1));
+  csr.yoff = ws.take<int>((size_t)nA * K * V * V);
+  csr.val = ws.take<float>((size_t)nA * K * V * V);
+  if (ws.measuring()) return 0;
+  STGCN_REQUIRE(!ws.overflow, "workspace too small (adjacency)");
+  STGCN_REQUIRE(V <= 1024, "too many joints (%d)", V);
+  ProfScope ps(KC_MISC, st);
+  k_build_adj_csr<<<nA, 64, (V + 1) * sizeof(int), st>>>(A, K, V, C, csr.ptr, csr.yoff, csr.val);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+int channel_stats(const float *x, long long rows, int C, double *sums /* [2*C] */, cudaStream_t st) {
+  STGCN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  long long rpb = 1024;
+  long long blocks = (rows + rpb - 1) / rpb;
+  if (blocks > 148 * 16) {
+    blocks = 148 * 16;
+    rpb = (rows + blocks - 1) / blocks;
+    blocks = (rows + rpb - 1) / rpb;
+  }
+  ProfScope ps(KC_BN, st);
+  k_channel_stats<<<(unsigned)blocks, 256, 0, st>>>(x, rows, C, rpb, sums, sums + C);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+int check_layer(const stgcn_layer_desc &d) {
+  STGCN_REQUIRE(d.kernel % 2 == 1, "temporal kernel must be odd (got %d)", d.kernel);
+  STGCN_REQUIRE(d.stride >= 1, "stride must be >= 1");
+  STGCN_REQUIRE(d.c_in % 4 == 0 && d.c_out % 4 == 0,
+                "layer channels must be multiples of 4 (got %d -> %d)", d.c_in, d.c_out);
+  STGCN_REQUIRE(d.residual != STGCN_RES_IDENTITY || (d.c_in == d.c_out && (d.stride == 1 || d.rt)),
+                "identity residual needs c_in == c_out and stride 1");
+  return 0;
+}
+
+// ---- ST-GCN layer on channels-last activations --------------------------------
+// x [N*T*V, c_in] -> out [N*T_out*V, c_out].  Scratch comes from `ws` (released on return).
+int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
+                       int N, int T, Bump &ws, cudaStream_t st) {
+  (void)math;
+  if (check_layer(d)) return 1;
+  const size_t mark = ws.mark();
+  const int T_out = (T - 1) / d.stride + 1;
+  const long long rows = (long long)N * T * V, rows_out = (long long)N * T_out * V;
+  const bool bn = d.norm == STGCN_NORM_BATCHNORM;
+
+  AdjCsr csr;
+  if (build_csr(d.a_eff, d.a_per_sample, N, K, V, d.c_out, ws, csr, st)) return 1;
+  float *u = ws.take<float>((size_t)rows * d.c_out);
+  double *sums = bn ? ws.take<double>((size_t)4 * d.c_out) : nullptr;
+  {
+    const size_t m2 = ws.mark();
+    float *y = ws.take<float>((size_t)rows * K * d.c_out);
+    float *z = bn ? ws.take<float>((size_t)rows * d.c_out) : nullptr;
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
+      if (launch_gemm(x, d.gcn_w, d.gcn_b, y, N, T, V, d.c_in, K * d.c_out, 1, 1, st)) return 1;
+      FrameArgs a{};
+      a.producer = FRAME_ADJ;
+      a.frames = (long long)N * T;
+      a.frames_per_sample = T;
+      a.K = K; a.V = V; a.C = d.c_out;
+      a.y = y;
+      a.adj_ptr = csr.ptr; a.adj_yoff = csr.yoff; a.adj_val = csr.val;
+      a.adj_per_sample = d.a_per_sample;
+      a.eps = kEps;
+      if (!bn) {
+        a.norm_a = 1; a.na_w = d.n1_w; a.na_b = d.n1_b; a.relu_out = 1; a.out = u;
+        if (launch_frame(a, st)) return 1;
+      } else {
+        a.out = z;
+        if (launch_frame(a, st)) return 1;
+        if (channel_stats(z, rows, d.c_out, sums, st)) return 1;
+        BnApplyArgs b{};
+        b.a = z; b.a_sum = sums; b.a_sumsq = sums + d.c_out; b.a_w = d.n1_w; b.a_b = d.n1_b;
+        b.relu_out = 1; b.rows = rows; b.C = d.c_out; b.inv_count = 1.0 / (double)rows; b.eps = kEps;
+        b.out = u;
+        ProfScope ps(KC_BN, st);
+        k_bn_apply<<<148 * 8, 256, 0, st>>>(b);
+        STGCN_LAUNCH_OK();
+      }
+    }
+    ws.release(m2);
+  }
+  float *wp = ws.take<float>((size_t)d.c_out * d.c_out * d.kernel);
+  float *q = ws.take<float>((size_t)rows_out * d.c_out);
+  float *qr = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
+  if (!ws.measuring()) {
+    STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
+    long long nw = (long long)d.c_out * d.c_out * d.kernel;
+    {
+      ProfScope ps(KC_MISC, st);
+      k_pack_tcn_w<<<cdiv(nw, 256), 256, 0, st>>>(d.tcn_w, wp, d.c_out, d.c_out, d.kernel, d.c_out, d.c_out);
+      STGCN_LAUNCH_OK();
+    }
+    if (launch_gemm(u, wp, d.tcn_b, q, N, T, V, d.c_out, d.c_out, d.kernel, d.stride, st)) return 1;
+    if (qr && launch_gemm(x, d.res_w, d.res_b, qr, N, T, V, d.c_in, d.c_out, 1, d.stride, st)) return 1;
+    if (!bn) {
+      FrameArgs a{};
+      a.producer = FRAME_LOAD;
+      a.frames = (long long)N * T_out;
+      a.frames_per_sample = T_out;
+      a.K = K; a.V = V; a.C = d.c_out;
+      a.a = q;
+      a.norm_a = 1; a.na_w = d.n2_w; a.na_b = d.n2_b;
+      a.eps = kEps;
+      if (d.residual == STGCN_RES_IDENTITY) { a.b_mode = B_RAW; a.b = x; }
+      else if (d.residual == STGCN_RES_CONV) { a.b_mode = B_LN; a.b = qr; a.nb_w = d.nr_w; a.nb_b = d.nr_b; }
+      a.relu_out = 1;
+      a.out = out;
+      if (launch_frame(a, st)) return 1;
+    } else {
+      if (channel_stats(q, rows_out, d.c_out, sums, st)) return 1;
+      BnApplyArgs b{};
+      b.a = q; b.a_sum = sums; b.a_sumsq = sums + d.c_out; b.a_w = d.n2_w; b.a_b = d.n2_b;
+      if (d.residual == STGCN_RES_IDENTITY) { b.b_mode = B_RAW; b.b = x; }
+      else if (d.residual == STGCN_RES_CONV) {
+        if (channel_stats(qr, rows_out, d.c_out, sums + 2 * d.c_out, st)) return 1;
+        b.b_mode = B_LN; b.b = qr; b.b_sum = sums + 2 * d.c_out; b.b_sumsq = sums + 3 * d.c_out;
+        b.b_w = d.nr_w; b.b_b = d.nr_b;
+      }
+      b.relu_out = 1; b.rows = rows_out; b.C = d.c_out; b.inv_count = 1.0 / (double)rows_out; b.eps = kEps;
+      b.out = out;
+      ProfScope ps(KC_BN, st);
+      k_bn_apply<<<148 * 8, 256, 0, st>>>(b);
+      STGCN_LAUNCH_OK();
+    }
+  }
+  ws.release(mark);
+  return 0;
+}
+
+// ---- RT online layer on channels-last frames -----------------------------------
+// x [B*V, c_in] -> out [B*V, c_out]; fifo [F][B][V][C], acc [S][B][V][C]; counter[B].
+int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
+                       float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st) {
+  (void)math;
+  if (check_layer(d)) return 1;
+  STGCN_REQUIRE(d.norm == STGCN_NORM_LAYERNORM,
+                "continual inference needs LayerNorm: batch statistics of a single frame are undefined "
+                "(reference raises at models/utils/batchnorm.py:20)");
+  const size_t mark = ws.mark();
+  AdjCsr csr;
+  if (build_csr(d.a_eff, 0, B, K, V, d.c_out, ws, csr, st)) return 1;
+  const long long rows = (long long)B * V;
+  float *y = ws.take<float>((size_t)rows * K * d.c_out);
+  float *qr = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows * d.c_out) : nullptr;
+  if (!ws.measuring()) {
+    STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer)");
+    if (launch_gemm(x, d.gcn_w, d.gcn_b, y, B, 1, V, d.c_in, K * d.c_out, 1, 1, st)) return 1;
+    // residual conv of the online layer has no bias and no stride (rtstgcn.py:503)
+    if (qr && launch_gemm(x, d.res_w, nullptr, qr, B, 1, V, d.c_in, d.c_out, 1, 1, st)) return 1;
+    FrameArgs a{};
+    a.producer = FRAME_RT;
+    a.frames = B;
+    a.frames_per_sample = 1;
+    a.K = K; a.V = V; a.C = d.c_out;
+    a.y = y;
+    a.adj_ptr = csr.ptr; a.adj_yoff = csr.yoff; a.adj_val = csr.val;
+    a.norm_a = 1; a.na_w = d.n1_w; a.na_b = d.n1_b;
+    a.relu_mid = 1;
+    if (d.residual == STGCN_RES_IDENTITY) { a.b_mode = B_RAW; a.b = x; }
+    else if (d.residual == STGCN_RES_CONV) { a.b_mode = B_LN; a.b = qr; a.nb_w = d.nr_w; a.nb_b = d.nr_b; }
+    a.relu_out = 1;
+    a.eps = kEps;
+    a.out = out;
+    a.fifo = fifo; a.acc = acc; a.counter = counter;
+    a.F = d.stride * (d.kernel - 1) + 1;
+    a.S = d.stride;
+    if (launch_frame(a, st)) return 1;
+  }
+  ws.release(mark);
+  return 0;
+}
+
+int pool_fc(const float *x, int N, long long R, int C, const float *W, const float *bias, int classes,
+            float *logits, Bump &ws, cudaStream_t st) {
+  const int rpc = 512;
+  const int nchunk = cdiv(R, rpc);
+  float *part = ws.take<float>((size_t)N * nchunk * C);
+  if (ws.measuring()) return 0;
+  STGCN_REQUIRE(!ws.overflow, "workspace too small (pool)");
+  ProfScope ps(KC_POOL, st);
+  k_pool_partial<<<dim3(nchunk, N), 256, 0, st>>>(x, R, C, rpc, nchunk, part);
+  STGCN_LAUNCH_OK();
+  k_pool_fc<<<N, 256, C * sizeof(float), st>>>(part, nchunk, C, 1.f / (float)R, W, bias, classes, logits);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+// input stage: x (N,C_in,T,V) -> h0 [N*T*V, C0]
+int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bump &ws, cudaStream_t st) {
+  const int V = m.num_joints, Ci = m.in_feat, C0 = m.layers[0].c_in;
+  const long long frames = (long long)N * T;
+  const size_t mark = ws.mark();
+  float *xin = ws.take<float>((size_t)frames * V * Ci);
+  double *sums = m.norm == STGCN_NORM_BATCHNORM ? ws.take<double>((size_t)2 * V * Ci) : nullptr;
+  if (!ws.measuring()) {
+    STGCN_REQUIRE(!ws.overflow, "workspace too small (embed)");
+    if (to_ntvc(x, xin, N, Ci, (long long)T * V, Ci, st)) return 1;
+    EmbedArgs e{};
+    e.x = xin; e.frames = frames; e.V = V; e.C_in = Ci; e.C0 = C0; e.norm = m.norm;
+    e.n_w = m.norm_in_w; e.n_b = m.norm_in_b; e.eps = kEps;
+    e.W = m.fcn_in_w; e.bias = m.fcn_in_b; e.out = h0;
+    if (m.norm == STGCN_NORM_BATCHNORM) {
+      if (channel_stats(xin, frames, V * Ci, sums, st)) return 1;
+      e.bn_sum = sums; e.bn_sumsq = sums + V * Ci; e.bn_inv_count = 1.0 / (double)frames;
+    }
+    size_t smem = sizeof(float) * ((size_t)3 * V * Ci + (size_t)C0 * Ci + C0);
+    STGCN_REQUIRE(smem <= 160 * 1024, "embed: input feature map too large");
+    if (smem > 48 * 1024)
+      STGCN_CUDA_OK(cudaFuncSetAttribute(k_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = frames < 148 * 8 ? frames : 148 * 8;
+    ProfScope ps(KC_EMBED, st);
+    k_embed<<<(unsigned)blocks, 256, smem, st>>>(e);
+    STGCN_LAUNCH_OK();
+  }
+  ws.release(mark);
+  return 0;
+}
+
+int check_model(const stgcn_model_desc *m) {
+  STGCN_REQUIRE(m && m->layers && m->num_layers > 0, "model descriptor is empty");
+  STGCN_REQUIRE(m->in_feat > 0 && m->num_joints > 1 && m->partitions > 0 && m->num_classes > 0,
+                "bad model dimensions");
+  for (int i = 0; i + 1 < m->num_layers; ++i)
+    STGCN_REQUIRE(m->layers[i].c_out == m->layers[i + 1].c_in, "layer %d/%d channel mismatch", i, i + 1);
+  return 0;
+}
+
+// ST-GCN model on `n` trials (one chunk).  logits [n, classes]; features optional (NCTV).
+int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float *features, int n, int T,
+                Bump &ws, cudaStream_t st) {
+  const int V = m.num_joints, K = m.partitions;
+  // ping-pong activation buffers sized for the largest layer interface
+  size_t max_act = (size_t)n * T * V * m.layers[0].c_in;
+  int t = T;
+  for (int i = 0; i < m.num_layers; ++i) {
+    t = (t - 1) / m.layers[i].stride + 1;
+    size_t a = (size_t)n * t * V * m.layers[i].c_out;
+    if (a > max_act) max_act = a;
+  }
+  float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
+  if (embed(m, x, buf[0], n, T, ws, st)) return 1;
+  int cur = 0;
+  t = T;
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    STGCN_REQUIRE(!d.rt, "stgcn_model_forward needs ST-GCN layers (rt == 0)");
+    STGCN_REQUIRE(!d.a_per_sample, "per-sample adjacency is only supported by the layer-level API");
+    if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st)) return 1;
+    t = (t - 1) / d.stride + 1;
+    cur ^= 1;
+  }
+  const int c_last = m.layers[m.num_layers - 1].c_out;
+  if (features && !ws.measuring())
+    if (to_nctv(buf[cur], features, n, c_last, (long long)t * V, c_last, st)) return 1;
+  if (pool_fc(buf[cur], n, (long long)t * V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, ws, st))
+    return 1;
+  return 0;
+}
+
+size_t model_chunk_bytes(const stgcn_model_desc &m, int n, int T) {
+  Bump ws(nullptr, 0);
+  model_chunk(m, nullptr, nullptr, nullptr, n, T, ws, nullptr);
+  return ws.peak;
+}
+
+// rows (trial-frames * V) one chunk of trials should carry when chunking is allowed
+constexpr long long kChunkRows = 3200000;
+
+int default_chunk(const stgcn_model_desc &m, int N, int T) {
+  if (m.norm == STGCN_NORM_BATCHNORM) return N;  // batch statistics span the whole call
+  long long per_trial = (long long)T * m.num_joints;
+  long long n = kChunkRows / (per_trial > 0 ? per_trial : 1);
+  if (n < 1) n = 1;
+  if (n > N) n = N;
+  return (int)n;
+}
+
+// ---- RT state layout ------------------------------------------------------------
+struct RtLayout {
+  size_t counters;  // offset of int32[B]
+  size_t fifo[64], acc[64];
+  size_t total;
+};
+int rt_layout(const stgcn_model_desc &m, int B, RtLayout &L) {
+  STGCN_REQUIRE(m.num_layers <= 64, "too many layers");
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off += (bytes + 255) & ~size_t(255);
+    return at;
+  };
+  L.counters = take(sizeof(int32_t) * (size_t)B);
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    size_t slot = (size_t)B * m.num_joints * d.c_out * sizeof(float);
+    L.fifo[i] = take(slot * (size_t)(d.stride * (d.kernel - 1) + 1));
+    L.acc[i] = take(slot * (size_t)d.stride);
+  }
+  L.total = off;
+  return 0;
+}
+
+int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logits, int B, Bump &ws,
+            cudaStream_t st) {
+  const int V = m.num_joints, K = m.partitions;
+  STGCN_REQUIRE(m.norm == STGCN_NORM_LAYERNORM,
+                "continual inference needs LayerNorm (reference raises at models/utils/batchnorm.py:20)");
+  RtLayout L;
+  if (rt_layout(m, B, L)) return 1;
+  size_t max_act = (size_t)B * V * m.layers[0].c_in;
+  for (int i = 0; i < m.num_layers; ++i) {
+    size_t a = (size_t)B * V * m.layers[i].c_out;
+    if (a > max_act) max_act = a;
+  }
+  float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
+  if (embed(m, x, buf[0], B, 1, ws, st)) return 1;
+  char *sb = static_cast<char *>(state);
+  int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters);
+  int cur = 0;
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    STGCN_REQUIRE(d.rt, "rtstgcn_step needs online layers (rt == 1)");
+    float *fifo = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.fifo[i]);
+    float *acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]);
+    if (rt_layer_step_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], fifo, acc, counter, B, ws, st)) return 1;
+    cur ^= 1;
+  }
+  const int c_last = m.layers[m.num_layers - 1].c_out;
+  if (pool_fc(buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, ws, st)) return 1;
+  if (!ws.measuring()) {
+    k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(counter, 0, B);
+    STGCN_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================
+// exported C ABI
+// =============================================================================
+extern "C" {
+
+int stgcn_abi_version(void) { return STGCN_ABI_VERSION; }
+const char *stgcn_last_error(void) { return err_buf(); }
+
+long long stgcn_launch_count(void) { return prof().launches.load(); }
+
+int stgcn_profile_begin(void) {
+  Profiler &p = prof();
+  p.n = 0;
+  for (int i = 0; i < KC_COUNT; ++i) {
+    p.ms[i] = 0.f;
+    p.count[i] = 0;
+  }
+  p.on = true;
+  return 0;
+}
+
+int stgcn_profile_end(float *ms_per_class, long long *launches_per_class, int n_classes) {
+  Profiler &p = prof();
+  p.on = false;
+  STGCN_CUDA_OK(cudaDeviceSynchronize());
+  for (int i = 0; i < p.n; ++i) {
+    float ms = 0.f;
+    STGCN_CUDA_OK(cudaEventElapsedTime(&ms, p.ev[i][0], p.ev[i][1]));
+    p.ms[p.cls[i]] += ms;
+    p.count[p.cls[i]] += 1;
+  }
+  for (int i = 0; i < n_classes && i < KC_COUNT; ++i) {
+    if (ms_per_class) ms_per_class[i] = p.ms[i];
+    if (launches_per_class) launches_per_class[i] = p.count[i];
+  }
+  p.n = 0;
+  return 0;
+}
+
+int stgcn_device_check(int device) {
+  cudaDeviceProp prop;
+  STGCN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  STGCN_REQUIRE(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  return 0;
+}
+
+// ---- LayerNorm (layernorm.py:22-28) ----------------------------------------
+int stgcn_layernorm_forward(const float *x, const float *w, const float *b, float *y, int N, int C, int T,
+                            int V, float eps, void *stream) {
+  // Stand-alone module call in the reference layout: frames are gathered with stride T*V.
+  STGCN_REQUIRE(N > 0 && C > 0 && T > 0 && V > 0 && (long long)C * V > 1, "layernorm: bad shape");
+  size_t smem = (size_t)C * V * sizeof(float);
+  STGCN_REQUIRE(smem <= 200 * 1024, "layernorm: C*V too large");
+  if (smem > 48 * 1024)
+    STGCN_CUDA_OK(cudaFuncSetAttribute(k_layernorm_nctv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long frames = (long long)N * T;
+  long long blocks = frames < 148 * 8 ? frames : 148 * 8;
+  k_layernorm_nctv<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(x, w, b, y, N, C, T, V, eps);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+// ---- BatchNorm (batchnorm.py:13-23, stgcn.py:152) ---------------------------
+size_t stgcn_batchnorm_workspace_bytes(int C, int V, int mode) {
+  size_t feats = mode == 1 ? (size_t)C * V : (size_t)C;
+  return ((sizeof(double) * 2 * feats) + 255) & ~size_t(255);
+}
+
+int stgcn_batchnorm_forward(const float *x, const float *w, const float *b, float *y, int N, int C, int T,
+                            int V, float eps, int mode, void *workspace, size_t workspace_bytes,
+                            void *stream) {
+  STGCN_REQUIRE(workspace && workspace_bytes >= stgcn_batchnorm_workspace_bytes(C, V, mode),
+                "batchnorm: workspace too small");
+  STGCN_REQUIRE(mode == 0 || mode == 1, "batchnorm: mode must be 0 or 1");
+  STGCN_REQUIRE((long long)N * T * (mode == 0 ? V : 1) > 1,
+                "Expected more than 1 value per channel when computing batch statistics");
+  const int feats = mode == 1 ? C * V : C;
+  double *sums = static_cast<double *>(workspace);
+  cudaStream_t st = as_stream(stream);
+  STGCN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * feats, st));
+  int tchunks = cdiv((long long)T * V, 4096);
+  k_bn_stats_nctv<<<dim3(tchunks, C, N), 256, sizeof(double) * 2 * V, st>>>(x, C, T, V, mode, 4096, sums,
+                                                                        sums + feats);
+  STGCN_LAUNCH_OK();
+  double inv = 1.0 / ((double)N * T * (mode == 0 ? V : 1));
+  k_bn_apply_nctv<<<148 * 8, 256, 0, st>>>(x, w, b, sums, sums + feats, y, N, C, T, V, mode, inv, eps);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+// ---- temporal / pointwise convolution ----------------------------------------
+size_t stgcn_conv_workspace_bytes(int N, int c_in, int c_out, int T, int V, int kernel, int stride) {
+  const int ci = round4(c_in), co = round4(c_out);
+  const int T_out = (T - 1) / stride + 1;
+  Bump ws(nullptr, 0);
+  ws.take<float>((size_t)N * T * V * ci);
+  ws.take<float>((size_t)N * T_out * V * co);
+  ws.take<float>((size_t)co * kernel * ci);
+  ws.take<float>((size_t)co);
+  return ws.peak;
+}
+
+int stgcn_conv_forward(const float *x, const float *w, const float *bias, float *y, int N, int c_in,
+                       int c_out, int T, int V, int kernel, int stride, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  STGCN_REQUIRE(kernel % 2 == 1 && stride >= 1, "conv: kernel must be odd, stride >= 1");
+  const int ci = round4(c_in), co = round4(c_out);
+  const int T_out = (T - 1) / stride + 1;
+  cudaStream_t st = as_stream(stream);
+  Bump ws(workspace, workspace_bytes);
+  float *xin = ws.take<float>((size_t)N * T * V * ci);
+  float *yo = ws.take<float>((size_t)N * T_out * V * co);
+  float *wp = ws.take<float>((size_t)co * kernel * ci);
+  float *bp = ws.take<float>((size_t)co);
+  STGCN_REQUIRE(workspace && !ws.overflow, "conv: workspace too small");
+  if (to_ntvc(x, xin, N, c_in, (long long)T * V, ci, st)) return 1;
+  long long nw = (long long)co * kernel * ci;
+  k_pack_tcn_w<<<cdiv(nw, 256), 256, 0, st>>>(w, wp, c_out, c_in, kernel, co, ci);
+  STGCN_LAUNCH_OK();
+  if (bias) {
+    k_pad_vec<<<cdiv(co, 256), 256, 0, st>>>(bias, bp, c_out, co);
+    STGCN_LAUNCH_OK();
+  }
+  if (launch_gemm(xin, wp, bias ? bp : nullptr, yo, N, T, V, ci, co, kernel, stride, st)) return 1;
+  return to_nctv(yo, y, N, c_out, (long long)T_out * V, co, st);
+}
+
+// ---- graph convolution (tgcn.py:58-79) -----------------------------------------
+size_t stgcn_graphconv_workspace_bytes(int N, int c_in, int c_out, int K, int T, int V) {
+  Bump ws(nullptr, 0);
+  ws.take<float>((size_t)N * T * V * c_in);
+  ws.take<float>((size_t)N * T * V * K * c_out);
+  ws.take<float>((size_t)N * T * V * c_out);
+  ws.take<int>((size_t)N * (V + 1));
+  ws.take<int>((size_t)N * K * V * V);
+  ws.take<float>((size_t)N * K * V * V);
+  return ws.peak;
+}
+
+int stgcn_graphconv_forward(const float *x, const float *w, const float *bias, const float *A,
+                            int a_per_sample, float *y, int N, int c_in, int c_out, int K, int T, int V,
+                            void *workspace, size_t workspace_bytes, void *stream) {
+  cudaStream_t st = as_stream(stream);
+  Bump ws(workspace, workspace_bytes);
+  float *xin = ws.take<float>((size_t)N * T * V * c_in);
+  float *yy = ws.take<float>((size_t)N * T * V * K * c_out);
+  float *z = ws.take<float>((size_t)N * T * V * c_out);
+  STGCN_REQUIRE(workspace && !ws.overflow, "graphconv: workspace too small");
+  AdjCsr csr;
+  if (build_csr(A, a_per_sample, N, K, V, c_out, ws, csr, st)) return 1;
+  if (to_ntvc(x, xin, N, c_in, (long long)T * V, c_in, st)) return 1;
+  if (launch_gemm(xin, w, bias, yy, N, T, V, c_in, K * c_out, 1, 1, st)) return 1;
+  FrameArgs a{};
+  a.producer = FRAME_ADJ;
+  a.frames = (long long)N * T;
+  a.frames_per_sample = T;
+  a.K = K; a.V = V; a.C = c_out;
+  a.y = yy;
+  a.adj_ptr = csr.ptr; a.adj_yoff = csr.yoff; a.adj_val = csr.val;
+  a.adj_per_sample = a_per_sample;
+  a.eps = kEps;
+  a.out = z;
+  if (launch_frame(a, st)) return 1;
+  return to_nctv(z, y, N, c_out, (long long)T * V, c_out, st);
+}
+
+// ---- ST-GCN layer (stgcn.py:181-193) --------------------------------------------
+size_t stgcn_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int N, int T) {
+  if (!d) return 0;
+  Bump ws(nullptr, 0);
+  const int T_out = (T - 1) / d->stride + 1;
+  ws.take<float>((size_t)N * T * V * d->c_in);
+  ws.take<float>((size_t)N * T_out * V * d->c_out);
+  layer_forward_ntvc(*d, K, V, 0, nullptr, nullptr, N, T, ws, nullptr);
+  return ws.peak;
+}
+
+int stgcn_layer_forward(const stgcn_layer_desc *d, int K, int V, int math, const float *x, float *y, int N,
+                        int T, void *workspace, size_t workspace_bytes, void *stream) {
+  STGCN_REQUIRE(d && !d->rt, "stgcn_layer_forward: descriptor must describe an ST-GCN layer");
+  cudaStream_t st = as_stream(stream);
+  Bump ws(workspace, workspace_bytes);
+  const int T_out = (T - 1) / d->stride + 1;
+  float *xin = ws.take<float>((size_t)N * T * V * d->c_in);
+  float *out = ws.take<float>((size_t)N * T_out * V * d->c_out);
+  STGCN_REQUIRE(workspace && !ws.overflow, "layer: workspace too small");
+  if (to_ntvc(x, xin, N, d->c_in, (long long)T * V, d->c_in, st)) return 1;
+  if (layer_forward_ntvc(*d, K, V, math, xin, out, N, T, ws, st)) return 1;
+  return to_nctv(out, y, N, d->c_out, (long long)T_out * V, d->c_out, st);
+}
+
+// ---- ST-GCN model (stgcn.py:80-97) ------------------------------------------------
+size_t stgcn_model_workspace_bytes(const stgcn_model_desc *m, int N, int T) {
+  if (check_model(m)) return 0;
+  return model_chunk_bytes(*m, default_chunk(*m, N, T), T);
+}
+
+int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits, float *features, int N,
+                        int T, void *workspace, size_t workspace_bytes, void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(N > 0 && T > 0, "model: empty input");
+  cudaStream_t st = as_stream(stream);
+  // largest trial chunk the caller's workspace can hold (LayerNorm: trials are independent)
+  int nc = default_chunk(*m, N, T);
+  while (nc > 1 && model_chunk_bytes(*m, nc, T) > workspace_bytes) nc = (nc + 1) / 2;
+  STGCN_REQUIRE(workspace && model_chunk_bytes(*m, nc, T) <= workspace_bytes,
+                "model: workspace too small (%zu B given, %zu B needed for %d trial(s))", workspace_bytes,
+                model_chunk_bytes(*m, nc, T), nc);
+  STGCN_REQUIRE(m->norm != STGCN_NORM_BATCHNORM || nc == N,
+                "model: BatchNorm needs the whole batch resident; workspace too small");
+  const int V = m->num_joints;
+  int t_final = T;
+  for (int i = 0; i < m->num_layers; ++i) t_final = (t_final - 1) / m->layers[i].stride + 1;
+  const int c_last = m->layers[m->num_layers - 1].c_out;
+  for (int n0 = 0; n0 < N; n0 += nc) {
+    int n = N - n0 < nc ? N - n0 : nc;
+    Bump ws(workspace, workspace_bytes);
+    if (model_chunk(*m, x + (size_t)n0 * m->in_feat * T * V, logits + (size_t)n0 * m->num_classes,
+                    features ? features + (size_t)n0 * c_last * t_final * V : nullptr, n, T, ws, st))
+      return 1;
+  }
+  return 0;
+}
+
+// ---- RT-ST-GCN continual step (rtstgcn.py:137-157, 528-553, 591-627) ---------------
+size_t rtstgcn_state_bytes(const stgcn_model_desc *m, int B) {
+  RtLayout L;
+  if (check_model(m) || rt_layout(*m, B, L)) return 0;
+  return L.total;
+}
+
+int rtstgcn_state_reset(const stgcn_model_desc *m, void *state, int B, int first, int count, void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(state && first >= 0 && count >= 0 && first + count <= B, "state_reset: bad stream range");
+  RtLayout L;
+  if (rt_layout(*m, B, L)) return 1;
+  cudaStream_t st = as_stream(stream);
+  char *sb = static_cast<char *>(state);
+  if (first == 0 && count == B) {
+    STGCN_CUDA_OK(cudaMemsetAsync(sb, 0, L.total, st));
+    return 0;
+  }
+  STGCN_CUDA_OK(cudaMemsetAsync(sb + L.counters + sizeof(int32_t) * first, 0, sizeof(int32_t) * count, st));
+  for (int i = 0; i < m->num_layers; ++i) {
+    const stgcn_layer_desc &d = m->layers[i];
+    size_t per = (size_t)m->num_joints * d.c_out * sizeof(float);
+    int F = d.stride * (d.kernel - 1) + 1;
+    for (int f = 0; f < F; ++f)
+      STGCN_CUDA_OK(cudaMemsetAsync(sb + L.fifo[i] + ((size_t)f * B + first) * per, 0, per * count, st));
+    for (int s = 0; s < d.stride; ++s)
+      STGCN_CUDA_OK(cudaMemsetAsync(sb + L.acc[i] + ((size_t)s * B + first) * per, 0, per * count, st));
+  }
+  return 0;
+}
+
+size_t rtstgcn_step_workspace_bytes(const stgcn_model_desc *m, int B) {
+  if (check_model(m)) return 0;
+  Bump ws(nullptr, 0);
+  rt_step(*m, nullptr, nullptr, nullptr, B, ws, nullptr);
+  return ws.peak;
+}
+
+int rtstgcn_step(const stgcn_model_desc *m, const float *x, void *state, float *logits, int B,
+                 void *workspace, size_t workspace_bytes, void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(state && workspace && B > 0, "rtstgcn_step: null state/workspace or empty batch");
+  Bump ws(workspace, workspace_bytes);
+  return rt_step(*m, x, state, logits, B, ws, as_stream(stream));
+}
+
+size_t rtstgcn_layer_state_bytes(const stgcn_layer_desc *d, int V, int B) {
+  if (!d) return 0;
+  size_t slot = (size_t)B * V * d->c_out * sizeof(float);
+  return slot * (size_t)(d->stride * (d->kernel - 1) + 1 + d->stride);
+}
+
+size_t rtstgcn_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int B) {
+  if (!d) return 0;
+  Bump ws(nullptr, 0);
+  ws.take<float>((size_t)B * V * d->c_in);
+  ws.take<float>((size_t)B * V * d->c_out);
+  rt_layer_step_ntvc(*d, K, V, 0, nullptr, nullptr, nullptr, nullptr, nullptr, B, ws, nullptr);
+  return ws.peak;
+}
+
+int rtstgcn_layer_step(const stgcn_layer_desc *d, int K, int V, int math, const float *x, float *y,
+                       void *layer_state, int32_t *frame_counter, int B, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  STGCN_REQUIRE(d && d->rt, "rtstgcn_layer_step: descriptor must describe an online layer");
+  STGCN_REQUIRE(layer_state && frame_counter && workspace, "rtstgcn_layer_step: null state/workspace");
+  cudaStream_t st = as_stream(stream);
+  Bump ws(workspace, workspace_bytes);
+  float *xin = ws.take<float>((size_t)B * V * d->c_in);
+  float *out = ws.take<float>((size_t)B * V * d->c_out);
+  STGCN_REQUIRE(!ws.overflow, "rt layer: workspace too small");
+  const int F = d->stride * (d->kernel - 1) + 1;
+  float *fifo = static_cast<float *>(layer_state);
+  float *acc = fifo + (size_t)F * B * V * d->c_out;
+  if (to_ntvc(x, xin, B, d->c_in, V, d->c_in, st)) return 1;
+  if (rt_layer_step_ntvc(*d, K, V, math, xin, out, fifo, acc, frame_counter, B, ws, st)) return 1;
+  k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(frame_counter, 0, B);
+  STGCN_LAUNCH_OK();
+  return to_nctv(out, y, B, d->c_out, V, d->c_out, st);
+}
+
+// ---- host-buffer entry points --------------------------------------------------------
+int stgcn_model_forward_host(const stgcn_model_desc *m, const float *x_host, float *logits_host, int N,
+                             int T, void *device_io, void *workspace, size_t workspace_bytes,
+                             void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(x_host && logits_host && device_io, "forward_host: null buffer");
+  cudaStream_t st = as_stream(stream);
+  const size_t nx = (size_t)N * m->in_feat * T * m->num_joints, nl = (size_t)N * m->num_classes;
+  float *dx = static_cast<float *>(device_io);
+  float *dl = dx + nx;
+  STGCN_CUDA_OK(cudaMemcpyAsync(dx, x_host, nx * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (stgcn_model_forward(m, dx, dl, nullptr, N, T, workspace, workspace_bytes, stream)) return 1;
+  STGCN_CUDA_OK(cudaMemcpyAsync(logits_host, dl, nl * sizeof(float), cudaMemcpyDeviceToHost, st));
+  STGCN_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int rtstgcn_step_host(const stgcn_model_desc *m, const float *x_host, void *state, float *logits_host,
+                      int B, void *device_io, void *workspace, size_t workspace_bytes, void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(x_host && logits_host && device_io, "step_host: null buffer");
+  cudaStream_t st = as_stream(stream);
+  const size_t nx = (size_t)B * m->in_feat * m->num_joints, nl = (size_t)B * m->num_classes;
+  float *dx = static_cast<float *>(device_io);
+  float *dl = dx + nx;
+  STGCN_CUDA_OK(cudaMemcpyAsync(dx, x_host, nx * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (rtstgcn_step(m, dx, state, dl, B, workspace, workspace_bytes, stream)) return 1;
+  STGCN_CUDA_OK(cudaMemcpyAsync(logits_host, dl, nl * sizeof(float), cudaMemcpyDeviceToHost, st));
+  STGCN_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

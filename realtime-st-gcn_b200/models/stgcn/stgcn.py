@@ -1,0 +1,199 @@
+"""Drop-in for the reference ``models/stgcn/stgcn.py`` (``Model``, ``StgcnLayer``).
+
+Same constructor kwargs, forward signatures and state_dict keys as the reference
+(SURVEY.md §8b); the forward bodies are replaced by the sm_100a kernels behind the
+C ABI (``stgcn_model_forward`` / ``stgcn_layer_forward``).  Inference only:
+forward runs under ``torch.no_grad()`` and dropout must be inactive, as in the
+reference's test/benchmark routines.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ..utils import BatchNorm1d, BatchNorm2d, Conv2d, ConvTemporalGraphical, Graph, LayerNorm
+
+
+def _norm(normalization, channels, joints):
+    if normalization == 'LayerNorm':
+        return LayerNorm([channels, 1, joints])
+    return BatchNorm2d(channels, track_running_stats=False)
+
+
+class Model(nn.Module):
+    """ST-GCN classifier: norm_in -> fcn_in -> L x StgcnLayer -> mean(T,V) -> fcn_out.
+
+    Input ``(N, in_feat, T, V)``; output ``(N, num_classes, 1)`` (reference
+    stgcn.py:80-97).  Extra, B200-only knobs (not in the reference): ``math``
+    selects the GEMM arithmetic ('fp32' | 'bf16x3' | 'bf16').
+    """
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        conf = kwargs['st-gcn']
+        self.graph = Graph(strategy=kwargs['strategy'], **kwargs['graph'])
+        A = torch.tensor(self.graph.A, dtype=torch.float32, requires_grad=False)
+        self.register_buffer('A', A)
+
+        kernel_size = (conf['kernel'], kwargs['graph']['num_node'])
+        self.normalization = kwargs['normalization']
+        self.math = kwargs.get('math', 'fp32')
+        if self.normalization == 'LayerNorm':
+            self.norm_in = LayerNorm([kwargs['in_feat'], 1, A.size(1)])
+        else:
+            self.norm_in = BatchNorm1d(kwargs['in_feat'] * A.size(1), track_running_stats=False)
+        self.fcn_in = Conv2d(in_channels=conf['in_feat'], out_channels=conf['in_ch'][0], kernel_size=1)
+        self.gcn_networks = nn.ModuleList([
+            StgcnLayer(in_channels=conf['in_ch'][i], out_channels=conf['out_ch'][i],
+                       kernel_size=kernel_size, partitions=A.size(0), num_joints=A.size(1),
+                       stride=conf['stride'][i], residual=not not conf['residual'][i],
+                       dropout=conf['dropout'][i], normalization=kwargs['normalization'])
+            for i in range(conf['layers'])])
+        if conf['importance']:
+            self.edge_importance = nn.ParameterList(
+                [nn.Parameter(torch.ones(self.A.size())) for _ in self.gcn_networks])
+        else:
+            self.edge_importance = [1] * len(self.gcn_networks)
+        self.fcn_out = Conv2d(conf['out_ch'][-1], out_channels=kwargs['num_classes'], kernel_size=1)
+        self.num_classes = kwargs['num_classes']
+        self._ws = _lib.Workspace()
+        self._desc = None
+
+    # ------------------------------------------------------------------ #
+    def _fingerprint(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.A.data_ptr(), self.math)
+
+    def _descriptor(self):
+        """(ModelDesc, keep-alive list); rebuilt when parameters change or move."""
+        fp = self._fingerprint()
+        if self._desc is not None and self._desc[0] == fp:
+            return self._desc[1]
+        keep = []
+        layers = (_lib.LayerDesc * len(self.gcn_networks))()
+        for i, (gcn, imp) in enumerate(zip(self.gcn_networks, self.edge_importance)):
+            a_eff = (self.A * imp).contiguous()           # stgcn.py:89
+            keep.append(a_eff)
+            gcn._fill_desc(layers[i], a_eff)
+        m = _lib.ModelDesc()
+        m.in_feat = self.fcn_in.in_channels
+        m.num_joints = self.A.size(1)
+        m.partitions = self.A.size(0)
+        m.num_classes = self.num_classes
+        m.num_layers = len(self.gcn_networks)
+        m.norm = _lib.NORM_LAYERNORM if self.normalization == 'LayerNorm' else _lib.NORM_BATCHNORM
+        m.math = _lib.MATH_NAMES[self.math]
+        nin = self.norm_in if self.normalization == 'LayerNorm' else self.norm_in.norm
+        m.norm_in_w, m.norm_in_b = nin.weight.data_ptr(), nin.bias.data_ptr()
+        m.fcn_in_w, m.fcn_in_b = self.fcn_in.weight.data_ptr(), self.fcn_in.bias.data_ptr()
+        m.fcn_out_w, m.fcn_out_b = self.fcn_out.weight.data_ptr(), self.fcn_out.bias.data_ptr()
+        m.layers = ctypes.cast(layers, ctypes.POINTER(_lib.LayerDesc))
+        keep.append(layers)
+        self._desc = (fp, (m, keep))
+        return self._desc[1]
+
+    @torch.no_grad()
+    def forward(self, x, return_features=False):
+        n, c, t, v = x.shape
+        x = x.contiguous()
+        dev = _lib.require_cuda(x, self.A, self.fcn_in.weight)
+        if self.training and any(g.dropout_p > 0 for g in self.gcn_networks):
+            raise RuntimeError("B200 ST-GCN path is inference-only (dropout active)")
+        lib = _lib.load()
+        m, _ = self._descriptor()
+        ws = self._ws.get(lib.stgcn_model_workspace_bytes(ctypes.byref(m), n, t), dev)
+        logits = torch.empty((n, self.num_classes), device=dev, dtype=torch.float32)
+        feats = None
+        if return_features:
+            tf = t
+            for g in self.gcn_networks:
+                tf = (tf - 1) // g.stride + 1
+            feats = torch.empty((n, self.gcn_networks[-1].out_channels, tf, v), device=dev,
+                                dtype=torch.float32)
+        _lib.check(lib.stgcn_model_forward(
+            ctypes.byref(m), _lib.ptr(x), _lib.ptr(logits), _lib.ptr(feats), n, t,
+            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        out = logits.unsqueeze(-1)                         # (N, classes, 1) like stgcn.py:97
+        return (out, feats) if return_features else out
+
+    def prepare_benchmark(self, arch_conf):
+        return arch_conf
+
+
+class StgcnLayer(nn.Module):
+    """One st_gcn block: ``relu(norm2(conv_Gx1(relu(norm1(gcn(x, A))))) + res(x))``
+    (reference stgcn.py:125-193).  ``forward(x, A)`` takes ``(N, C_in, T, V)`` and
+    ``A`` as ``(K, V, V)`` or ``(N, K, V, V)``.
+    """
+
+    def __init__(self, in_channels, out_channels, kernel_size, partitions, num_joints, stride=1,
+                 dropout=0, residual=True, normalization='LayerNorm'):
+        super().__init__()
+        assert len(kernel_size) == 2
+        assert kernel_size[0] % 2 == 1
+        padding = ((kernel_size[0] - 1) // 2, 0)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.temporal_kernel, self.stride = kernel_size[0], stride
+        self.partitions, self.num_joints = partitions, num_joints
+        self.normalization = normalization
+        self.dropout_p = dropout
+        self.is_residual = residual
+        self.is_residual_conv = residual and not ((in_channels == out_channels) and (stride == 1))
+
+        self.gcn = ConvTemporalGraphical(in_channels, out_channels, kernel_size[1], partitions)
+        self.tcn = nn.Sequential(
+            _norm(normalization, out_channels, num_joints),
+            nn.ReLU(inplace=True),
+            Conv2d(out_channels, out_channels, (kernel_size[0], 1), stride=(stride, 1), padding=padding),
+            _norm(normalization, out_channels, num_joints),
+            nn.Dropout(dropout, inplace=True))
+        if self.is_residual_conv:
+            self.residual = nn.Sequential(
+                Conv2d(in_channels, out_channels, kernel_size=1, stride=(stride, 1)),
+                _norm(normalization, out_channels, num_joints))
+        else:
+            self.residual = nn.Identity()
+        self.relu = nn.ReLU(inplace=True)
+        self._ws = _lib.Workspace()
+
+    def _fill_desc(self, d, a_eff, per_sample=0):
+        d.c_in, d.c_out = self.in_channels, self.out_channels
+        d.kernel, d.stride = self.temporal_kernel, self.stride
+        d.residual = (_lib.RES_NONE if not self.is_residual else
+                      _lib.RES_CONV if self.is_residual_conv else _lib.RES_IDENTITY)
+        d.norm = _lib.NORM_LAYERNORM if self.normalization == 'LayerNorm' else _lib.NORM_BATCHNORM
+        d.rt = 0
+        d.a_per_sample = per_sample
+        d.gcn_w, d.gcn_b = self.gcn.conv.weight.data_ptr(), self.gcn.conv.bias.data_ptr()
+        d.a_eff = a_eff.data_ptr()
+        d.n1_w, d.n1_b = self.tcn[0].weight.data_ptr(), self.tcn[0].bias.data_ptr()
+        d.tcn_w, d.tcn_b = self.tcn[2].weight.data_ptr(), self.tcn[2].bias.data_ptr()
+        d.n2_w, d.n2_b = self.tcn[3].weight.data_ptr(), self.tcn[3].bias.data_ptr()
+        if self.is_residual_conv:
+            d.res_w, d.res_b = self.residual[0].weight.data_ptr(), self.residual[0].bias.data_ptr()
+            d.nr_w, d.nr_b = self.residual[1].weight.data_ptr(), self.residual[1].bias.data_ptr()
+
+    @torch.no_grad()
+    def forward(self, x, A, math='fp32'):
+        n, c, t, v = x.shape
+        x = x.contiguous()
+        A = A.contiguous()
+        dev = _lib.require_cuda(x, A, self.gcn.conv.weight)
+        if self.training and self.dropout_p > 0:
+            raise RuntimeError("B200 ST-GCN path is inference-only (dropout active)")
+        k = self.partitions
+        per_sample = 1 if A.dim() == 4 else 0
+        if c != self.in_channels or v != self.num_joints or tuple(A.shape[-3:]) != (k, v, v) \
+                or (per_sample and A.shape[0] != n):
+            raise RuntimeError("StgcnLayer: bad input/adjacency shape %s / %s"
+                               % (tuple(x.shape), tuple(A.shape)))
+        lib = _lib.load()
+        d = _lib.LayerDesc()
+        self._fill_desc(d, A, per_sample)
+        ws = self._ws.get(lib.stgcn_layer_workspace_bytes(ctypes.byref(d), k, v, n, t), dev)
+        t_out = (t - 1) // self.stride + 1
+        y = torch.empty((n, self.out_channels, t_out, v), device=dev, dtype=torch.float32)
+        _lib.check(lib.stgcn_layer_forward(
+            ctypes.byref(d), k, v, _lib.MATH_NAMES[math], _lib.ptr(x), _lib.ptr(y), n, t,
+            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        return y

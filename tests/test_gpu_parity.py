@@ -1,0 +1,259 @@
+"""GPU parity: the CUDA path (through the nn.Module drop-ins -> ctypes -> C ABI) against the
+reference's golden outputs and against the CPU oracle on seeded inputs.
+
+Tolerance: north_star's 1e-4 relative (max|diff| / max|ref|) in fp32.
+"""
+import ctypes
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import stgcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+SMALL = dict(in_ch=[16, 16, 32], out_ch=[16, 32, 32], stride=[1, 2, 1])
+
+
+def _cuda_sd(w, dev):
+    return {k: v.to(dev) for k, v in w.items()}
+
+
+# ------------------------------------------------------------------ primitives
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_layernorm(pkg, cuda, tag):
+    from importlib import import_module
+    LN = import_module('realtime-st-gcn_b200.models.utils').LayerNorm
+    a, w = load_golden('layernorm_' + tag)
+    c, v = a['x'].shape[1], a['x'].shape[3]
+    ln = LN([c, 1, v]).to(cuda)
+    ln.load_state_dict(w)
+    assert rel_err(ln(a['x'].to(cuda)), a['y']) < 1e-5
+
+
+def test_batchnorms(pkg, cuda):
+    from importlib import import_module
+    U = import_module('realtime-st-gcn_b200.models.utils')
+    a, w = load_golden('batchnorm1d')
+    bn = U.BatchNorm1d(75).to(cuda)
+    bn.load_state_dict(w)
+    assert rel_err(bn(a['x'].to(cuda)), a['y']) < 1e-5
+    a, w = load_golden('batchnorm2d')
+    bn = U.BatchNorm2d(16).to(cuda)
+    bn.load_state_dict(w)
+    assert rel_err(bn(a['x'].to(cuda)), a['y']) < 1e-5
+    with pytest.raises(RuntimeError, match='more than 1 value'):
+        U.BatchNorm1d(75).to(cuda)(torch.zeros(1, 3, 1, 25, device=cuda))
+
+
+def test_conv_matches_torch_cpu(pkg, cuda):
+    """Gamma x 1 / 1 x 1 convolution kernel vs torch CPU conv2d (odd channel counts, strides)."""
+    from importlib import import_module
+    Conv2d = import_module('realtime-st-gcn_b200.models.utils').Conv2d
+    g = torch.Generator().manual_seed(3)
+    for (ci, co, k, s, n, t, v) in [(3, 64, 1, 1, 2, 7, 25), (16, 16, 9, 1, 2, 20, 25),
+                                    (16, 32, 9, 2, 1, 21, 7), (6, 10, 3, 3, 1, 10, 5),
+                                    (256, 52, 1, 1, 3, 1, 1)]:
+        conv = Conv2d(ci, co, (k, 1), stride=(s, 1), padding=((k - 1) // 2, 0))
+        x = torch.randn(n, ci, t, v, generator=g)
+        ref = torch.nn.functional.conv2d(x, conv.weight, conv.bias, stride=(s, 1), padding=((k - 1) // 2, 0))
+        got = conv.to(cuda)(x.to(cuda))
+        assert got.shape == ref.shape
+        assert rel_err(got, ref.detach()) < 1e-5
+
+
+def test_graph_conv(pkg, cuda):
+    from importlib import import_module
+    T = import_module('realtime-st-gcn_b200.models.utils').ConvTemporalGraphical
+    a, w = load_golden('tgcn')
+    tg = T(16, 32, 25, 3).to(cuda)
+    tg.load_state_dict(w)
+    x = a['x'].to(cuda)
+    assert rel_err(tg(x, a['A'].to(cuda)), a['y3']) < 1e-5
+    assert rel_err(tg(x, a['A4'].to(cuda)), a['y4']) < 1e-5       # dense per-sample adjacency
+
+
+# ------------------------------------------------------------------ ST-GCN layer
+@pytest.mark.parametrize('tag', ['ln_id', 'ln_conv_s2', 'ln_nores', 'ln_64', 'ln_imu_s2', 'bn_id',
+                                 'bn_conv_s2'])
+def test_stgcn_layer_golden(pkg, cuda, tag):
+    from importlib import import_module
+    Layer = import_module('realtime-st-gcn_b200.models.stgcn').StgcnLayer
+    a, w = load_golden('stgcn_layer_' + tag)
+    ci, co, s, res, bn = [int(v) for v in a['meta']]
+    v = a['x'].shape[3]
+    layer = Layer(ci, co, (9, v), 3, v, stride=s, residual=bool(res),
+                  normalization='BatchNorm' if bn else 'LayerNorm').to(cuda)
+    layer.load_state_dict(w)
+    layer.eval()
+    y = layer(a['x'].to(cuda), a['A'].to(cuda))
+    assert y.shape == a['y'].shape
+    assert rel_err(y, a['y']) < TOL
+
+
+def test_stgcn_layer_per_sample_adjacency(pkg, cuda):
+    """AA-GCN style call: forward(x, A[N,K,V,V]) (reference models/aagcn/aagcn.py:148)."""
+    from importlib import import_module
+    Layer = import_module('realtime-st-gcn_b200.models.stgcn').StgcnLayer
+    a, w = load_golden('stgcn_layer_ln_id')
+    g = torch.Generator().manual_seed(5)
+    A4 = a['A'].unsqueeze(0) + 0.05 * torch.randn(2, 3, 25, 25, generator=g)
+    ref = O.stgcn_layer(a['x'], A4, w)
+    layer = Layer(16, 16, (9, 25), 3, 25).to(cuda)
+    layer.load_state_dict(w)
+    assert rel_err(layer(a['x'].to(cuda), A4.to(cuda)), ref) < TOL
+
+
+# ------------------------------------------------------------------ ST-GCN model
+@pytest.mark.parametrize('tag,norm', [('ln', 'LayerNorm'), ('bn', 'BatchNorm')])
+def test_stgcn_model_small(pkg, syn, cuda, tag, norm):
+    a, w = load_golden('stgcn_model_small_' + tag)
+    m = pkg.Stgcn(**syn.arch_config('st-gcn', normalization=norm, num_classes=12, **SMALL)).to(cuda)
+    m.load_state_dict(w)
+    m.eval()
+    logits, feats = m(a['x'].to(cuda), return_features=True)
+    assert logits.shape == (2, 12, 1)
+    assert rel_err(feats, a['features']) < TOL
+    assert rel_err(logits, a['logits']) < TOL
+
+
+@pytest.mark.parametrize('tag,norm', [('ln', 'LayerNorm'), ('bn', 'BatchNorm')])
+def test_stgcn_model_c1(pkg, syn, cuda, tag, norm):
+    """BASELINE config 1: N=1, C=3, T=300, V=25, full 9-layer trunk, vs the reference's output."""
+    a, _ = load_golden('stgcn_model_c1_' + tag)
+    m = pkg.Stgcn(**syn.arch_config('st-gcn', normalization=norm))
+    sd = syn.synth_state_dict(m.state_dict(), int(a['seeds'][0]))
+    assert syn.state_digest(sd) == str(a['digest'])
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    x = syn.synth_input((1, 3, 300, 25), int(a['seeds'][1])).to(cuda)
+    logits, feats = m(x, return_features=True)
+    assert logits.shape == (1, 52, 1) and feats.shape == (1, 256, 75, 25)
+    assert rel_err(feats[:, :, [0, 37, 74]], a['features_t0_t37_t74']) < TOL
+    assert rel_err(logits, a['logits']) < TOL
+
+
+def test_stgcn_model_trials_are_independent_and_chunked(pkg, syn, cuda):
+    """LayerNorm mode: a batch equals its trials run one by one (the property trial-sharding and
+    the internal trial chunking rely on); also exercises a ragged T and the chunk loop."""
+    m = pkg.Stgcn(**syn.arch_config('st-gcn', num_classes=12, **SMALL))
+    m.load_state_dict(syn.synth_state_dict(m.state_dict(), 5))
+    m = m.to(cuda).eval()
+    x = syn.synth_input((5, 3, 37, 25), 6).to(cuda)
+    full = m(x)
+    single = torch.cat([m(x[i:i + 1]) for i in range(5)])
+    assert torch.equal(full, single)
+    # force the C side to chunk: hand it a workspace that only fits 2 trials
+    lib = pkg._lib.load()
+    desc, _ = m._descriptor()
+    small = lib.stgcn_model_workspace_bytes(ctypes.byref(desc), 2, 37)
+    ws = torch.empty(small, dtype=torch.uint8, device=cuda)
+    logits = torch.empty(5, 12, device=cuda)
+    pkg._lib.check(lib.stgcn_model_forward(ctypes.byref(desc), x.data_ptr(), logits.data_ptr(), None, 5, 37,
+                                           ws.data_ptr(), ws.numel(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(logits, full.squeeze(-1))
+    oracle = O.stgcn_model(x.cpu(), {k: v.cpu() for k, v in m.state_dict().items()},
+                           dict(layers=3, stride=[1, 2, 1], residual=[1, 1, 1], normalization='LayerNorm'))
+    assert rel_err(full, oracle) < TOL
+
+
+def test_stgcn_model_host_entry(pkg, syn, cuda):
+    """stgcn_model_forward_host: pinned host buffers in, host logits out (H2D + forward + D2H)."""
+    m = pkg.Stgcn(**syn.arch_config('st-gcn', num_classes=12, **SMALL))
+    m.load_state_dict(syn.synth_state_dict(m.state_dict(), 5))
+    m = m.to(cuda).eval()
+    x = syn.synth_input((3, 3, 30, 25), 8).pin_memory()
+    out = torch.empty(3, 12).pin_memory()
+    lib = pkg._lib.load()
+    desc, _ = m._descriptor()
+    ws = torch.empty(lib.stgcn_model_workspace_bytes(ctypes.byref(desc), 3, 30), dtype=torch.uint8, device=cuda)
+    io = torch.empty(x.numel() + out.numel(), device=cuda)
+    pkg._lib.check(lib.stgcn_model_forward_host(ctypes.byref(desc), x.data_ptr(), out.data_ptr(), 3, 30,
+                                                io.data_ptr(), ws.data_ptr(), ws.numel(), None))
+    assert torch.equal(out, m(x.to(cuda)).squeeze(-1).cpu())
+
+
+# ------------------------------------------------------------------ RT-ST-GCN continual
+def _online(pkg, syn, cuda, cfg_kw, sd):
+    m = pkg.RtStgcn(**syn.arch_config('rt-st-gcn', **cfg_kw))
+    m.load_state_dict(sd)
+    m = m.to(cuda)
+    m.prepare_benchmark({})
+    return m.eval()
+
+
+def test_rt_small(pkg, syn, cuda):
+    a, w = load_golden('rtstgcn_small')
+    m = _online(pkg, syn, cuda, dict(num_classes=12, **SMALL), w)
+    out = m(a['x'].to(cuda))                      # both streams at once, 40 frames
+    assert out.shape == (2, 12, 40)
+    assert rel_err(out, a['logits']) < TOL
+    a, w = load_golden('rtstgcn_small_nores')
+    m = _online(pkg, syn, cuda, dict(num_classes=6, in_ch=[16, 16], out_ch=[16, 32], stride=[1, 1],
+                                     residual=[0, 1], importance=False), w)
+    assert rel_err(m(a['x'].to(cuda)), a['logits']) < TOL
+
+
+@pytest.mark.parametrize('tag', ['pku', 'imu'])
+def test_rt_full(pkg, syn, cuda, tag):
+    """BASELINE configs 2/5 trunks vs the reference's own continual loop (48 frames: covers the
+    stride-2 FIFO wrap at t = 17 and t = 34)."""
+    a, _ = load_golden('rtstgcn_' + tag)
+    kw = {} if tag == 'pku' else dict(graph='imu_fogit_ABCD', in_feat=6, num_classes=8)
+    cfg = syn.arch_config('rt-st-gcn', **kw)
+    sd = syn.synth_state_dict(pkg.RtStgcn(**cfg).state_dict(), int(a['seeds'][0]))
+    assert syn.state_digest(sd) == str(a['digest'])
+    m = _online(pkg, syn, cuda, kw, sd)
+    x = syn.synth_input((2, cfg['in_feat'], 48, cfg['graph']['num_node']), int(a['seeds'][1])).to(cuda)
+    out = m(x)
+    assert rel_err(out, a['logits']) < TOL
+
+
+def test_rt_streams_independent_reset_and_many_streams(pkg, syn, cuda):
+    """Streams are independent; resetting one stream restarts only that stream; a 300-stream batch
+    agrees with the oracle on a sampled subset."""
+    _, w = load_golden('rtstgcn_small')
+    m = _online(pkg, syn, cuda, dict(num_classes=12, **SMALL), w)
+    B, L = 300, 30
+    x = syn.synth_input((B, 3, L, 25), 77)
+    out = m(x.to(cuda)).cpu()
+    cfg = dict(layers=3, stride=[1, 2, 1], residual=[1, 1, 1], importance=True, kernel=9, out_ch=[16, 32, 32])
+    pick = [0, 1, 137, 299]
+    ref = O.rt_model_run(x[pick], w, cfg)
+    assert rel_err(out[pick], ref) < TOL
+    # reset stream 137 only, replay: stream 137 restarts from scratch, stream 0 continues
+    m.reset_streams(137, 1)
+    out2 = m(x[:, :, :5].to(cuda)).cpu()
+    assert rel_err(out2[137], ref[2][:, :5]) < TOL
+    cont = O.rt_model_run(torch.cat([x[0:1], x[0:1, :, :5]], dim=2), w, cfg)[:, :, L:]
+    assert rel_err(out2[0:1], cont) < TOL
+
+
+def test_rt_online_layer_module(pkg, syn, cuda):
+    """OnlineLayer.forward (single layer API) vs the oracle recurrence, stride 2 + residual conv."""
+    from importlib import import_module
+    R = import_module('realtime-st-gcn_b200.models.rtstgcn')
+    _, w = load_golden('rtstgcn_small')
+    A = w['A']
+    layer = R.OnlineLayer(in_channels=16, out_channels=32, kernel_size=9, num_joints=25, stride=2,
+                          num_partitions=3, dropout=0, residual=True, importance=True, graph=A)
+    sub = {k[len('st_gcn.1.'):]: v for k, v in w.items() if k.startswith('st_gcn.1.')}
+    layer.load_state_dict(sub)
+    layer = layer.to(cuda)
+    layer.eval_()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 16, 40, 25, generator=g)
+    got = torch.cat([layer(x[:, :, t:t + 1].to(cuda), None) for t in range(40)], dim=2)
+    st = O.rt_state_init(dict(layers=1, stride=[2], kernel=9, out_ch=[32]), w, 3)
+    ref = torch.cat([O.rt_layer_step(x[:, :, t:t + 1], A * w['st_gcn.1.edge_importance'], w, 'st_gcn.1.',
+                                     st[0], 32, 2) for t in range(40)], dim=2)
+    assert rel_err(got, ref) < TOL
+
+
+def test_rt_batchnorm_rejected(pkg, syn, cuda):
+    m = pkg.RtStgcn(**syn.arch_config('rt-st-gcn', normalization='BatchNorm', num_classes=12, **SMALL)).to(cuda)
+    m.prepare_benchmark({})
+    with pytest.raises(RuntimeError, match='LayerNorm'):
+        m(torch.zeros(1, 3, 1, 25, device=cuda))

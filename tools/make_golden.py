@@ -1,0 +1,219 @@
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE.
+
+Run in the build container only (needs /root/reference, which does not exist on the
+GPU box):
+
+    python tools/make_golden.py
+
+The reference ships no golden vectors, so parity is pinned by executing
+the untouched reference modules on seeded weights/inputs and committing the results.
+Small cases store inputs, weights and outputs; full-size cases store the seeds, a digest
+of the generated weights and the outputs (weights are regenerated with
+``synthetic.synth_state_dict``).  Harness-side workarounds only:
+``_swap_layers_for_inference()`` + ``eval_()`` per online layer; LayerNorm for continual.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get('STGCN_REFERENCE', '/root/reference')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+syn = importlib.import_module('realtime-st-gcn_b200.synthetic')
+skel = importlib.import_module('realtime-st-gcn_b200.skeletons')
+
+from models.stgcn.stgcn import Model as RefStgcn, StgcnLayer as RefStgcnLayer      # noqa: E402
+from models.rtstgcn.rtstgcn import Model as RefRt                                   # noqa: E402
+from models.utils import ConvTemporalGraphical as RefTgcn, Graph as RefGraph       # noqa: E402
+from models.utils import LayerNorm as RefLN, BatchNorm1d as RefBN1d                # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(4)
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                 for k, v in arrays.items()})
+    print('%-32s %8.1f KB' % (name, os.path.getsize(path) / 1024))
+
+
+def sd_arrays(sd, prefix='w:'):
+    return {prefix + k: v for k, v in sd.items()}
+
+
+# ---------------------------------------------------------------------------- graphs
+def gen_graphs():
+    arrays = {}
+    for name in skel.names():
+        g = skel.skeleton(name)
+        for strategy in ('spatial', 'distance', 'uniform'):
+            for norm in ('symmetric', 'nonsymmetric'):
+                A = RefGraph(strategy=strategy, normalization=norm, **g).A
+                arrays['%s|%s|%s' % (name, strategy, norm)] = A
+    g = skel.skeleton('pku-mmd')
+    arrays['pku-mmd|spatial|symmetric|hop2'] = RefGraph(strategy='spatial', max_hop=2, **g).A
+    arrays['pku-mmd|distance|symmetric|hop2dil2'] = RefGraph(strategy='distance', max_hop=2, dilation=2, **g).A
+    save('graphs', **arrays)
+
+
+# ---------------------------------------------------------------------------- primitives
+def gen_primitives():
+    g = torch.Generator().manual_seed(11)
+    # LayerNorm [C,1,V]
+    for tag, (n, c, t, v) in {'a': (2, 16, 5, 25), 'b': (1, 3, 7, 7), 'c': (3, 64, 2, 25)}.items():
+        ln = RefLN([c, 1, v])
+        sd = syn.synth_state_dict(ln.state_dict(), 100 + c)
+        ln.load_state_dict(sd)
+        x = torch.randn(n, c, t, v, generator=g) * 3 + 1
+        with torch.no_grad():
+            y = ln(x)
+        save('layernorm_' + tag, x=x, y=y, **sd_arrays(sd))
+    # input BatchNorm1d (per (v,c) feature) and trunk BatchNorm2d (batch statistics)
+    n, c, t, v = 3, 3, 9, 25
+    bn = RefBN1d(c * v, track_running_stats=False)
+    sd = syn.synth_state_dict(bn.state_dict(), 7)
+    bn.load_state_dict(sd)
+    bn.eval()
+    x = torch.randn(n, c, t, v, generator=g) * 2 - 0.5
+    with torch.no_grad():
+        y = bn(x)
+    save('batchnorm1d', x=x, y=y.contiguous(), **sd_arrays(sd))
+    bn2 = torch.nn.BatchNorm2d(16, track_running_stats=False)
+    sd = syn.synth_state_dict(bn2.state_dict(), 8)
+    bn2.load_state_dict(sd)
+    bn2.eval()
+    x = torch.randn(2, 16, 6, 25, generator=g) * 2 + 0.3
+    with torch.no_grad():
+        y = bn2(x)
+    save('batchnorm2d', x=x, y=y, **sd_arrays(sd))
+    # graph conv with (K,V,V) and per-sample (N,K,V,V) adjacency
+    A = torch.tensor(RefGraph(**skel.skeleton('pku-mmd')).A, dtype=torch.float32)
+    tg = RefTgcn(16, 32, 25, 3)
+    sd = syn.synth_state_dict(tg.state_dict(), 9)
+    tg.load_state_dict(sd)
+    x = torch.randn(2, 16, 6, 25, generator=g)
+    A4 = A.unsqueeze(0) * (torch.rand(2, 3, 25, 25, generator=g) + 0.5) + \
+        0.05 * torch.randn(2, 3, 25, 25, generator=g)          # dense, like AA-GCN's A+B+C
+    with torch.no_grad():
+        y3 = tg(x, A)
+        y4 = tg(x, A4)
+    save('tgcn', x=x, A=A, A4=A4, y3=y3, y4=y4, **sd_arrays(sd))
+
+
+# ---------------------------------------------------------------------------- ST-GCN layer
+def gen_layers():
+    g = torch.Generator().manual_seed(21)
+    A = torch.tensor(RefGraph(**skel.skeleton('pku-mmd')).A, dtype=torch.float32)
+    Aimu = torch.tensor(RefGraph(**skel.skeleton('imu_fogit_ABCD')).A, dtype=torch.float32)
+    cases = {
+        # tag: (c_in, c_out, stride, residual, norm, N, T, A)
+        'ln_id': (16, 16, 1, True, 'LayerNorm', 2, 12, A),
+        'ln_conv_s2': (16, 32, 2, True, 'LayerNorm', 2, 13, A),
+        'ln_nores': (16, 16, 1, False, 'LayerNorm', 1, 10, A),
+        'ln_64': (64, 64, 1, True, 'LayerNorm', 1, 20, A),
+        'ln_imu_s2': (16, 32, 2, True, 'LayerNorm', 2, 11, Aimu),
+        'bn_id': (16, 16, 1, True, 'BatchNorm', 2, 12, A),
+        'bn_conv_s2': (16, 32, 2, True, 'BatchNorm', 2, 13, A),
+    }
+    for tag, (ci, co, s, res, norm, n, t, adj) in cases.items():
+        v = adj.shape[-1]
+        layer = RefStgcnLayer(ci, co, (9, v), 3, v, stride=s, residual=res, normalization=norm)
+        sd = syn.synth_state_dict(layer.state_dict(), 300 + len(tag))
+        layer.load_state_dict(sd)
+        layer.eval()
+        imp = torch.rand(3, v, v, generator=g) + 0.5
+        x = torch.randn(n, ci, t, v, generator=g)
+        with torch.no_grad():
+            y = layer(x.clone(), adj * imp)
+        save('stgcn_layer_' + tag, x=x, A=adj * imp, y=y,
+             meta=np.array([ci, co, s, int(res), int(norm == 'BatchNorm')]), **sd_arrays(sd))
+
+
+# ---------------------------------------------------------------------------- models
+SMALL = dict(in_ch=[16, 16, 32], out_ch=[16, 32, 32], stride=[1, 2, 1])
+
+
+def gen_stgcn_models():
+    for norm, tag in (('LayerNorm', 'ln'), ('BatchNorm', 'bn')):
+        cfg = syn.arch_config('st-gcn', normalization=norm, num_classes=12, **SMALL)
+        m = RefStgcn(**cfg)
+        sd = syn.synth_state_dict(m.state_dict(), 41)
+        m.load_state_dict(sd)
+        m.eval()
+        x = syn.synth_input((2, 3, 24, 25), 42)
+        with torch.no_grad():
+            h = m.fcn_in(m.norm_in(x))
+            for gcn, imp in zip(m.gcn_networks, m.edge_importance):
+                h = gcn(h, m.A * imp)
+            logits = m(x)
+        save('stgcn_model_small_' + tag, x=x, logits=logits, features=h, **sd_arrays(sd))
+
+        # BASELINE config C1: N=1, C=3, T=300, V=25, full trunk, 52 classes
+        cfg = syn.arch_config('st-gcn', normalization=norm)
+        m = RefStgcn(**cfg)
+        sd = syn.synth_state_dict(m.state_dict(), 1234)
+        m.load_state_dict(sd)
+        m.eval()
+        x = syn.synth_input((1, 3, 300, 25), 4321)
+        with torch.no_grad():
+            h = m.fcn_in(m.norm_in(x))
+            for gcn, imp in zip(m.gcn_networks, m.edge_importance):
+                h = gcn(h, m.A * imp)
+            logits = m(x)
+        save('stgcn_model_c1_' + tag, logits=logits, features_t0_t37_t74=h[:, :, [0, 37, 74]],
+             features_absmax=h.abs().max(), seeds=np.array([1234, 4321]),
+             digest=np.array(syn.state_digest(sd)))
+
+
+def run_ref_online(cfg, sd, x):
+    """Reference continual loop, one fresh model per stream (reference is batch-1)."""
+    outs = []
+    for b in range(x.shape[0]):
+        m = RefRt(**cfg)
+        m.load_state_dict(sd)
+        m._swap_layers_for_inference()
+        for layer in m.st_gcn:
+            layer.eval_()
+        m.eval()
+        with torch.no_grad():
+            o = [m(x[b:b + 1, :, t:t + 1]).clone() for t in range(x.shape[2])]
+        outs.append(torch.cat(o, dim=2))
+    return torch.cat(outs, dim=0)
+
+
+def gen_rt_models():
+    cfg = syn.arch_config('rt-st-gcn', num_classes=12, **SMALL)
+    sd = syn.synth_state_dict(RefRt(**cfg).state_dict(), 51)
+    x = syn.synth_input((2, 3, 40, 25), 52)
+    save('rtstgcn_small', x=x, logits=run_ref_online(cfg, sd, x), **sd_arrays(sd))
+
+    # no-residual / no-importance variant
+    cfg = syn.arch_config('rt-st-gcn', num_classes=6, in_ch=[16, 16], out_ch=[16, 32], stride=[1, 1],
+                          residual=[0, 1], importance=False)
+    sd = syn.synth_state_dict(RefRt(**cfg).state_dict(), 53)
+    x = syn.synth_input((1, 3, 24, 25), 54)
+    save('rtstgcn_small_nores', x=x, logits=run_ref_online(cfg, sd, x), **sd_arrays(sd))
+
+    # BASELINE configs C2 (PKU graph) and C5 (IMU graph), full trunk
+    for tag, kw, shape in (('pku', dict(), (2, 3, 48, 25)),
+                           ('imu', dict(graph='imu_fogit_ABCD', in_feat=6, num_classes=8), (2, 6, 48, 7))):
+        cfg = syn.arch_config('rt-st-gcn', **kw)
+        sd = syn.synth_state_dict(RefRt(**cfg).state_dict(), 61)
+        x = syn.synth_input(shape, 62)
+        save('rtstgcn_' + tag, logits=run_ref_online(cfg, sd, x), seeds=np.array([61, 62]),
+             digest=np.array(syn.state_digest(sd)))
+
+
+if __name__ == '__main__':
+    gen_graphs()
+    gen_primitives()
+    gen_layers()
+    gen_stgcn_models()
+    gen_rt_models()
