@@ -8,6 +8,8 @@
 // also the path for shapes the tcgen05 kernels do not cover: C % 64 != 0, tiny
 // batches).  The tensor-core kernels live in kernels_tc.cuh.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace stgcn {
@@ -291,6 +293,9 @@ struct FrameArgs {
   int relu_out;
   float eps;
   float *out;
+  // optional split-bf16 output (hi = bf16(v), lo = bf16(v - hi)) feeding the tcgen05 kernels;
+  // when out_hi is set, `out` is not written.  out_lo may be null (single-plane bf16 mode).
+  __nv_bfloat16 *out_hi, *out_lo;
   // RT state
   float *fifo, *acc;
   const int *counter;
@@ -389,7 +394,13 @@ __global__ void __launch_bounds__(256) k_frame(FrameArgs p) {
         v += (zb[i] - mean_b) * rstd_b * p.nb_w[pi] + p.nb_b[pi];
       }
       if (p.relu_out) v = fmaxf(v, 0.f);
-      dst[i] = v;
+      if (p.out_hi) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        p.out_hi[row0 * p.C + i] = hi;
+        if (p.out_lo) p.out_lo[row0 * p.C + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      } else {
+        dst[i] = v;
+      }
     }
     __syncthreads();
   }

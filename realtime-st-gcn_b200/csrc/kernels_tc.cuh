@@ -1,0 +1,450 @@
+// tcgen05 / TMEM / TMA kernels of the ST-GCN forward path (sm_100a).
+//
+// Arithmetic modes (STGCN_MATH_*):
+//   BF16X3: every fp32 operand is split into two bf16 planes, x = hi + lo with
+//           hi = bf16(x), lo = bf16(x - hi).  The product is accumulated in fp32 TMEM as
+//           hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-18 relative), which keeps
+//           the result inside the 1e-4 fp32-parity bound at 3 bf16 MMAs per product.
+//   BF16  : single bf16 MMA (hi planes only).
+//
+// Shared-memory operand layout is the canonical K-major SWIZZLE_128B UMMA layout: rows of
+// 64 bf16 (128 B), 8-row groups 1024 B apart, written by TMA with CU_TENSOR_MAP_SWIZZLE_128B.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace stgcn {
+namespace tc {
+
+// --------------------------------------------------------------------------- //
+// PTX wrappers
+// --------------------------------------------------------------------------- //
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+      printf("stgcn_b200: mbarrier timeout (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, issued by one thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 (1024 B)
+//   [46,48) version = 1 | [49,52) base offset = 0 (all starts are 1024-B-atom aligned + k*32 B)
+//   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// --------------------------------------------------------------------------- //
+// operand preparation
+// --------------------------------------------------------------------------- //
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// temporal conv weight (c_out, c_in, G) fp32 -> Wp[plane][tap][c_out][c_in] bf16 (hi, lo)
+__global__ void k_pack_tcn_w_bf16(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wp, int c_out,
+                                  int c_in, int G) {
+  const long long total = (long long)G * c_out * c_in;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = (int)(i % c_in);
+  const long long r = i / c_in;
+  const int co = (int)(r % c_out);
+  const int j = (int)(r / c_out);
+  __nv_bfloat16 hi, lo;
+  split_bf16(w[((long long)co * c_in + ci) * G + j], hi, lo);
+  wp[i] = hi;
+  wp[total + i] = lo;
+}
+
+// --------------------------------------------------------------------------- //
+// Temporal (Gamma x 1, stride 1) convolution as a TMA-fed tcgen05 implicit GEMM, fused with
+// bias + LayerNorm(C,V) + residual + ReLU  (stgcn.py:154-161,193).
+//
+//   out[n,t,v,:] = relu( LN_{C,V}( sum_j Wt[:, :, j] u[n, t+j-pad, v, :] + bt ) + res[n,t,v,:] )
+//
+// One CTA = 8 consecutive output frames of one trial = two 128-row UMMA tiles (4 frames x 32
+// padded joint rows each), all C output channels (so the LayerNorm statistics of a frame are
+// CTA-local: one epilogue warp owns one frame, one lane one joint).  The input window of 16
+// frames is staged ONCE per 64-channel K chunk; every temporal tap reuses it through a
+// descriptor whose start address is shifted by whole frames (32 rows = 4096 B, swizzle-atom
+// aligned).  TMA zero-fills joints 25..31 and frames outside [0,T): the conv's zero padding.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM -> registers -> HBM).
+// --------------------------------------------------------------------------- //
+constexpr int kFrameRows = 32;
+constexpr int kOutFrames = 8;
+constexpr int kInFrames = 16;
+constexpr int kABytes = kInFrames * kFrameRows * 128;  // 65536: one plane, one 64-channel chunk
+constexpr int kTcnThreads = 192;
+
+template <int C>
+struct TcnCfg {
+  static constexpr int kBBytes = C * 128;                               // [C rows][64 ch] bf16
+  static constexpr int kStages = C == 64 ? 8 : (C == 128 ? 5 : 3);
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmem = 2 * kABytes + kStages * kBBytes + kBarBytes + 1024;  // + align slack
+  static constexpr int kTmemCols = 2 * C < 32 ? 32 : 2 * C;             // 128 / 256 / 512 (powers of two)
+};
+
+struct TcnTcParams {
+  int T, V, G, pad;
+  int planes;           // 1: bf16, 2: bf16x3
+  const float *bias;    // [C]
+  const float *n_w;     // [C][V]
+  const float *n_b;
+  const float *res;     // fp32 [rows][C] or nullptr
+  float *out;           // fp32 [rows][C]
+  float eps;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTcnThreads, 1)
+    k_tcn_tc(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_w,
+             const TcnTcParams p) {
+  using Cfg = TcnCfg<C>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + 2 * kABytes;
+  const uint32_t sBar = sB + S * Cfg::kBBytes;
+  // barrier map (8 B each): fullA[2] emptyA[2] fullB[S] emptyB[S] tmem_full, then tmem ptr
+  const uint32_t bFullA = sBar, bEmptyA = sBar + 16, bFullB = sBar + 32, bEmptyB = bFullB + 8 * S;
+  const uint32_t bTmemFull = bEmptyB + 8 * S;
+  const uint32_t sTmemPtr = bTmemFull + 8;
+  uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * kOutFrames;
+  const int KC = C / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_u);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bFullA + 8 * i, 1);
+      mbar_init(bEmptyA + 8 * i, 1);
+    }
+    for (int i = 0; i < S; ++i) {
+      mbar_init(bFullB + 8 * i, 1);
+      mbar_init(bEmptyB + 8 * i, 1);
+    }
+    mbar_init(bTmemFull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(sTmemPtr, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // The K loop is a flat schedule of "A stages" (one plane of one 64-channel chunk of the
+  // 16-frame input window), each followed by the weight tiles multiplied against it:
+  //   A = hi plane: for every tap j: B = hi(j), [B = lo(j)]      (hi*hi, hi*lo)
+  //   A = lo plane: for every tap j: B = hi(j)                   (lo*hi)
+  if (warp == 0) {
+    if (lane == 0) {
+      int a_it = 0, b_it = 0;
+      for (int kc = 0; kc < KC; ++kc) {
+        for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
+          const int as = a_it & 1;
+          mbar_wait(bEmptyA + 8 * as, ((a_it >> 1) & 1) ^ 1);
+          mbar_expect_tx(bFullA + 8 * as, kABytes);
+          tma_load_5d(sA + as * kABytes, &tm_u, bFullA + 8 * as, kc * 64, 0, t0 - p.pad, n, ap);
+          const int nb = (ap == 0) ? p.planes : 1;
+          for (int j = 0; j < p.G; ++j) {
+            for (int bp = 0; bp < nb; ++bp, ++b_it) {
+              const int bs = b_it % S;
+              mbar_wait(bEmptyB + 8 * bs, ((b_it / S) & 1) ^ 1);
+              mbar_expect_tx(bFullB + 8 * bs, Cfg::kBBytes);
+              tma_load_4d(sB + bs * Cfg::kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, j, bp);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, C);
+      int a_it = 0, b_it = 0;
+      uint32_t acc = 0;
+      for (int kc = 0; kc < KC; ++kc) {
+        for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
+          const int as = a_it & 1;
+          mbar_wait(bFullA + 8 * as, (a_it >> 1) & 1);
+          tc_fence_after();
+          const int nb = (ap == 0) ? p.planes : 1;
+          for (int j = 0; j < p.G; ++j) {
+            for (int bp = 0; bp < nb; ++bp, ++b_it) {
+              const int bs = b_it % S;
+              mbar_wait(bFullB + 8 * bs, (b_it / S) & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                const uint32_t a0 = sA + as * kABytes + (4 * m + j) * (kFrameRows * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(tmem_base + m * C, umma_desc_sw128(a0 + k * 32),
+                            umma_desc_sw128(sB + bs * Cfg::kBBytes + k * 32), idesc, acc | (uint32_t)k);
+                }
+              }
+              acc = 1;
+              umma_commit(bEmptyB + 8 * bs);  // frees the weight stage when these MMAs retire
+            }
+          }
+          umma_commit(bEmptyA + 8 * as);      // frees the input-window stage
+        }
+      }
+      umma_commit(bTmemFull);                 // accumulators complete
+    }
+  } else {
+    // ---- epilogue: warp q owns TMEM lanes [32q, 32q+32) = frame q of each tile; lane = joint ----
+    const int q = warp & 3;
+    mbar_wait(bTmemFull, 0);
+    tc_fence_after();
+    const float inv_n = 1.f / (float)(p.V * C), inv_nm1 = 1.f / (float)(p.V * C - 1);
+#pragma unroll 1
+    for (int m = 0; m < 2; ++m) {
+      const int t = t0 + 4 * m + q;
+      const bool row_ok = (t < p.T) && (lane < p.V);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * C);
+      const long long row = ((long long)n * p.T + t) * p.V + lane;
+      float v[32];
+      float s = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < C; cb += 32) {
+        tmem_ld32(taddr + cb, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s += v[i] + __ldg(p.bias + cb + i);
+      }
+      const float mean = warp_sum(row_ok ? s : 0.f) * inv_n;
+      float ss = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < C; cb += 32) {
+        tmem_ld32(taddr + cb, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float d = v[i] + __ldg(p.bias + cb + i) - mean;
+          ss = fmaf(d, d, ss);
+        }
+      }
+      const float rstd = 1.f / sqrtf(warp_sum(row_ok ? ss : 0.f) * inv_nm1 + p.eps);
+#pragma unroll 1
+      for (int cb = 0; cb < C; cb += 32) {
+        tmem_ld32(taddr + cb, v);
+        if (row_ok) {
+          float *dst = p.out + row * C + cb;
+          const float *rs = p.res ? p.res + row * C + cb : nullptr;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = cb + i + e;
+              o[e] = (v[i + e] + __ldg(p.bias + c) - mean) * rstd * __ldg(p.n_w + c * p.V + lane) +
+                     __ldg(p.n_b + c * p.V + lane);
+            }
+            if (rs) {
+              const float4 r4 = *reinterpret_cast<const float4 *>(rs + i);
+              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+            }
+            *reinterpret_cast<float4 *>(dst + i) =
+                make_float4(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f), fmaxf(o[2], 0.f), fmaxf(o[3], 0.f));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// --------------------------------------------------------------------------- //
+// host side: tensor maps
+// --------------------------------------------------------------------------- //
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor, `rank` dims (innermost first), 128B swizzle, zero OOB fill
+inline int make_tmap_bf16(CUtensorMap *m, const void *base, int rank, const uint64_t *dims,
+                          const uint64_t *strides_bytes /* rank-1 */, const uint32_t *box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled is unavailable");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base),
+                  reinterpret_cast<const cuuint64_t *>(dims), reinterpret_cast<const cuuint64_t *>(strides_bytes),
+                  reinterpret_cast<const cuuint32_t *>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+inline bool tcn_tc_supported(int C, int V, int G, int stride) {
+  return (C == 64 || C == 128 || C == 256) && V <= kFrameRows && G <= 9 && (G & 1) && stride == 1;
+}
+
+// u planes: bf16 [planes][N][T][V][C]; wp: bf16 [2][G][C][C]
+template <int C>
+int launch_tcn_tc_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTcParams &p, int N,
+                    cudaStream_t st) {
+  CUtensorMap tm_u, tm_w;
+  const uint64_t ud[5] = {(uint64_t)C, (uint64_t)p.V, (uint64_t)p.T, (uint64_t)N, (uint64_t)p.planes};
+  const uint64_t us[4] = {(uint64_t)C * 2, (uint64_t)p.V * C * 2, (uint64_t)p.T * p.V * C * 2,
+                          (uint64_t)N * p.T * p.V * C * 2};
+  const uint32_t ub[5] = {64, kFrameRows, kInFrames, 1, 1};
+  if (make_tmap_bf16(&tm_u, u, 5, ud, us, ub)) return 1;
+  const uint64_t wd[4] = {(uint64_t)C, (uint64_t)C, (uint64_t)p.G, 2};
+  const uint64_t wst[3] = {(uint64_t)C * 2, (uint64_t)C * C * 2, (uint64_t)p.G * C * C * 2};
+  const uint32_t wb[4] = {64, (uint32_t)C, 1, 1};
+  if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_tcn_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcnCfg<C>::kSmem));
+  dim3 grid((p.T + kOutFrames - 1) / kOutFrames, N);
+  k_tcn_tc<C><<<grid, kTcnThreads, TcnCfg<C>::kSmem, st>>>(tm_u, tm_w, p);
+  return 0;
+}
+
+inline int launch_tcn_tc(int C, const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTcParams &p, int N,
+                         cudaStream_t st) {
+  switch (C) {
+    case 64: return launch_tcn_tc_c<64>(u, wp, p, N, st);
+    case 128: return launch_tcn_tc_c<128>(u, wp, p, N, st);
+    case 256: return launch_tcn_tc_c<256>(u, wp, p, N, st);
+  }
+  return fail("tcn tensor-core kernel: unsupported channel count %d", C);
+}
+
+}  // namespace tc
+}  // namespace stgcn

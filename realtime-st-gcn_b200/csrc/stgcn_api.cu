@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
 
 using namespace stgcn;
 
@@ -116,16 +117,20 @@ int check_layer(const stgcn_layer_desc &d) {
 // x [N*T*V, c_in] -> out [N*T_out*V, c_out].  Scratch comes from `ws` (released on return).
 int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        int N, int T, Bump &ws, cudaStream_t st) {
-  (void)math;
   if (check_layer(d)) return 1;
   const size_t mark = ws.mark();
   const int T_out = (T - 1) / d.stride + 1;
   const long long rows = (long long)N * T * V, rows_out = (long long)N * T_out * V;
   const bool bn = d.norm == STGCN_NORM_BATCHNORM;
+  // tensor-core temporal stage: LayerNorm, stride 1, identity/no residual, C in {64,128,256}
+  const bool tc_tcn = math != STGCN_MATH_FP32 && !bn && d.residual != STGCN_RES_CONV &&
+                      tc::tcn_tc_supported(d.c_out, V, d.kernel, d.stride);
+  const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
 
   AdjCsr csr;
   if (build_csr(d.a_eff, d.a_per_sample, N, K, V, d.c_out, ws, csr, st)) return 1;
-  float *u = ws.take<float>((size_t)rows * d.c_out);
+  float *u = tc_tcn ? nullptr : ws.take<float>((size_t)rows * d.c_out);
+  __nv_bfloat16 *u16 = tc_tcn ? ws.take<__nv_bfloat16>((size_t)planes * rows * d.c_out) : nullptr;
   double *sums = bn ? ws.take<double>((size_t)4 * d.c_out) : nullptr;
   {
     const size_t m2 = ws.mark();
@@ -145,6 +150,10 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       a.eps = kEps;
       if (!bn) {
         a.norm_a = 1; a.na_w = d.n1_w; a.na_b = d.n1_b; a.relu_out = 1; a.out = u;
+        if (tc_tcn) {
+          a.out_hi = u16;
+          a.out_lo = planes == 2 ? u16 + (size_t)rows * d.c_out : nullptr;
+        }
         if (launch_frame(a, st)) return 1;
       } else {
         a.out = z;
@@ -160,6 +169,30 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       }
     }
     ws.release(m2);
+  }
+  if (tc_tcn) {
+    const long long nw = (long long)d.c_out * d.c_out * d.kernel;
+    __nv_bfloat16 *wp16 = ws.take<__nv_bfloat16>((size_t)2 * nw);
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
+      {
+        ProfScope ps(KC_MISC, st);
+        tc::k_pack_tcn_w_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.tcn_w, wp16, d.c_out, d.c_out, d.kernel);
+        STGCN_LAUNCH_OK();
+      }
+      tc::TcnTcParams p{};
+      p.T = T; p.V = V; p.G = d.kernel; p.pad = (d.kernel - 1) / 2;
+      p.planes = planes;
+      p.bias = d.tcn_b; p.n_w = d.n2_w; p.n_b = d.n2_b;
+      p.res = d.residual == STGCN_RES_IDENTITY ? x : nullptr;
+      p.out = out;
+      p.eps = kEps;
+      ProfScope ps(KC_GEMM_TCN, st);
+      if (tc::launch_tcn_tc(d.c_out, u16, wp16, p, N, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    ws.release(mark);
+    return 0;
   }
   float *wp = ws.take<float>((size_t)d.c_out * d.c_out * d.kernel);
   float *q = ws.take<float>((size_t)rows_out * d.c_out);

@@ -257,3 +257,70 @@ def test_rt_batchnorm_rejected(pkg, syn, cuda):
     m.prepare_benchmark({})
     with pytest.raises(RuntimeError, match='LayerNorm'):
         m(torch.zeros(1, 3, 1, 25, device=cuda))
+
+
+# ------------------------------------------------------------------ tensor-core (tcgen05) arithmetic
+BF16_TOL = 3e-2      # stated bf16 tolerance (single-pass bf16 operands, fp32 accumulate/statistics)
+
+
+def _layer_case(cuda, c, stride, residual, v_graph, n, t, seed):
+    from importlib import import_module
+    pk = import_module('realtime-st-gcn_b200')
+    Layer = import_module('realtime-st-gcn_b200.models.stgcn').StgcnLayer
+    from oracle import build_adjacency
+    g = pk.skeletons.skeleton(v_graph)
+    v = g['num_node']
+    A = torch.tensor(build_adjacency(**g), dtype=torch.float32)
+    gen = torch.Generator().manual_seed(seed)
+    A = A * (torch.rand(3, v, v, generator=gen) + 0.5)
+    layer = Layer(c, c, (9, v), 3, v, stride=stride, residual=residual)
+    sd = pk.synthetic.synth_state_dict(layer.state_dict(), seed)
+    layer.load_state_dict(sd)
+    x = torch.randn(n, c, t, v, generator=gen)
+    ref = O.stgcn_layer(x, A, sd, stride=stride, residual=residual)
+    return layer.to(cuda).eval(), x.to(cuda), A.to(cuda), ref
+
+
+@pytest.mark.parametrize('c,residual,graph,n,t', [
+    (64, True, 'pku-mmd', 2, 20), (64, False, 'pku-mmd', 1, 8), (128, True, 'pku-mmd', 2, 37),
+    (256, True, 'pku-mmd', 1, 19), (64, True, 'imu_fogit_ABCD', 3, 11), (128, True, 'pku-mmd', 1, 3)])
+def test_stgcn_layer_tensor_core(cuda, c, residual, graph, n, t):
+    """tcgen05 temporal stage (bf16x3 split = fp32 parity; bf16 = stated tolerance), ragged T
+    (tail tiles, T < one tile), 7- and 25-joint graphs, with and without residual."""
+    layer, x, A, ref = _layer_case(cuda, c, 1, residual, graph, n, t, 100 + c + t)
+    exact = layer(x, A, math='fp32')
+    assert rel_err(exact, ref) < 1e-5
+    y3 = layer(x, A, math='bf16x3')
+    assert rel_err(y3, ref) < TOL, rel_err(y3, ref)
+    y1 = layer(x, A, math='bf16')
+    assert rel_err(y1, ref) < BF16_TOL, rel_err(y1, ref)
+    assert rel_err(y1, ref) > 1e-5       # really ran reduced precision
+
+
+def test_stgcn_layer_golden_tensor_core(cuda):
+    from importlib import import_module
+    Layer = import_module('realtime-st-gcn_b200.models.stgcn').StgcnLayer
+    a, w = load_golden('stgcn_layer_ln_64')
+    layer = Layer(64, 64, (9, 25), 3, 25).to(cuda)
+    layer.load_state_dict(w)
+    y = layer.eval()(a['x'].to(cuda), a['A'].to(cuda), math='bf16x3')
+    assert rel_err(y, a['y']) < TOL
+
+
+@pytest.mark.parametrize('math,tol', [('bf16x3', TOL), ('bf16', BF16_TOL)])
+def test_stgcn_model_c1_tensor_core(pkg, syn, cuda, math, tol):
+    """BASELINE config 1 on the tensor-core path vs the reference's fp32 output."""
+    a, _ = load_golden('stgcn_model_c1_ln')
+    cfg = syn.arch_config('st-gcn')
+    cfg['math'] = math
+    m = pkg.Stgcn(**cfg)
+    m.load_state_dict(syn.synth_state_dict(m.state_dict(), int(a['seeds'][0])))
+    m = m.to(cuda).eval()
+    x = syn.synth_input((1, 3, 300, 25), int(a['seeds'][1])).to(cuda)
+    logits, feats = m(x, return_features=True)
+    e_f = rel_err(feats[:, :, [0, 37, 74]], a['features_t0_t37_t74'])
+    e_l = rel_err(logits, a['logits'])
+    print("math=%s  rel_err features %.3e  logits %.3e" % (math, e_f, e_l))
+    assert e_f < tol and e_l < tol
+    if math == 'bf16':
+        assert logits.argmax(1).item() == a['logits'].argmax(1).item()
