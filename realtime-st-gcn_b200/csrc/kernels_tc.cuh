@@ -378,6 +378,340 @@ __global__ void __launch_bounds__(kTcnThreads, 1)
 }
 
 // --------------------------------------------------------------------------- //
+// Graph-convolution stage on tensor cores, fused with LayerNorm(C,V) + ReLU
+// (tgcn.py:70-79 + stgcn.py:152-153):
+//
+//   u[n,t,w,:] = relu( LN_{C,V}( sum_k sum_v A[k,v,w] * (Wg_k x[n,t,v,:] + bg_k) ) )
+//
+// The 1x1 feature transform and the V x V adjacency contraction act on different indices, so
+// they commute: the contraction is applied FIRST, on the C_in-channel input tile staged in
+// shared memory (A is a tree adjacency: ~1 non-zero per (k,w), kept in CSR, dense A still
+// works), producing xa_k[(t,w), ci] = sum_v A[k,v,w] x[(t,v), ci]; then ONE GEMM with
+// K = 3*C_in gives z directly:  z[(t,w), c] = sum_k sum_ci xa_k[(t,w),ci] Wg[k*C_out+c, ci].
+// That keeps the whole z tile (8 frames x C_out) in TMEM, so the LayerNorm statistics are one
+// warp-shuffle reduction per frame in the epilogue, and it needs no 3*C_out-wide intermediate.
+// The bias term flows through A: bz[w,c] = sum_k bg[k*C_out+c] * colsum_k[w] (precomputed).
+//
+// Warp roles: 0 = TMA producer (fp32 input tile + bf16 weight tiles), 1 = MMA issuer,
+// 2..9 = transform warps (contraction + bf16 hi/lo split -> swizzled UMMA A operand in smem),
+// of which 2..5 then run the epilogue.
+// --------------------------------------------------------------------------- //
+constexpr int kGcnThreads = 320;
+constexpr int kGcnXform = 8;                 // transform warps
+constexpr int kGcnAStage = 2 * 128 * 128;    // 2 tiles x 128 rows x 128 B = 32768
+constexpr int kGcnARing = 3;
+constexpr int kGcnXsBytes = kOutFrames * kFrameRows * 64 * 4;  // 65536 (V <= 32)
+
+template <int CO>
+struct GcnCfg {
+  static constexpr int kBBytes = CO * 128;
+  static constexpr int kStages = CO == 256 ? 2 : 4;
+  static constexpr int kSmem = kGcnARing * kGcnAStage + kGcnXsBytes + kStages * kBBytes + 256 + 1024;
+  static constexpr int kTmemCols = 2 * CO;
+};
+
+struct GcnTcParams {
+  int T, V, K, Cin;
+  int planes;
+  const int *csr_ptr;   // [K*V + 1], (k,w)-major
+  const int *csr_v;     // source joint of each entry
+  const float *csr_a;   // A[k,v,w]
+  const float *bzT;     // [CO][V] bias through the adjacency
+  const float *n_w, *n_b;
+  __nv_bfloat16 *out_hi, *out_lo;   // [rows][CO] planes (tensor-core temporal stage) or null
+  float *out_f32;                   // [rows][CO] (CUDA-core temporal stage) or null
+  float eps;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int CO>
+__global__ void __launch_bounds__(kGcnThreads, 1)
+    k_gcn_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+             const GcnTcParams p) {
+  using Cfg = GcnCfg<CO>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sA = smem_base;
+  const uint32_t sXs = sA + kGcnARing * kGcnAStage;
+  const uint32_t sB = sXs + kGcnXsBytes;
+  const uint32_t sBar = sB + S * Cfg::kBBytes;
+  const uint32_t bXsFull = sBar, bXsEmpty = sBar + 8;
+  const uint32_t bAFull = sBar + 16, bAEmpty = bAFull + 8 * kGcnARing;
+  const uint32_t bFullB = bAEmpty + 8 * kGcnARing, bEmptyB = bFullB + 8 * S;
+  const uint32_t bTmemFull = bEmptyB + 8 * S;
+  const uint32_t sTmemPtr = bTmemFull + 8;
+  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
+  const float *xs = reinterpret_cast<const float *>(gen_base + (sXs - smem_base));
+  uint8_t *a_gen = gen_base;  // A ring starts at smem_base
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * kOutFrames;
+  const int KC = p.Cin / 64;
+  const uint32_t xs_bytes = (uint32_t)(kOutFrames * p.V * 64 * 4);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    mbar_init(bXsFull, 1);
+    mbar_init(bXsEmpty, kGcnXform);
+    for (int i = 0; i < kGcnARing; ++i) {
+      mbar_init(bAFull + 8 * i, kGcnXform);
+      mbar_init(bAEmpty + 8 * i, 1);
+    }
+    for (int i = 0; i < S; ++i) {
+      mbar_init(bFullB + 8 * i, 1);
+      mbar_init(bEmptyB + 8 * i, 1);
+    }
+    mbar_init(bTmemFull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(sTmemPtr, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int b_it = 0;
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(bXsEmpty, (kc & 1) ^ 1);
+        mbar_expect_tx(bXsFull, xs_bytes);
+        tma_load_4d(sXs, &tm_x, bXsFull, kc * 64, 0, t0, n);
+        for (int k = 0; k < p.K; ++k)
+          for (int ap = 0; ap < p.planes; ++ap) {
+            const int nb = (ap == 0) ? p.planes : 1;
+            for (int bp = 0; bp < nb; ++bp, ++b_it) {
+              const int bs = b_it % S;
+              mbar_wait(bEmptyB + 8 * bs, ((b_it / S) & 1) ^ 1);
+              mbar_expect_tx(bFullB + 8 * bs, Cfg::kBBytes);
+              tma_load_4d(sB + bs * Cfg::kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, k, bp);
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, CO);
+      int a_it = 0, b_it = 0;
+      uint32_t acc = 0;
+      for (int kc = 0; kc < KC; ++kc)
+        for (int k = 0; k < p.K; ++k)
+          for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
+            const int as = a_it % kGcnARing;
+            mbar_wait(bAFull + 8 * as, (a_it / kGcnARing) & 1);
+            tc_fence_after();
+            const int nb = (ap == 0) ? p.planes : 1;
+            for (int bp = 0; bp < nb; ++bp, ++b_it) {
+              const int bs = b_it % S;
+              mbar_wait(bFullB + 8 * bs, (b_it / S) & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16(tmem_base + m * CO, umma_desc_sw128(sA + as * kGcnAStage + m * 16384 + kk * 32),
+                            umma_desc_sw128(sB + bs * Cfg::kBBytes + kk * 32), idesc, acc | (uint32_t)kk);
+              }
+              acc = 1;
+              umma_commit(bEmptyB + 8 * bs);
+            }
+            umma_commit(bAEmpty + 8 * as);
+          }
+      umma_commit(bTmemFull);
+    }
+  } else {
+    // ---- transform warps: xa_k = A_k-contraction of the staged fp32 tile -> bf16 plane ----
+    const int tw = warp - 2;
+    int a_it = 0;
+    for (int kc = 0; kc < KC; ++kc) {
+      mbar_wait(bXsFull, kc & 1);
+      for (int k = 0; k < p.K; ++k)
+        for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
+          const int as = a_it % kGcnARing;
+          mbar_wait(bAEmpty + 8 * as, ((a_it / kGcnARing) & 1) ^ 1);
+          uint8_t *stage = a_gen + as * kGcnAStage;
+          for (int i = tw; i < kOutFrames * p.V; i += kGcnXform) {
+            const int f = i / p.V, w = i - f * p.V;
+            const int e1 = __ldg(p.csr_ptr + k * p.V + w + 1);
+            float ax = 0.f, ay = 0.f;
+            for (int e = __ldg(p.csr_ptr + k * p.V + w); e < e1; ++e) {
+              const float a = __ldg(p.csr_a + e);
+              const float2 xv =
+                  *reinterpret_cast<const float2 *>(xs + (f * p.V + __ldg(p.csr_v + e)) * 64 + 2 * lane);
+              ax = fmaf(a, xv.x, ax);
+              ay = fmaf(a, xv.y, ay);
+            }
+            __nv_bfloat16 hx, lx, hy, ly;
+            split_bf16(ax, hx, lx);
+            split_bf16(ay, hy, ly);
+            __nv_bfloat162 pk = ap == 0 ? __nv_bfloat162(hx, hy) : __nv_bfloat162(lx, ly);
+            const int R = f * kFrameRows + w;                 // row in the 256-row stage
+            const int chunk = (lane >> 2) ^ (R & 7);          // 128B swizzle: 16B chunk ^ (row % 8)
+            *reinterpret_cast<__nv_bfloat162 *>(stage + R * 128 + chunk * 16 + (lane & 3) * 4) = pk;
+          }
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bAFull + 8 * as);
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bXsEmpty);
+    }
+    if (warp < 6) {
+      // ---- epilogue (warps 2..5): one frame per warp, one joint per lane ----
+      const int q = warp & 3;
+      mbar_wait(bTmemFull, 0);
+      tc_fence_after();
+      const float inv_n = 1.f / (float)(p.V * CO), inv_nm1 = 1.f / (float)(p.V * CO - 1);
+      const int lv = lane < p.V ? lane : 0;
+#pragma unroll 1
+      for (int m = 0; m < 2; ++m) {
+        const int t = t0 + 4 * m + q;
+        const bool row_ok = (t < p.T) && (lane < p.V);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * CO);
+        const long long row = ((long long)n * p.T + t) * p.V + lane;
+        float v[32];
+        float s = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < CO; cb += 32) {
+          tmem_ld32(taddr + cb, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s += v[i] + __ldg(p.bzT + (cb + i) * p.V + lv);
+        }
+        const float mean = warp_sum(row_ok ? s : 0.f) * inv_n;
+        float ss = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < CO; cb += 32) {
+          tmem_ld32(taddr + cb, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = v[i] + __ldg(p.bzT + (cb + i) * p.V + lv) - mean;
+            ss = fmaf(d, d, ss);
+          }
+        }
+        const float rstd = 1.f / sqrtf(warp_sum(row_ok ? ss : 0.f) * inv_nm1 + p.eps);
+#pragma unroll 1
+        for (int cb = 0; cb < CO; cb += 32) {
+          tmem_ld32(taddr + cb, v);
+          if (row_ok) {
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = cb + i;
+              const float y = (v[i] + __ldg(p.bzT + c * p.V + lane) - mean) * rstd * __ldg(p.n_w + c * p.V + lane) +
+                              __ldg(p.n_b + c * p.V + lane);
+              o[i] = fmaxf(y, 0.f);
+            }
+            if (p.out_f32) {
+              float *dst = p.out_f32 + row * CO + cb;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4 *>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+            }
+            if (p.out_hi) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(o[2 * i], h0, l0);
+                split_bf16(o[2 * i + 1], h1, l1);
+                __nv_bfloat162 hh(h0, h1), ll(l0, l1);
+                hi[i] = *reinterpret_cast<uint32_t *>(&hh);
+                lo[i] = *reinterpret_cast<uint32_t *>(&ll);
+              }
+              uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + row * CO + cb);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              if (p.out_lo) {
+                uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + row * CO + cb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// adjacency CSR ordered by (k, w): ptr[k*V + w] .. ptr[k*V + w + 1] -> (v, A[k,v,w]); and the bias
+// that flows through A, transposed for coalesced epilogue reads: bzT[c][w].
+__global__ void k_build_adj_csr_kw(const float *__restrict__ A, int K, int V, int *__restrict__ ptr,
+                                   int *__restrict__ vidx, float *__restrict__ val) {
+  extern __shared__ int s_cnt[];  // K*V + 1
+  const int P = K * V;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const int k = i / V, w = i - k * V;
+    int c = 0;
+    for (int v = 0; v < V; ++v) c += (A[((long long)k * V + v) * V + w] != 0.f);
+    s_cnt[i] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < P; ++i) {
+      int c = s_cnt[i];
+      s_cnt[i] = run;
+      run += c;
+    }
+    s_cnt[P] = run;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= P; i += blockDim.x) ptr[i] = s_cnt[i];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const int k = i / V, w = i - k * V;
+    int at = s_cnt[i];
+    for (int v = 0; v < V; ++v) {
+      const float x = A[((long long)k * V + v) * V + w];
+      if (x != 0.f) {
+        vidx[at] = v;
+        val[at] = x;
+        ++at;
+      }
+    }
+  }
+}
+
+__global__ void k_bias_through_adj(const float *__restrict__ A, const float *__restrict__ bg, int K, int V,
+                                   int CO, float *__restrict__ bzT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= CO * V) return;
+  const int c = i / V, w = i - c * V;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float col = 0.f;
+    for (int v = 0; v < V; ++v) col += A[((long long)k * V + v) * V + w];
+    s = fmaf(bg[k * CO + c], col, s);
+  }
+  bzT[i] = s;
+}
+
+// 1x1 weights (K*c_out, c_in) fp32 -> bf16 planes [2][K][c_out][c_in] (same order, split only)
+__global__ void k_split_bf16(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wp, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  __nv_bfloat16 hi, lo;
+  split_bf16(w[i], hi, lo);
+  wp[i] = hi;
+  wp[total + i] = lo;
+}
+
+// --------------------------------------------------------------------------- //
 // host side: tensor maps
 // --------------------------------------------------------------------------- //
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -410,6 +744,53 @@ inline int make_tmap_bf16(CUtensorMap *m, const void *base, int rank, const uint
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
+}
+
+inline int make_tmap_f32_noswizzle(CUtensorMap *m, const void *base, int rank, const uint64_t *dims,
+                                   const uint64_t *strides_bytes, const uint32_t *box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled is unavailable");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base),
+                  reinterpret_cast<const cuuint64_t *>(dims), reinterpret_cast<const cuuint64_t *>(strides_bytes),
+                  reinterpret_cast<const cuuint32_t *>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+inline bool gcn_tc_supported(int c_in, int c_out, int V, int K) {
+  return (c_out == 64 || c_out == 128 || c_out == 256) && c_in % 64 == 0 && c_in >= 64 && V <= kFrameRows &&
+         V >= 2 && K >= 1;
+}
+
+// x: fp32 [N][T][V][c_in]; wp: bf16 [2][K][c_out][c_in]
+template <int CO>
+int launch_gcn_tc_c(const float *x, const __nv_bfloat16 *wp, const GcnTcParams &p, int N, cudaStream_t st) {
+  CUtensorMap tm_x, tm_w;
+  const uint64_t xd[4] = {(uint64_t)p.Cin, (uint64_t)p.V, (uint64_t)p.T, (uint64_t)N};
+  const uint64_t xst[3] = {(uint64_t)p.Cin * 4, (uint64_t)p.V * p.Cin * 4, (uint64_t)p.T * p.V * p.Cin * 4};
+  const uint32_t xb[4] = {64, (uint32_t)p.V, kOutFrames, 1};
+  if (make_tmap_f32_noswizzle(&tm_x, x, 4, xd, xst, xb)) return 1;
+  const uint64_t wd[4] = {(uint64_t)p.Cin, (uint64_t)CO, (uint64_t)p.K, 2};
+  const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)p.K * CO * p.Cin * 2};
+  const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
+  if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn_tc<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcnCfg<CO>::kSmem));
+  dim3 grid((p.T + kOutFrames - 1) / kOutFrames, N);
+  k_gcn_tc<CO><<<grid, kGcnThreads, GcnCfg<CO>::kSmem, st>>>(tm_x, tm_w, p);
+  return 0;
+}
+
+inline int launch_gcn_tc(int CO, const float *x, const __nv_bfloat16 *wp, const GcnTcParams &p, int N,
+                         cudaStream_t st) {
+  switch (CO) {
+    case 64: return launch_gcn_tc_c<64>(x, wp, p, N, st);
+    case 128: return launch_gcn_tc_c<128>(x, wp, p, N, st);
+    case 256: return launch_gcn_tc_c<256>(x, wp, p, N, st);
+  }
+  return fail("gcn tensor-core kernel: unsupported channel count %d", CO);
 }
 
 inline bool tcn_tc_supported(int C, int V, int G, int stride) {

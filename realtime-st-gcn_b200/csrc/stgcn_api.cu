@@ -127,12 +127,48 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
                       tc::tcn_tc_supported(d.c_out, V, d.kernel, d.stride);
   const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
 
-  AdjCsr csr;
-  if (build_csr(d.a_eff, d.a_per_sample, N, K, V, d.c_out, ws, csr, st)) return 1;
+  // tensor-core graph-convolution stage: LayerNorm, shared adjacency, C_in % 64 == 0
+  const bool tc_gcn = math != STGCN_MATH_FP32 && !bn && !d.a_per_sample &&
+                      tc::gcn_tc_supported(d.c_in, d.c_out, V, K);
+
   float *u = tc_tcn ? nullptr : ws.take<float>((size_t)rows * d.c_out);
   __nv_bfloat16 *u16 = tc_tcn ? ws.take<__nv_bfloat16>((size_t)planes * rows * d.c_out) : nullptr;
+  __nv_bfloat16 *u16_lo = (tc_tcn && planes == 2 && u16) ? u16 + (size_t)rows * d.c_out : nullptr;
   double *sums = bn ? ws.take<double>((size_t)4 * d.c_out) : nullptr;
-  {
+  if (tc_gcn) {
+    const size_t m2 = ws.mark();
+    const long long nw = (long long)K * d.c_out * d.c_in;
+    int *kw_ptr = ws.take<int>((size_t)K * V + 1);
+    int *kw_v = ws.take<int>((size_t)K * V * V);
+    float *kw_a = ws.take<float>((size_t)K * V * V);
+    float *bzT = ws.take<float>((size_t)d.c_out * V);
+    __nv_bfloat16 *wg16 = ws.take<__nv_bfloat16>((size_t)2 * nw);
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
+      {
+        ProfScope ps(KC_MISC, st);
+        tc::k_build_adj_csr_kw<<<1, 128, (K * V + 1) * sizeof(int), st>>>(d.a_eff, K, V, kw_ptr, kw_v, kw_a);
+        STGCN_LAUNCH_OK();
+        tc::k_bias_through_adj<<<cdiv((long long)d.c_out * V, 256), 256, 0, st>>>(d.a_eff, d.gcn_b, K, V,
+                                                                                  d.c_out, bzT);
+        STGCN_LAUNCH_OK();
+        tc::k_split_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.gcn_w, wg16, nw);
+        STGCN_LAUNCH_OK();
+      }
+      tc::GcnTcParams g{};
+      g.T = T; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
+      g.csr_ptr = kw_ptr; g.csr_v = kw_v; g.csr_a = kw_a; g.bzT = bzT;
+      g.n_w = d.n1_w; g.n_b = d.n1_b;
+      g.out_hi = u16; g.out_lo = u16_lo; g.out_f32 = u;
+      g.eps = kEps;
+      ProfScope ps(KC_GEMM_1X1, st);
+      if (tc::launch_gcn_tc(d.c_out, x, wg16, g, N, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    ws.release(m2);
+  } else {
+    AdjCsr csr;
+    if (build_csr(d.a_eff, d.a_per_sample, N, K, V, d.c_out, ws, csr, st)) return 1;
     const size_t m2 = ws.mark();
     float *y = ws.take<float>((size_t)rows * K * d.c_out);
     float *z = bn ? ws.take<float>((size_t)rows * d.c_out) : nullptr;
@@ -150,10 +186,8 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       a.eps = kEps;
       if (!bn) {
         a.norm_a = 1; a.na_w = d.n1_w; a.na_b = d.n1_b; a.relu_out = 1; a.out = u;
-        if (tc_tcn) {
-          a.out_hi = u16;
-          a.out_lo = planes == 2 ? u16 + (size_t)rows * d.c_out : nullptr;
-        }
+        a.out_hi = u16;
+        a.out_lo = u16_lo;
         if (launch_frame(a, st)) return 1;
       } else {
         a.out = z;

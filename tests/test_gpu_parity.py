@@ -297,6 +297,27 @@ def test_stgcn_layer_tensor_core(cuda, c, residual, graph, n, t):
     assert rel_err(y1, ref) > 1e-5       # really ran reduced precision
 
 
+@pytest.mark.parametrize('ci,co,stride,n,t', [(64, 128, 2, 2, 21), (128, 256, 2, 1, 16), (64, 128, 1, 1, 9)])
+def test_stgcn_layer_tensor_core_conv_residual(pkg, cuda, ci, co, stride, n, t):
+    """Channel-changing / strided layers: tensor-core graph-conv stage feeding the temporal stage."""
+    from importlib import import_module
+    from oracle import build_adjacency
+    Layer = import_module('realtime-st-gcn_b200.models.stgcn').StgcnLayer
+    A = torch.tensor(build_adjacency(**pkg.skeletons.skeleton('pku-mmd')), dtype=torch.float32)
+    gen = torch.Generator().manual_seed(ci + co + t)
+    A = A * (torch.rand(3, 25, 25, generator=gen) + 0.5)
+    layer = Layer(ci, co, (9, 25), 3, 25, stride=stride, residual=True)
+    sd = pkg.synthetic.synth_state_dict(layer.state_dict(), 7)
+    layer.load_state_dict(sd)
+    x = torch.randn(n, ci, t, 25, generator=gen)
+    ref = O.stgcn_layer(x, A, sd, stride=stride, residual=True)
+    layer = layer.to(cuda).eval()
+    y3 = layer(x.to(cuda), A.to(cuda), math='bf16x3')
+    assert y3.shape == ref.shape
+    assert rel_err(y3, ref) < TOL, rel_err(y3, ref)
+    assert rel_err(layer(x.to(cuda), A.to(cuda), math='bf16'), ref) < BF16_TOL
+
+
 def test_stgcn_layer_golden_tensor_core(cuda):
     from importlib import import_module
     Layer = import_module('realtime-st-gcn_b200.models.stgcn').StgcnLayer
