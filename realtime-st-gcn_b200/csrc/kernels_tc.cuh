@@ -39,6 +39,10 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -378,6 +382,238 @@ __global__ void __launch_bounds__(kTcnThreads, 1)
 }
 
 // --------------------------------------------------------------------------- //
+// Temporal convolution v2: persistent, unpadded rows, stride 1 or 2.
+//
+// Measured on B200 (tools/probes/umma_row_offset.cu): a K-major SWIZZLE_128B descriptor whose
+// start address is offset by ANY number of 128-B rows (base_offset field 0) addresses the rows
+// TMA wrote -- the swizzle is a function of the absolute shared-memory address.  So the input
+// window is staged densely (V rows per frame, no padding to 32) and a temporal tap is a shift
+// of V rows.  A 128-row UMMA tile carries FT = floor(128 / V) whole frames (125 of 128 rows
+// useful for V = 25); the few spill rows belong to the next tile and are ignored.
+//
+// Each CTA is persistent over "items" (NT consecutive tiles of one trial).  TMA producer, MMA
+// issuer and epilogue run as a pipeline across items: the producer prefetches the next item's
+// input window / weight tiles while the tensor core works, and (C <= 128) the accumulators
+// are double buffered in TMEM so the LayerNorm epilogue of item i overlaps the MMAs of i+1.
+// Stride 2: even and odd input frames are staged as two dense windows through two tensor maps
+// (frame stride 2), so every tap again reads a contiguous window.
+// --------------------------------------------------------------------------- //
+constexpr int kTcn2Threads = 192;
+
+struct TcnTc2Params {
+  int T_out, V, G, planes;
+  int FT, NT;                 // frames per 128-row tile, tiles per item
+  int groups_per_trial, items;
+  int a_stage_bytes, b_stages;
+  int n_loads;                // TMA loads per A stage (1: stride 1, 2: stride 2 even/odd windows)
+  int load_f0[2];             // first frame of the window relative to the item's first output frame
+  int load_row[2];            // destination row in the stage
+  int load_bytes[2];
+  int tap_row[16];            // first stage row of tap j for tile 0
+  const float *bias, *n_w, *n_b, *res;
+  float *out;
+  float eps;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTcn2Threads, 1)
+    k_tcn_tc2(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__ CUtensorMap tm_u1,
+              const __grid_constant__ CUtensorMap tm_w, const TcnTc2Params p) {
+  constexpr int kBBytes = C * 128;
+  constexpr int TB = (4 * C <= 512) ? 2 : 1;      // TMEM accumulator buffers (2 tiles each)
+  constexpr int kTmemCols = TB * 2 * C;           // 256 / 512 / 512
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int S = p.b_stages;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + 2 * p.a_stage_bytes;
+  const uint32_t sPart = sB + S * kBBytes;                    // float[2][128]
+  const uint32_t sBar = sPart + 1024;
+  const uint32_t bFullA = sBar, bEmptyA = sBar + 16, bTmemFull = sBar + 32, bTmemEmpty = sBar + 48;
+  const uint32_t bFullB = sBar + 64, bEmptyB = bFullB + 8 * S;
+  const uint32_t sTmemPtr = bEmptyB + 8 * S;
+  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
+  float *s_part = reinterpret_cast<float *>(gen_base + (sPart - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = C / 64;
+  const int RT = p.FT * p.V;                      // useful rows per tile
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_u0);
+    tma_prefetch_desc(&tm_u1);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bFullA + 8 * i, 1);
+      mbar_init(bEmptyA + 8 * i, 1);
+      mbar_init(bTmemFull + 8 * i, 1);
+      mbar_init(bTmemEmpty + 8 * i, 4);           // one arrive per epilogue warp
+    }
+    for (int i = 0; i < S; ++i) {
+      mbar_init(bFullB + 8 * i, 1);
+      mbar_init(bEmptyB + 8 * i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(sTmemPtr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int a_it = 0, b_it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.groups_per_trial;
+        const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;   // first output frame
+        for (int kc = 0; kc < KC; ++kc)
+          for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
+            const int as = a_it & 1;
+            mbar_wait(bEmptyA + 8 * as, ((a_it >> 1) & 1) ^ 1);
+            mbar_expect_tx(bFullA + 8 * as, (uint32_t)(p.load_bytes[0] + (p.n_loads > 1 ? p.load_bytes[1] : 0)));
+            tma_load_5d(sA + as * p.a_stage_bytes + p.load_row[0] * 128, &tm_u0, bFullA + 8 * as, kc * 64, 0,
+                        f0 + p.load_f0[0], n, ap);
+            if (p.n_loads > 1)
+              tma_load_5d(sA + as * p.a_stage_bytes + p.load_row[1] * 128, &tm_u1, bFullA + 8 * as, kc * 64, 0,
+                          f0 + p.load_f0[1], n, ap);
+            const int nb = (ap == 0) ? p.planes : 1;
+            for (int j = 0; j < p.G; ++j)
+              for (int bp = 0; bp < nb; ++bp, ++b_it) {
+                const int bs = b_it % S;
+                mbar_wait(bEmptyB + 8 * bs, ((b_it / S) & 1) ^ 1);
+                mbar_expect_tx(bFullB + 8 * bs, kBBytes);
+                tma_load_4d(sB + bs * kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, j, bp);
+              }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, C);
+      int a_it = 0, b_it = 0, it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int buf = it % TB;
+        mbar_wait(bTmemEmpty + 8 * buf, ((it / TB) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * 2 * C;
+        uint32_t acc = 0;
+        for (int kc = 0; kc < KC; ++kc)
+          for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
+            const int as = a_it & 1;
+            mbar_wait(bFullA + 8 * as, (a_it >> 1) & 1);
+            tc_fence_after();
+            const int nb = (ap == 0) ? p.planes : 1;
+            for (int j = 0; j < p.G; ++j)
+              for (int bp = 0; bp < nb; ++bp, ++b_it) {
+                const int bs = b_it % S;
+                mbar_wait(bFullB + 8 * bs, (b_it / S) & 1);
+                tc_fence_after();
+                for (int m = 0; m < p.NT; ++m) {
+                  const uint32_t a0 = sA + as * p.a_stage_bytes + (p.tap_row[j] + m * RT) * 128;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(tacc + m * C, umma_desc_sw128(a0 + k * 32),
+                              umma_desc_sw128(sB + bs * kBBytes + k * 32), idesc, acc | (uint32_t)k);
+                }
+                acc = 1;
+                umma_commit(bEmptyB + 8 * bs);
+              }
+            umma_commit(bEmptyA + 8 * as);
+          }
+        umma_commit(bTmemFull + 8 * buf);
+      }
+    }
+  } else {
+    // ---- epilogue: thread <-> accumulator row r = 32*(warp&3) + lane = (frame r / V, joint r % V) ----
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int fr = r / p.V, w = r - fr * p.V;
+    const float inv_n = 1.f / (float)(p.V * C), inv_nm1 = 1.f / (float)(p.V * C - 1);
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int buf = it % TB;
+      const int n = item / p.groups_per_trial;
+      const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;
+      mbar_wait(bTmemFull + 8 * buf, (it / TB) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < p.NT; ++m) {
+        const int t = f0 + m * p.FT + fr;
+        const bool row_ok = (r < RT) && (t < p.T_out);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * C + m * C);
+        const long long row = ((long long)n * p.T_out + t) * p.V + w;
+        float v[32];
+        float s = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < C; cb += 32) {
+          tmem_ld32(taddr + cb, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s += v[i] + __ldg(p.bias + cb + i);
+        }
+        s_part[r] = row_ok ? s : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float tot = 0.f;
+        if (r < RT)
+          for (int j = 0; j < p.V; ++j) tot += s_part[fr * p.V + j];
+        const float mean = tot * inv_n;
+        float ss = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < C; cb += 32) {
+          tmem_ld32(taddr + cb, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = v[i] + __ldg(p.bias + cb + i) - mean;
+            ss = fmaf(d, d, ss);
+          }
+        }
+        s_part[128 + r] = row_ok ? ss : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float tq = 0.f;
+        if (r < RT)
+          for (int j = 0; j < p.V; ++j) tq += s_part[128 + fr * p.V + j];
+        const float rstd = 1.f / sqrtf(tq * inv_nm1 + p.eps);
+#pragma unroll 1
+        for (int cb = 0; cb < C; cb += 32) {
+          tmem_ld32(taddr + cb, v);
+          if (row_ok) {
+            float *dst = p.out + row * C + cb;
+            const float *rs = p.res ? p.res + row * C + cb : nullptr;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = cb + i + e;
+                o[e] = (v[i + e] + __ldg(p.bias + c) - mean) * rstd * __ldg(p.n_w + c * p.V + w) +
+                       __ldg(p.n_b + c * p.V + w);
+              }
+              if (rs) {
+                const float4 r4 = *reinterpret_cast<const float4 *>(rs + i);
+                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+              }
+              *reinterpret_cast<float4 *>(dst + i) =
+                  make_float4(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f), fmaxf(o[2], 0.f), fmaxf(o[3], 0.f));
+            }
+          }
+        }
+      }
+      // accumulator buffer drained: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTmemEmpty + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// --------------------------------------------------------------------------- //
 // Graph-convolution stage on tensor cores, fused with LayerNorm(C,V) + ReLU
 // (tgcn.py:70-79 + stgcn.py:152-153):
 //
@@ -400,22 +636,28 @@ constexpr int kGcnThreads = 320;
 constexpr int kGcnXform = 8;                 // transform warps
 constexpr int kGcnAStage = 2 * 128 * 128;    // 2 tiles x 128 rows x 128 B = 32768
 constexpr int kGcnARing = 3;
-constexpr int kGcnXsBytes = kOutFrames * kFrameRows * 64 * 4;  // 65536 (V <= 32)
+constexpr int kGcnCsrMax = 384;              // CSR entries cached in shared memory (tree graphs: ~75)
+constexpr int kGcnCsrBytes = 4096;           // ptr[K*V+1] + kGcnCsrMax (v, a) pairs
+constexpr int kGcnMaxJoints = 4;             // joints per transform warp (V <= 32, 8 warps)
 
 template <int CO>
 struct GcnCfg {
   static constexpr int kBBytes = CO * 128;
   static constexpr int kStages = CO == 256 ? 2 : 4;
-  static constexpr int kSmem = kGcnARing * kGcnAStage + kGcnXsBytes + kStages * kBBytes + 256 + 1024;
   static constexpr int kTmemCols = 2 * CO;
+  // input tile: 8 frames x V joints x 64 fp32 channels, rounded up to 1 KB
+  static int xs_bytes(int V) { return (kOutFrames * V * 64 * 4 + 1023) & ~1023; }
+  static int smem(int V) {
+    return kGcnARing * kGcnAStage + xs_bytes(V) + kStages * kBBytes + kGcnCsrBytes + 256 + 1024;
+  }
 };
 
 struct GcnTcParams {
   int T, V, K, Cin;
   int planes;
+  int xs_alloc;         // bytes reserved for the fp32 input tile (GcnCfg::xs_bytes)
   const int *csr_ptr;   // [K*V + 1], (k,w)-major
-  const int *csr_v;     // source joint of each entry
-  const float *csr_a;   // A[k,v,w]
+  const int2 *csr_va;   // per entry: (source joint v, bits of A[k,v,w])
   const float *bzT;     // [CO][V] bias through the adjacency
   const float *n_w, *n_b;
   __nv_bfloat16 *out_hi, *out_lo;   // [rows][CO] planes (tensor-core temporal stage) or null
@@ -423,10 +665,6 @@ struct GcnTcParams {
   float eps;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int CO>
 __global__ void __launch_bounds__(kGcnThreads, 1)
@@ -439,8 +677,9 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
   uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t sA = smem_base;
   const uint32_t sXs = sA + kGcnARing * kGcnAStage;
-  const uint32_t sB = sXs + kGcnXsBytes;
-  const uint32_t sBar = sB + S * Cfg::kBBytes;
+  const uint32_t sB = sXs + p.xs_alloc;
+  const uint32_t sCsr = sB + S * Cfg::kBBytes;
+  const uint32_t sBar = sCsr + kGcnCsrBytes;
   const uint32_t bXsFull = sBar, bXsEmpty = sBar + 8;
   const uint32_t bAFull = sBar + 16, bAEmpty = bAFull + 8 * kGcnARing;
   const uint32_t bFullB = bAEmpty + 8 * kGcnARing, bEmptyB = bFullB + 8 * S;
@@ -449,6 +688,8 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
   volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
   const float *xs = reinterpret_cast<const float *>(gen_base + (sXs - smem_base));
   uint8_t *a_gen = gen_base;  // A ring starts at smem_base
+  int *s_ptr = reinterpret_cast<int *>(gen_base + (sCsr - smem_base));          // [K*V + 1]
+  int2 *s_va = reinterpret_cast<int2 *>(gen_base + (sCsr - smem_base) + 1024);  // [kGcnCsrMax]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y;
@@ -473,6 +714,12 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(sTmemPtr, Cfg::kTmemCols);
+  const int nnz = __ldg(p.csr_ptr + p.K * p.V);
+  const bool csr_smem = nnz <= kGcnCsrMax && p.K * p.V + 1 <= 256;
+  if (csr_smem) {
+    for (int i = threadIdx.x; i <= p.K * p.V; i += blockDim.x) s_ptr[i] = __ldg(p.csr_ptr + i);
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) s_va[i] = __ldg(p.csr_va + i);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -528,34 +775,58 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
       umma_commit(bTmemFull);
     }
   } else {
-    // ---- transform warps: xa_k = A_k-contraction of the staged fp32 tile -> bf16 plane ----
+    // ---- transform warps: xa_k = A_k-contraction of the staged fp32 tile -> bf16 planes ----
+    // Warp tw owns joints w = tw, tw+8, ... for all 8 frames (the 8 frames share every CSR
+    // entry, giving 8 independent shared-memory loads per entry); lane owns channels 2l, 2l+1.
+    // The fp32 results stay in registers between the hi-plane and the lo-plane stage.
     const int tw = warp - 2;
     int a_it = 0;
+    float2 xa[kGcnMaxJoints][kOutFrames];
     for (int kc = 0; kc < KC; ++kc) {
       mbar_wait(bXsFull, kc & 1);
       for (int k = 0; k < p.K; ++k)
         for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
           const int as = a_it % kGcnARing;
+          if (ap == 0) {
+#pragma unroll
+            for (int jw = 0; jw < kGcnMaxJoints; ++jw) {
+              const int w = tw + jw * kGcnXform;
+#pragma unroll
+              for (int f = 0; f < kOutFrames; ++f) xa[jw][f] = make_float2(0.f, 0.f);
+              if (w < p.V) {
+                const int e0 = csr_smem ? s_ptr[k * p.V + w] : __ldg(p.csr_ptr + k * p.V + w);
+                const int e1 = csr_smem ? s_ptr[k * p.V + w + 1] : __ldg(p.csr_ptr + k * p.V + w + 1);
+                for (int e = e0; e < e1; ++e) {
+                  const int2 va = csr_smem ? s_va[e] : __ldg(p.csr_va + e);
+                  const float a = __int_as_float(va.y);
+                  const float *xr = xs + va.x * 64 + 2 * lane;
+#pragma unroll
+                  for (int f = 0; f < kOutFrames; ++f) {
+                    const float2 xv = *reinterpret_cast<const float2 *>(xr + f * p.V * 64);
+                    xa[jw][f].x = fmaf(a, xv.x, xa[jw][f].x);
+                    xa[jw][f].y = fmaf(a, xv.y, xa[jw][f].y);
+                  }
+                }
+              }
+            }
+          }
           mbar_wait(bAEmpty + 8 * as, ((a_it / kGcnARing) & 1) ^ 1);
           uint8_t *stage = a_gen + as * kGcnAStage;
-          for (int i = tw; i < kOutFrames * p.V; i += kGcnXform) {
-            const int f = i / p.V, w = i - f * p.V;
-            const int e1 = __ldg(p.csr_ptr + k * p.V + w + 1);
-            float ax = 0.f, ay = 0.f;
-            for (int e = __ldg(p.csr_ptr + k * p.V + w); e < e1; ++e) {
-              const float a = __ldg(p.csr_a + e);
-              const float2 xv =
-                  *reinterpret_cast<const float2 *>(xs + (f * p.V + __ldg(p.csr_v + e)) * 64 + 2 * lane);
-              ax = fmaf(a, xv.x, ax);
-              ay = fmaf(a, xv.y, ay);
+#pragma unroll
+          for (int jw = 0; jw < kGcnMaxJoints; ++jw) {
+            const int w = tw + jw * kGcnXform;
+            if (w < p.V) {
+#pragma unroll
+              for (int f = 0; f < kOutFrames; ++f) {
+                __nv_bfloat16 hx, lx, hy, ly;
+                split_bf16(xa[jw][f].x, hx, lx);
+                split_bf16(xa[jw][f].y, hy, ly);
+                const __nv_bfloat162 pk = ap == 0 ? __nv_bfloat162(hx, hy) : __nv_bfloat162(lx, ly);
+                const int R = f * kFrameRows + w;               // row in the 256-row stage
+                const int chunk = (lane >> 2) ^ (R & 7);        // 128B swizzle: 16B chunk ^ (row % 8)
+                *reinterpret_cast<__nv_bfloat162 *>(stage + R * 128 + chunk * 16 + (lane & 3) * 4) = pk;
+              }
             }
-            __nv_bfloat16 hx, lx, hy, ly;
-            split_bf16(ax, hx, lx);
-            split_bf16(ay, hy, ly);
-            __nv_bfloat162 pk = ap == 0 ? __nv_bfloat162(hx, hy) : __nv_bfloat162(lx, ly);
-            const int R = f * kFrameRows + w;                 // row in the 256-row stage
-            const int chunk = (lane >> 2) ^ (R & 7);          // 128B swizzle: 16B chunk ^ (row % 8)
-            *reinterpret_cast<__nv_bfloat162 *>(stage + R * 128 + chunk * 16 + (lane & 3) * 4) = pk;
           }
           fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
@@ -652,7 +923,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
 // adjacency CSR ordered by (k, w): ptr[k*V + w] .. ptr[k*V + w + 1] -> (v, A[k,v,w]); and the bias
 // that flows through A, transposed for coalesced epilogue reads: bzT[c][w].
 __global__ void k_build_adj_csr_kw(const float *__restrict__ A, int K, int V, int *__restrict__ ptr,
-                                   int *__restrict__ vidx, float *__restrict__ val) {
+                                   int2 *__restrict__ va) {
   extern __shared__ int s_cnt[];  // K*V + 1
   const int P = K * V;
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
@@ -679,8 +950,7 @@ __global__ void k_build_adj_csr_kw(const float *__restrict__ A, int K, int V, in
     for (int v = 0; v < V; ++v) {
       const float x = A[((long long)k * V + v) * V + w];
       if (x != 0.f) {
-        vidx[at] = v;
-        val[at] = x;
+        va[at] = make_int2(v, __float_as_int(x));
         ++at;
       }
     }
@@ -761,8 +1031,8 @@ inline int make_tmap_f32_noswizzle(CUtensorMap *m, const void *base, int rank, c
 }
 
 inline bool gcn_tc_supported(int c_in, int c_out, int V, int K) {
-  return (c_out == 64 || c_out == 128 || c_out == 256) && c_in % 64 == 0 && c_in >= 64 && V <= kFrameRows &&
-         V >= 2 && K >= 1;
+  return (c_out == 64 || c_out == 128 || c_out == 256) && c_in % 64 == 0 && c_in >= 64 && V <= 28 &&
+         V >= 2 && K >= 1 && K * V + 1 <= 256;
 }
 
 // x: fp32 [N][T][V][c_in]; wp: bf16 [2][K][c_out][c_in]
@@ -777,9 +1047,13 @@ int launch_gcn_tc_c(const float *x, const __nv_bfloat16 *wp, const GcnTcParams &
   const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)p.K * CO * p.Cin * 2};
   const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
   if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
-  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn_tc<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcnCfg<CO>::kSmem));
+  GcnTcParams q = p;
+  q.xs_alloc = GcnCfg<CO>::xs_bytes(p.V);
+  const int smem = GcnCfg<CO>::smem(p.V);
+  if (smem > 232448) return fail("gcn tensor-core kernel: %d joints need %d B of shared memory", p.V, smem);
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn_tc<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((p.T + kOutFrames - 1) / kOutFrames, N);
-  k_gcn_tc<CO><<<grid, kGcnThreads, GcnCfg<CO>::kSmem, st>>>(tm_x, tm_w, p);
+  k_gcn_tc<CO><<<grid, kGcnThreads, smem, st>>>(tm_x, tm_w, q);
   return 0;
 }
 
@@ -815,6 +1089,115 @@ int launch_tcn_tc_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTc
   dim3 grid((p.T + kOutFrames - 1) / kOutFrames, N);
   k_tcn_tc<C><<<grid, kTcnThreads, TcnCfg<C>::kSmem, st>>>(tm_u, tm_w, p);
   return 0;
+}
+
+// ---- v2 launcher -----------------------------------------------------------------
+inline bool tcn_tc2_supported(int C, int V, int G, int stride, int T) {
+  return (C == 64 || C == 128 || C == 256) && V >= 2 && V <= 64 && G <= 15 && (G & 1) &&
+         (stride == 1 || (stride == 2 && T >= 2));
+}
+
+inline int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// u planes: bf16 [planes][N][T][V][C] (T = input frames); wp: bf16 [2][G][C][C]; out/res rows over T_out
+template <int C>
+int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Params p, int N, int T, int stride,
+                     cudaStream_t st) {
+  const int V = p.V, pad = (p.G - 1) / 2;
+  const int kMaxSmem = 232448;
+  // frames per tile: as many whole frames as fit 128 rows; shrink for the big stride-2 case
+  int FT = 128 / V;
+  int a_rows = 0;
+  for (;; --FT) {
+    if (FT < 1) return fail("tcn tensor-core kernel: %d joints do not fit a 128-row tile", V);
+    p.FT = FT;
+    p.NT = 2;
+    const int out_f = p.NT * FT, spill = 128 - FT * V;
+    if (stride == 1) {
+      const int wf = out_f + 2 * pad;
+      p.n_loads = 1;
+      p.load_f0[0] = -pad; p.load_row[0] = 0; p.load_bytes[0] = wf * V * 128;
+      for (int j = 0; j < p.G; ++j) p.tap_row[j] = j * V;
+      a_rows = wf * V + spill;
+    } else {
+      // input frame of tap j for output frame tau: 2*tau + d, d = j - pad; parity d & 1, position
+      // tau + (d >> 1) in that parity's frame sequence
+      int lo[2] = {1 << 30, 1 << 30}, hi[2] = {-(1 << 30), -(1 << 30)};
+      for (int j = 0; j < p.G; ++j) {
+        const int d = j - pad, par = d & 1, pos = d >> 1;
+        if (pos < lo[par]) lo[par] = pos;
+        if (pos > hi[par]) hi[par] = pos;
+      }
+      if (hi[1] < lo[1]) return fail("tcn tensor-core kernel: stride 2 needs a kernel of at least 3 taps");
+      int nf[2], base_row[2];
+      nf[0] = out_f + hi[0] - lo[0];
+      nf[1] = out_f + hi[1] - lo[1];
+      base_row[0] = 0;
+      base_row[1] = nf[0] * V;
+      p.n_loads = 2;
+      for (int q = 0; q < 2; ++q) {
+        p.load_f0[q] = lo[q]; p.load_row[q] = base_row[q]; p.load_bytes[q] = nf[q] * V * 128;
+      }
+      for (int j = 0; j < p.G; ++j) {
+        const int d = j - pad, par = d & 1, pos = d >> 1;
+        p.tap_row[j] = base_row[par] + (pos - lo[par]) * V;
+      }
+      a_rows = (nf[0] + nf[1]) * V + spill;
+    }
+    p.a_stage_bytes = (a_rows * 128 + 1023) & ~1023;
+    const int left = kMaxSmem - 2 * p.a_stage_bytes - 1024 - 512 - 1024;
+    p.b_stages = left / (C * 128);
+    if (p.b_stages > 8) p.b_stages = 8;
+    if (p.b_stages >= 2) break;
+  }
+  p.groups_per_trial = (p.T_out + p.NT * p.FT - 1) / (p.NT * p.FT);
+  p.items = N * p.groups_per_trial;
+  const int smem = 2 * p.a_stage_bytes + p.b_stages * C * 128 + 1024 + 512 + 1024;
+
+  CUtensorMap tm_u0, tm_u1, tm_w;
+  const uint64_t plane_stride = (uint64_t)N * T * V * C * 2;
+  if (stride == 1) {
+    const uint64_t ud[5] = {(uint64_t)C, (uint64_t)V, (uint64_t)T, (uint64_t)N, (uint64_t)p.planes};
+    const uint64_t us[4] = {(uint64_t)C * 2, (uint64_t)V * C * 2, (uint64_t)T * V * C * 2, plane_stride};
+    const uint32_t ub[5] = {64, (uint32_t)V, (uint32_t)(p.load_bytes[0] / (V * 128)), 1, 1};
+    if (make_tmap_bf16(&tm_u0, u, 5, ud, us, ub)) return 1;
+    tm_u1 = tm_u0;
+  } else {
+    for (int q = 0; q < 2; ++q) {
+      const uint64_t tq = q == 0 ? (uint64_t)(T + 1) / 2 : (uint64_t)T / 2;
+      const uint64_t ud[5] = {(uint64_t)C, (uint64_t)V, tq, (uint64_t)N, (uint64_t)p.planes};
+      const uint64_t us[4] = {(uint64_t)C * 2, (uint64_t)2 * V * C * 2, (uint64_t)T * V * C * 2, plane_stride};
+      const uint32_t ub[5] = {64, (uint32_t)V, (uint32_t)(p.load_bytes[q] / (V * 128)), 1, 1};
+      if (make_tmap_bf16(q == 0 ? &tm_u0 : &tm_u1, u + (size_t)q * V * C, 5, ud, us, ub)) return 1;
+    }
+  }
+  const uint64_t wd[4] = {(uint64_t)C, (uint64_t)C, (uint64_t)p.G, 2};
+  const uint64_t wst[3] = {(uint64_t)C * 2, (uint64_t)C * C * 2, (uint64_t)p.G * C * C * 2};
+  const uint32_t wb[4] = {64, (uint32_t)C, 1, 1};
+  if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_tcn_tc2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  k_tcn_tc2<C><<<grid, kTcn2Threads, smem, st>>>(tm_u0, tm_u1, tm_w, p);
+  return 0;
+}
+
+inline int launch_tcn_tc2(int C, const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTc2Params &p, int N,
+                          int T, int stride, cudaStream_t st) {
+  switch (C) {
+    case 64: return launch_tcn_tc2_c<64>(u, wp, p, N, T, stride, st);
+    case 128: return launch_tcn_tc2_c<128>(u, wp, p, N, T, stride, st);
+    case 256: return launch_tcn_tc2_c<256>(u, wp, p, N, T, stride, st);
+  }
+  return fail("tcn tensor-core kernel: unsupported channel count %d", C);
 }
 
 inline int launch_tcn_tc(int C, const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTcParams &p, int N,

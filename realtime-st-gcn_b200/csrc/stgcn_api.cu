@@ -123,8 +123,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   const long long rows = (long long)N * T * V, rows_out = (long long)N * T_out * V;
   const bool bn = d.norm == STGCN_NORM_BATCHNORM;
   // tensor-core temporal stage: LayerNorm, stride 1, identity/no residual, C in {64,128,256}
-  const bool tc_tcn = math != STGCN_MATH_FP32 && !bn && d.residual != STGCN_RES_CONV &&
-                      tc::tcn_tc_supported(d.c_out, V, d.kernel, d.stride);
+  const bool tc_tcn = math != STGCN_MATH_FP32 && !bn && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, T);
   const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
 
   // tensor-core graph-convolution stage: LayerNorm, shared adjacency, C_in % 64 == 0
@@ -139,15 +138,14 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     const size_t m2 = ws.mark();
     const long long nw = (long long)K * d.c_out * d.c_in;
     int *kw_ptr = ws.take<int>((size_t)K * V + 1);
-    int *kw_v = ws.take<int>((size_t)K * V * V);
-    float *kw_a = ws.take<float>((size_t)K * V * V);
+    int2 *kw_va = ws.take<int2>((size_t)K * V * V);
     float *bzT = ws.take<float>((size_t)d.c_out * V);
     __nv_bfloat16 *wg16 = ws.take<__nv_bfloat16>((size_t)2 * nw);
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
       {
         ProfScope ps(KC_MISC, st);
-        tc::k_build_adj_csr_kw<<<1, 128, (K * V + 1) * sizeof(int), st>>>(d.a_eff, K, V, kw_ptr, kw_v, kw_a);
+        tc::k_build_adj_csr_kw<<<1, 128, (K * V + 1) * sizeof(int), st>>>(d.a_eff, K, V, kw_ptr, kw_va);
         STGCN_LAUNCH_OK();
         tc::k_bias_through_adj<<<cdiv((long long)d.c_out * V, 256), 256, 0, st>>>(d.a_eff, d.gcn_b, K, V,
                                                                                   d.c_out, bzT);
@@ -157,7 +155,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       }
       tc::GcnTcParams g{};
       g.T = T; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
-      g.csr_ptr = kw_ptr; g.csr_v = kw_v; g.csr_a = kw_a; g.bzT = bzT;
+      g.csr_ptr = kw_ptr; g.csr_va = kw_va; g.bzT = bzT;
       g.n_w = d.n1_w; g.n_b = d.n1_b;
       g.out_hi = u16; g.out_lo = u16_lo; g.out_f32 = u;
       g.eps = kEps;
@@ -207,6 +205,9 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   if (tc_tcn) {
     const long long nw = (long long)d.c_out * d.c_out * d.kernel;
     __nv_bfloat16 *wp16 = ws.take<__nv_bfloat16>((size_t)2 * nw);
+    // channel-changing / strided residual: LN_R(conv1x1_stride(x)) precomputed into `resb`
+    float *resb = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
+    float *qr = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
       {
@@ -214,15 +215,28 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
         tc::k_pack_tcn_w_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.tcn_w, wp16, d.c_out, d.c_out, d.kernel);
         STGCN_LAUNCH_OK();
       }
-      tc::TcnTcParams p{};
-      p.T = T; p.V = V; p.G = d.kernel; p.pad = (d.kernel - 1) / 2;
+      if (resb) {
+        if (launch_gemm(x, d.res_w, d.res_b, qr, N, T, V, d.c_in, d.c_out, 1, d.stride, st)) return 1;
+        FrameArgs a{};
+        a.producer = FRAME_LOAD;
+        a.frames = (long long)N * T_out;
+        a.frames_per_sample = T_out;
+        a.K = K; a.V = V; a.C = d.c_out;
+        a.a = qr;
+        a.norm_a = 1; a.na_w = d.nr_w; a.na_b = d.nr_b;
+        a.eps = kEps;
+        a.out = resb;
+        if (launch_frame(a, st)) return 1;
+      }
+      tc::TcnTc2Params p{};
+      p.T_out = T_out; p.V = V; p.G = d.kernel;
       p.planes = planes;
       p.bias = d.tcn_b; p.n_w = d.n2_w; p.n_b = d.n2_b;
-      p.res = d.residual == STGCN_RES_IDENTITY ? x : nullptr;
+      p.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
       p.out = out;
       p.eps = kEps;
       ProfScope ps(KC_GEMM_TCN, st);
-      if (tc::launch_tcn_tc(d.c_out, u16, wp16, p, N, st)) return 1;
+      if (tc::launch_tcn_tc2(d.c_out, u16, wp16, p, N, T, d.stride, st)) return 1;
       STGCN_LAUNCH_OK();
     }
     ws.release(mark);
