@@ -53,15 +53,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trap, never as a hung GPU.
+// try_wait with a suspend-time hint: the hardware may park the thread until the phase completes
+// (or the hint expires) instead of returning immediately.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap, never as a hung GPU.  Waiters back off
+// with nanosleep so that spinning warps do not steal issue slots from the working warps
+// (ncu on the first persistent kernel showed ~40% of all issued instructions were wait spins).
+template <int kSleepNs = 64>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
-      printf("stgcn_b200: mbarrier timeout (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-             blockIdx.y, threadIdx.x, bar, parity);
-      __trap();
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (kSleepNs > 0) __nanosleep(kSleepNs);
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+        printf("stgcn_b200: mbarrier timeout (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+               blockIdx.y, threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }
@@ -123,6 +144,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -382,6 +416,116 @@ __global__ void __launch_bounds__(kTcnThreads, 1)
 }
 
 // --------------------------------------------------------------------------- //
+// Shared LayerNorm epilogue of the persistent kernels.  One thread owns one accumulator row
+// r = (frame r / V, joint r % V) of a 128-row tile held in TMEM (C fp32 columns):
+//   y = LN_{C,V}(acc + bias) * g + b  [+ res]  [relu]  -> fp32 rows or split-bf16 planes.
+// The (C,V) statistics of a frame are reduced across its V rows through `s_part`
+// (float[2][128] in shared memory) and named barrier 1 (the 128 epilogue threads).
+// --------------------------------------------------------------------------- //
+struct EpiParams {
+  const float *bias;
+  int bias_sc, bias_sw;          // bias index = c * bias_sc + w * bias_sw
+  const float *n_w, *n_b;        // LayerNorm affine, reference layout (C, V)
+  const float *res;              // fp32 [rows][C] added after the norm, or null
+  float *out_f32;                // fp32 [rows][C] or null
+  __nv_bfloat16 *out_hi, *out_lo;  // split-bf16 planes [rows][C] or null
+  int relu;
+  float eps;
+  int debug;                     // measurement aid: 1 = skip the epilogue body, 2 = skip transform math
+};
+
+// Statistics in ONE pass over TMEM: each row accumulates sum / sum of squares of (x - shift) with
+// shift = its first element (so the squares do not cancel), giving a row mean and a row M2; the V
+// rows of a frame are then merged exactly (Chan et al.):  M2 = sum M2_r + C * sum (m_r - mean)^2.
+// `s_part` is float[2][256]; `tile_parity` alternates the half used so one barrier per tile suffices.
+template <int C>
+__device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
+                                                 int w, bool row_ok, long long row, float *s_part,
+                                                 int tile_parity) {
+  if (e.debug & 1) return;
+  const float *bias = e.bias + w * e.bias_sw;
+  float *sp = s_part + tile_parity * 256;
+  float v[16];
+  float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < C; cb += 16) {
+    tmem_ld16(taddr + cb, v);
+    if (cb == 0) shift = v[0] + __ldg(bias);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d = v[i] + __ldg(bias + (cb + i) * e.bias_sc) - shift;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
+    }
+  }
+  const float m_r = shift + s1 * (1.f / (float)C);
+  const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)C), 0.f);
+  sp[r] = row_ok ? m_r : 0.f;
+  sp[128 + r] = row_ok ? M2_r : 0.f;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  float mean = 0.f, rstd = 0.f;
+  if (r < RT) {
+    float tm = 0.f, tq = 0.f;
+    for (int j = 0; j < V; ++j) tm += sp[fr * V + j];
+    mean = tm * (1.f / (float)V);
+    for (int j = 0; j < V; ++j) {
+      const float dm = sp[fr * V + j] - mean;
+      tq += sp[128 + fr * V + j] + (float)C * dm * dm;
+    }
+    rstd = 1.f / sqrtf(tq * (1.f / (float)(V * C - 1)) + e.eps);
+  }
+#pragma unroll 1
+  for (int cb = 0; cb < C; cb += 16) {
+    tmem_ld16(taddr + cb, v);
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = cb + i;
+        v[i] = (v[i] + __ldg(bias + c * e.bias_sc) - mean) * rstd * __ldg(e.n_w + c * V + w) +
+               __ldg(e.n_b + c * V + w);
+      }
+      if (e.res) {
+        const float4 *rs = reinterpret_cast<const float4 *>(e.res + row * C + cb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 r4 = rs[i];
+          v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+        }
+      }
+      if (e.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (e.out_f32) {
+        float4 *dst = reinterpret_cast<float4 *>(e.out_f32 + row * C + cb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      if (e.out_hi) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v[2 * i], h0, l0);
+          split_bf16(v[2 * i + 1], h1, l1);
+          __nv_bfloat162 hh(h0, h1), ll(l0, l1);
+          hi[i] = *reinterpret_cast<uint32_t *>(&hh);
+          lo[i] = *reinterpret_cast<uint32_t *>(&ll);
+        }
+        uint4 *dh = reinterpret_cast<uint4 *>(e.out_hi + row * C + cb);
+        dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        if (e.out_lo) {
+          uint4 *dl = reinterpret_cast<uint4 *>(e.out_lo + row * C + cb);
+          dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- //
 // Temporal convolution v2: persistent, unpadded rows, stride 1 or 2.
 //
 // Measured on B200 (tools/probes/umma_row_offset.cu): a K-major SWIZZLE_128B descriptor whose
@@ -398,7 +542,7 @@ __global__ void __launch_bounds__(kTcnThreads, 1)
 // Stride 2: even and odd input frames are staged as two dense windows through two tensor maps
 // (frame stride 2), so every tap again reads a contiguous window.
 // --------------------------------------------------------------------------- //
-constexpr int kTcn2Threads = 192;
+constexpr int kTcn2Threads = 224;   // warps: 0 A producer, 1 MMA, 2 B producer, 3..6 epilogue
 
 struct TcnTc2Params {
   int T_out, V, G, planes;
@@ -410,9 +554,7 @@ struct TcnTc2Params {
   int load_row[2];            // destination row in the stage
   int load_bytes[2];
   int tap_row[16];            // first stage row of tap j for tile 0
-  const float *bias, *n_w, *n_b, *res;
-  float *out;
-  float eps;
+  EpiParams epi;
 };
 
 template <int C>
@@ -428,8 +570,8 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
   const int S = p.b_stages;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + 2 * p.a_stage_bytes;
-  const uint32_t sPart = sB + S * kBBytes;                    // float[2][128]
-  const uint32_t sBar = sPart + 1024;
+  const uint32_t sPart = sB + S * kBBytes;                    // float[2][256]
+  const uint32_t sBar = sPart + 2048;
   const uint32_t bFullA = sBar, bEmptyA = sBar + 16, bTmemFull = sBar + 32, bTmemEmpty = sBar + 48;
   const uint32_t bFullB = sBar + 64, bEmptyB = bFullB + 8 * S;
   const uint32_t sTmemPtr = bEmptyB + 8 * S;
@@ -456,15 +598,16 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(sTmemPtr, kTmemCols);
+  if (warp == 1) tmem_alloc(sTmemPtr, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
+    // ---- input-window producer (runs ahead by the 2-deep A ring, independent of the weights) ----
     if (lane == 0) {
-      int a_it = 0, b_it = 0;
+      int a_it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int n = item / p.groups_per_trial;
         const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;   // first output frame
@@ -478,6 +621,16 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
             if (p.n_loads > 1)
               tma_load_5d(sA + as * p.a_stage_bytes + p.load_row[1] * 128, &tm_u1, bFullA + 8 * as, kc * 64, 0,
                           f0 + p.load_f0[1], n, ap);
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ---- weight-tile producer ----
+    if (lane == 0) {
+      int b_it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x)
+        for (int kc = 0; kc < KC; ++kc)
+          for (int ap = 0; ap < p.planes; ++ap) {
             const int nb = (ap == 0) ? p.planes : 1;
             for (int j = 0; j < p.G; ++j)
               for (int bp = 0; bp < nb; ++bp, ++b_it) {
@@ -487,7 +640,6 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
                 tma_load_4d(sB + bs * kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, j, bp);
               }
           }
-      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -530,7 +682,6 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int fr = r / p.V, w = r - fr * p.V;
-    const float inv_n = 1.f / (float)(p.V * C), inv_nm1 = 1.f / (float)(p.V * C - 1);
     int it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int buf = it % TB;
@@ -544,60 +695,7 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
         const bool row_ok = (r < RT) && (t < p.T_out);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * C + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        float v[32];
-        float s = 0.f;
-#pragma unroll 1
-        for (int cb = 0; cb < C; cb += 32) {
-          tmem_ld32(taddr + cb, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s += v[i] + __ldg(p.bias + cb + i);
-        }
-        s_part[r] = row_ok ? s : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        float tot = 0.f;
-        if (r < RT)
-          for (int j = 0; j < p.V; ++j) tot += s_part[fr * p.V + j];
-        const float mean = tot * inv_n;
-        float ss = 0.f;
-#pragma unroll 1
-        for (int cb = 0; cb < C; cb += 32) {
-          tmem_ld32(taddr + cb, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float d = v[i] + __ldg(p.bias + cb + i) - mean;
-            ss = fmaf(d, d, ss);
-          }
-        }
-        s_part[128 + r] = row_ok ? ss : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        float tq = 0.f;
-        if (r < RT)
-          for (int j = 0; j < p.V; ++j) tq += s_part[128 + fr * p.V + j];
-        const float rstd = 1.f / sqrtf(tq * inv_nm1 + p.eps);
-#pragma unroll 1
-        for (int cb = 0; cb < C; cb += 32) {
-          tmem_ld32(taddr + cb, v);
-          if (row_ok) {
-            float *dst = p.out + row * C + cb;
-            const float *rs = p.res ? p.res + row * C + cb : nullptr;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = cb + i + e;
-                o[e] = (v[i + e] + __ldg(p.bias + c) - mean) * rstd * __ldg(p.n_w + c * p.V + w) +
-                       __ldg(p.n_b + c * p.V + w);
-              }
-              if (rs) {
-                const float4 r4 = *reinterpret_cast<const float4 *>(rs + i);
-                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-              }
-              *reinterpret_cast<float4 *>(dst + i) =
-                  make_float4(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f), fmaxf(o[2], 0.f), fmaxf(o[3], 0.f));
-            }
-          }
-        }
+        ln_epilogue_tile<C>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, s_part, m & 1);
       }
       // accumulator buffer drained: hand it back to the MMA issuer
       tc_fence_before();
@@ -607,7 +705,7 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -982,6 +1080,271 @@ __global__ void k_split_bf16(const float *__restrict__ w, __nv_bfloat16 *__restr
 }
 
 // --------------------------------------------------------------------------- //
+// Graph convolution v2: persistent + pipelined version of k_gcn_tc with dense (unpadded)
+// rows.  Also serves the residual branch LN_R(conv1x1_stride(x)) of channel-changing layers
+// (identity "adjacency", K = 1, frame stride folded into the tensor map, no ReLU).
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2..9 transform (contraction + bf16 split into the
+// swizzled A ring), 10..13 epilogue (TMEM double buffered for C <= 128).
+// --------------------------------------------------------------------------- //
+constexpr int kGcn2Threads = 480;   // + warp 14: weight-tile producer
+constexpr int kGcn2Csr = 2048;               // ptr[<=128] + 192 entries
+constexpr int kGcn2CsrMax = 192;
+
+struct GcnTc2Params {
+  int T_out, V, K, Cin, planes;
+  int FT, NT, groups_per_trial, items;
+  int a_stage_bytes, a_ring, xs_alloc, xs_tx, xs_bufs, b_stages;
+  int identity;
+  const int *csr_ptr;
+  const int2 *csr_va;
+  EpiParams epi;
+};
+
+template <int CO>
+__global__ void __launch_bounds__(kGcn2Threads, 1)
+    k_gcn_tc2(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+              const GcnTc2Params p) {
+  constexpr int kBBytes = CO * 128;
+  constexpr int TB = (4 * CO <= 512) ? 2 : 1;
+  constexpr int kTmemCols = TB * 2 * CO;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int S = p.b_stages, AR = p.a_ring, XB = p.xs_bufs;
+  const uint32_t sA = smem_base;
+  const uint32_t sXs = sA + AR * p.a_stage_bytes;
+  const uint32_t sB = sXs + XB * p.xs_alloc;
+  const uint32_t sCsr = sB + S * kBBytes;
+  const uint32_t sPart = sCsr + kGcn2Csr;
+  const uint32_t sBar = sPart + 2048;
+  const uint32_t bXsFull = sBar, bXsEmpty = sBar + 16, bTmemFull = sBar + 32, bTmemEmpty = sBar + 48;
+  const uint32_t bAFull = sBar + 64, bAEmpty = sBar + 96;
+  const uint32_t bFullB = sBar + 128, bEmptyB = bFullB + 8 * S;
+  const uint32_t sTmemPtr = bEmptyB + 8 * S;
+  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
+  int *s_ptr = reinterpret_cast<int *>(gen_base + (sCsr - smem_base));
+  int2 *s_va = reinterpret_cast<int2 *>(gen_base + (sCsr - smem_base) + 512);
+  float *s_part = reinterpret_cast<float *>(gen_base + (sPart - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = p.Cin / 64;
+  const int RT = p.FT * p.V;
+  const int rows_item = p.NT * RT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bXsFull + 8 * i, 1);
+      mbar_init(bXsEmpty + 8 * i, 8);
+      mbar_init(bTmemFull + 8 * i, 1);
+      mbar_init(bTmemEmpty + 8 * i, 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bAFull + 8 * i, 8);
+      mbar_init(bAEmpty + 8 * i, 1);
+    }
+    for (int i = 0; i < S; ++i) {
+      mbar_init(bFullB + 8 * i, 1);
+      mbar_init(bEmptyB + 8 * i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(sTmemPtr, kTmemCols);
+  bool csr_smem = false;
+  if (!p.identity) {
+    const int nnz = __ldg(p.csr_ptr + p.K * p.V);
+    csr_smem = nnz <= kGcn2CsrMax && p.K * p.V + 1 <= 128;
+    if (csr_smem) {
+      for (int i = threadIdx.x; i <= p.K * p.V; i += blockDim.x) s_ptr[i] = __ldg(p.csr_ptr + i);
+      for (int i = threadIdx.x; i < nnz; i += blockDim.x) s_va[i] = __ldg(p.csr_va + i);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ---- fp32 input-tile producer ----
+    if (lane == 0) {
+      int x_it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.groups_per_trial;
+        const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;
+        for (int kc = 0; kc < KC; ++kc, ++x_it) {
+          const int xb = x_it % XB;
+          mbar_wait(bXsEmpty + 8 * xb, ((x_it / XB) & 1) ^ 1);
+          mbar_expect_tx(bXsFull + 8 * xb, (uint32_t)p.xs_tx);
+          tma_load_4d(sXs + xb * p.xs_alloc, &tm_x, bXsFull + 8 * xb, kc * 64, 0, f0, n);
+          tma_load_4d(sXs + xb * p.xs_alloc + p.xs_alloc / 2, &tm_x, bXsFull + 8 * xb, kc * 64 + 32, 0, f0, n);
+        }
+      }
+    }
+  } else if (warp == 14) {
+    // ---- weight-tile producer ----
+    if (lane == 0) {
+      int b_it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x)
+        for (int kc = 0; kc < KC; ++kc)
+          for (int k = 0; k < p.K; ++k)
+            for (int ap = 0; ap < p.planes; ++ap) {
+              const int nb = (ap == 0) ? p.planes : 1;
+              for (int bp = 0; bp < nb; ++bp, ++b_it) {
+                const int bs = b_it % S;
+                mbar_wait(bEmptyB + 8 * bs, ((b_it / S) & 1) ^ 1);
+                mbar_expect_tx(bFullB + 8 * bs, kBBytes);
+                tma_load_4d(sB + bs * kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, k, bp);
+              }
+            }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, CO);
+      int a_it = 0, b_it = 0, it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int buf = it % TB;
+        mbar_wait(bTmemEmpty + 8 * buf, ((it / TB) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * 2 * CO;
+        uint32_t acc = 0;
+        for (int kc = 0; kc < KC; ++kc)
+          for (int k = 0; k < p.K; ++k)
+            for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
+              const int as = a_it % AR;
+              mbar_wait(bAFull + 8 * as, (a_it / AR) & 1);
+              tc_fence_after();
+              const int nb = (ap == 0) ? p.planes : 1;
+              for (int bp = 0; bp < nb; ++bp, ++b_it) {
+                const int bs = b_it % S;
+                mbar_wait(bFullB + 8 * bs, (b_it / S) & 1);
+                tc_fence_after();
+                for (int m = 0; m < p.NT; ++m) {
+                  const uint32_t a0 = sA + as * p.a_stage_bytes + m * RT * 128;
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tacc + m * CO, umma_desc_sw128(a0 + kk * 32),
+                              umma_desc_sw128(sB + bs * kBBytes + kk * 32), idesc, acc | (uint32_t)kk);
+                }
+                acc = 1;
+                umma_commit(bEmptyB + 8 * bs);
+              }
+              umma_commit(bAEmpty + 8 * as);
+            }
+        umma_commit(bTmemFull + 8 * buf);
+      }
+    }
+  } else if (warp < 10) {
+    // ---- transform warps: ONE THREAD PER ROW (256 threads >= rows of an item) ----
+    // The fp32 input tile is staged as two 32-channel sub-tiles with the 128-B TMA swizzle, so
+    // threads of a warp (consecutive rows) read 16-B chunks from distinct banks.  Each thread
+    // walks its row in groups of 4 channels: gather-sum over the CSR entries of (k, joint),
+    // split into bf16 hi/lo, store hi as 8 B into the swizzled UMMA A stage and keep lo packed
+    // in registers for the following lo-plane stage.
+    const int r = (warp - 2) * 32 + lane;
+    const bool r_ok = r < rows_item;
+    const int f = r / p.V, w = r - f * p.V;
+    const int src_base = f * p.V;                       // first source row of this row's frame
+    int a_it = 0, x_it = 0;
+    uint2 lo_stash[16];
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      for (int kc = 0; kc < KC; ++kc, ++x_it) {
+        const int xb = x_it % XB;
+        mbar_wait(bXsFull + 8 * xb, (x_it / XB) & 1);
+        const uint8_t *xs = gen_base + (sXs - smem_base) + xb * p.xs_alloc;
+        const int half = p.xs_alloc / 2;
+        for (int k = 0; k < p.K; ++k)
+          for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
+            const int as = a_it % AR;
+            int e0 = 0, e1 = 0;
+            if (ap == 0 && r_ok && !p.identity) {
+              e0 = csr_smem ? s_ptr[k * p.V + w] : __ldg(p.csr_ptr + k * p.V + w);
+              e1 = csr_smem ? s_ptr[k * p.V + w + 1] : __ldg(p.csr_ptr + k * p.V + w + 1);
+            }
+            mbar_wait(bAEmpty + 8 * as, ((a_it / AR) & 1) ^ 1);
+            uint8_t *dst_row = gen_base + as * p.a_stage_bytes + r * 128;
+            if (r_ok && !(p.epi.debug & 2)) {
+              if (ap == 0) {
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                  const int sub = g >> 3, j = g & 7;           // 32-channel sub-tile, 16-B chunk
+                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (p.identity) {
+                    acc = *reinterpret_cast<const float4 *>(xs + sub * half + r * 128 + ((j ^ (r & 7)) << 4));
+                  } else {
+                    for (int e = e0; e < e1; ++e) {
+                      const int2 va = csr_smem ? s_va[e] : __ldg(p.csr_va + e);
+                      const float a = __int_as_float(va.y);
+                      const int rs = src_base + va.x;
+                      const float4 xv =
+                          *reinterpret_cast<const float4 *>(xs + sub * half + rs * 128 + ((j ^ (rs & 7)) << 4));
+                      acc.x = fmaf(a, xv.x, acc.x);
+                      acc.y = fmaf(a, xv.y, acc.y);
+                      acc.z = fmaf(a, xv.z, acc.z);
+                      acc.w = fmaf(a, xv.w, acc.w);
+                    }
+                  }
+                  const __nv_bfloat162 h01 = __floats2bfloat162_rn(acc.x, acc.y);
+                  const __nv_bfloat162 h23 = __floats2bfloat162_rn(acc.z, acc.w);
+                  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                  const __nv_bfloat162 l01 = __floats2bfloat162_rn(acc.x - f01.x, acc.y - f01.y);
+                  const __nv_bfloat162 l23 = __floats2bfloat162_rn(acc.z - f23.x, acc.w - f23.y);
+                  lo_stash[g] = make_uint2(*reinterpret_cast<const uint32_t *>(&l01),
+                                           *reinterpret_cast<const uint32_t *>(&l23));
+                  *reinterpret_cast<uint2 *>(dst_row + ((((sub << 2) | (j >> 1)) ^ (r & 7)) << 4) + ((j & 1) << 3)) =
+                      make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+                }
+              } else {
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                  const int sub = g >> 3, j = g & 7;
+                  *reinterpret_cast<uint2 *>(dst_row + ((((sub << 2) | (j >> 1)) ^ (r & 7)) << 4) + ((j & 1) << 3)) =
+                      lo_stash[g];
+                }
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bAFull + 8 * as);
+          }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bXsEmpty + 8 * xb);
+      }
+    }
+  } else if (warp < 14) {
+    // ---- epilogue warps 10..13 ----
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int fr = r / p.V, w = r - fr * p.V;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int buf = it % TB;
+      const int n = item / p.groups_per_trial;
+      const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;
+      mbar_wait(bTmemFull + 8 * buf, (it / TB) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < p.NT; ++m) {
+        const int t = f0 + m * p.FT + fr;
+        const bool row_ok = (r < RT) && (t < p.T_out);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * CO + m * CO);
+        const long long row = ((long long)n * p.T_out + t) * p.V + w;
+        ln_epilogue_tile<CO>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, s_part, m & 1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTmemEmpty + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// --------------------------------------------------------------------------- //
 // host side: tensor maps
 // --------------------------------------------------------------------------- //
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -1011,6 +1374,19 @@ inline int make_tmap_bf16(CUtensorMap *m, const void *base, int rank, const uint
                   reinterpret_cast<const cuuint64_t *>(dims), reinterpret_cast<const cuuint64_t *>(strides_bytes),
                   reinterpret_cast<const cuuint32_t *>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+inline int make_tmap(CUtensorMap *m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void *base, int rank,
+                    const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled is unavailable");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void *>(base), reinterpret_cast<const cuuint64_t *>(dims),
+                  reinterpret_cast<const cuuint64_t *>(strides_bytes), reinterpret_cast<const cuuint32_t *>(box),
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
@@ -1091,12 +1467,6 @@ int launch_tcn_tc_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTc
   return 0;
 }
 
-// ---- v2 launcher -----------------------------------------------------------------
-inline bool tcn_tc2_supported(int C, int V, int G, int stride, int T) {
-  return (C == 64 || C == 128 || C == 256) && V >= 2 && V <= 64 && G <= 15 && (G & 1) &&
-         (stride == 1 || (stride == 2 && T >= 2));
-}
-
 inline int num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -1106,6 +1476,67 @@ inline int num_sms() {
     if (sms <= 0) sms = 148;
   }
   return sms;
+}
+
+// x: fp32 view [N][T_view][V][c_in] with frame stride `fstride` frames (residual branch: stride s);
+// wp: bf16 [2][K][c_out][c_in]
+template <int CO>
+int launch_gcn_tc2_c(const float *x, const __nv_bfloat16 *wp, GcnTc2Params p, int N, int T_full, int fstride,
+                     cudaStream_t st) {
+  const int V = p.V, kMaxSmem = 232448;
+  p.FT = 128 / V;
+  p.NT = 2;
+  if (p.FT < 1) return fail("gcn tensor-core kernel: %d joints do not fit a 128-row tile", V);
+  const int RT = p.FT * V;
+  p.a_stage_bytes = ((p.NT * RT + 128 - RT) * 128 + 1023) & ~1023;
+  p.xs_tx = p.NT * p.FT * V * 64 * 4;
+  p.xs_alloc = 2 * ((p.NT * p.FT * V * 128 + 1023) & ~1023);   // two 32-channel swizzled sub-tiles
+  const int fixed = kGcn2Csr + 2048 + 512 + 1024;
+  // prefer: double-buffered input tile, 3-deep A ring, >= 2 weight stages; back off as smem requires
+  const int tries[4][2] = {{2, 3}, {2, 2}, {1, 3}, {1, 2}};
+  int ok = 0;
+  for (int i = 0; i < 4 && !ok; ++i) {
+    p.xs_bufs = tries[i][0];
+    p.a_ring = tries[i][1];
+    const int left = kMaxSmem - fixed - p.xs_bufs * p.xs_alloc - p.a_ring * p.a_stage_bytes;
+    p.b_stages = left / (CO * 128);
+    if (p.b_stages > 6) p.b_stages = 6;
+    if (p.b_stages >= 2) ok = 1;
+  }
+  if (!ok) return fail("gcn tensor-core kernel: shared memory does not fit V=%d", V);
+  const int smem = fixed + p.xs_bufs * p.xs_alloc + p.a_ring * p.a_stage_bytes + p.b_stages * CO * 128;
+  p.groups_per_trial = (p.T_out + p.NT * p.FT - 1) / (p.NT * p.FT);
+  p.items = N * p.groups_per_trial;
+
+  CUtensorMap tm_x, tm_w;
+  const uint64_t xd[4] = {(uint64_t)p.Cin, (uint64_t)V, (uint64_t)p.T_out, (uint64_t)N};
+  const uint64_t xst[3] = {(uint64_t)p.Cin * 4, (uint64_t)fstride * V * p.Cin * 4, (uint64_t)T_full * V * p.Cin * 4};
+  const uint32_t xb[4] = {32, (uint32_t)V, (uint32_t)(p.NT * p.FT), 1};
+  if (make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, x, 4, xd, xst, xb)) return 1;
+  const uint64_t wd[4] = {(uint64_t)p.Cin, (uint64_t)CO, (uint64_t)p.K, 2};
+  const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)p.K * CO * p.Cin * 2};
+  const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
+  if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn_tc2<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  k_gcn_tc2<CO><<<grid, kGcn2Threads, smem, st>>>(tm_x, tm_w, p);
+  return 0;
+}
+
+inline int launch_gcn_tc2(int CO, const float *x, const __nv_bfloat16 *wp, const GcnTc2Params &p, int N,
+                          int T_full, int fstride, cudaStream_t st) {
+  switch (CO) {
+    case 64: return launch_gcn_tc2_c<64>(x, wp, p, N, T_full, fstride, st);
+    case 128: return launch_gcn_tc2_c<128>(x, wp, p, N, T_full, fstride, st);
+    case 256: return launch_gcn_tc2_c<256>(x, wp, p, N, T_full, fstride, st);
+  }
+  return fail("gcn tensor-core kernel: unsupported channel count %d", CO);
+}
+
+// ---- v2 launcher -----------------------------------------------------------------
+inline bool tcn_tc2_supported(int C, int V, int G, int stride, int T) {
+  return (C == 64 || C == 128 || C == 256) && V >= 2 && V <= 64 && G <= 15 && (G & 1) &&
+         (stride == 1 || (stride == 2 && T >= 2));
 }
 
 // u planes: bf16 [planes][N][T][V][C] (T = input frames); wp: bf16 [2][G][C][C]; out/res rows over T_out
@@ -1154,14 +1585,14 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
       a_rows = (nf[0] + nf[1]) * V + spill;
     }
     p.a_stage_bytes = (a_rows * 128 + 1023) & ~1023;
-    const int left = kMaxSmem - 2 * p.a_stage_bytes - 1024 - 512 - 1024;
+    const int left = kMaxSmem - 2 * p.a_stage_bytes - 2048 - 512 - 1024;
     p.b_stages = left / (C * 128);
     if (p.b_stages > 8) p.b_stages = 8;
     if (p.b_stages >= 2) break;
   }
   p.groups_per_trial = (p.T_out + p.NT * p.FT - 1) / (p.NT * p.FT);
   p.items = N * p.groups_per_trial;
-  const int smem = 2 * p.a_stage_bytes + p.b_stages * C * 128 + 1024 + 512 + 1024;
+  const int smem = 2 * p.a_stage_bytes + p.b_stages * C * 128 + 2048 + 512 + 1024;
 
   CUtensorMap tm_u0, tm_u1, tm_w;
   const uint64_t plane_stride = (uint64_t)N * T * V * C * 2;

@@ -1,6 +1,8 @@
 // C ABI of the B200-native ST-GCN / RT-ST-GCN forward path (see include/stgcn_b200.h).
 #include "../../include/stgcn_b200.h"
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
@@ -10,6 +12,17 @@ using namespace stgcn;
 namespace {
 
 constexpr float kEps = 1e-5f;  // reference LayerNorm / BatchNorm eps (layernorm.py:8)
+
+// measurement aid (STGCN_DEBUG=1: skip tensor-core epilogues, 2: skip transform math); results are
+// then wrong on purpose -- used only to attribute time between pipeline roles
+inline int debug_mode() {
+  static int m = -1;
+  if (m < 0) {
+    const char *e = getenv("STGCN_DEBUG");
+    m = e ? atoi(e) : 0;
+  }
+  return m;
+}
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int round4(int x) { return (x + 3) & ~3; }
@@ -153,14 +166,17 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
         tc::k_split_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.gcn_w, wg16, nw);
         STGCN_LAUNCH_OK();
       }
-      tc::GcnTcParams g{};
-      g.T = T; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
-      g.csr_ptr = kw_ptr; g.csr_va = kw_va; g.bzT = bzT;
-      g.n_w = d.n1_w; g.n_b = d.n1_b;
-      g.out_hi = u16; g.out_lo = u16_lo; g.out_f32 = u;
-      g.eps = kEps;
+      tc::GcnTc2Params g{};
+      g.T_out = T; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
+      g.csr_ptr = kw_ptr; g.csr_va = kw_va;
+      g.epi.bias = bzT; g.epi.bias_sc = V; g.epi.bias_sw = 1;
+      g.epi.n_w = d.n1_w; g.epi.n_b = d.n1_b;
+      g.epi.out_hi = u16; g.epi.out_lo = u16_lo; g.epi.out_f32 = u;
+      g.epi.relu = 1;
+      g.epi.eps = kEps;
+      g.epi.debug = debug_mode();
       ProfScope ps(KC_GEMM_1X1, st);
-      if (tc::launch_gcn_tc(d.c_out, x, wg16, g, N, st)) return 1;
+      if (tc::launch_gcn_tc2(d.c_out, x, wg16, g, N, T, 1, st)) return 1;
       STGCN_LAUNCH_OK();
     }
     ws.release(m2);
@@ -206,8 +222,12 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     const long long nw = (long long)d.c_out * d.c_out * d.kernel;
     __nv_bfloat16 *wp16 = ws.take<__nv_bfloat16>((size_t)2 * nw);
     // channel-changing / strided residual: LN_R(conv1x1_stride(x)) precomputed into `resb`
-    float *resb = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
-    float *qr = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
+    const bool res_conv = d.residual == STGCN_RES_CONV;
+    const bool res_tc = res_conv && tc::gcn_tc_supported(d.c_in, d.c_out, V, 1);
+    const long long nwr = (long long)d.c_out * d.c_in;
+    float *resb = res_conv ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
+    float *qr = (res_conv && !res_tc) ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
+    __nv_bfloat16 *wr16 = res_tc ? ws.take<__nv_bfloat16>((size_t)2 * nwr) : nullptr;
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
       {
@@ -215,7 +235,25 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
         tc::k_pack_tcn_w_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.tcn_w, wp16, d.c_out, d.c_out, d.kernel);
         STGCN_LAUNCH_OK();
       }
-      if (resb) {
+      if (res_tc) {
+        {
+          ProfScope ps(KC_MISC, st);
+          tc::k_split_bf16<<<cdiv(nwr, 256), 256, 0, st>>>(d.res_w, wr16, nwr);
+          STGCN_LAUNCH_OK();
+        }
+        tc::GcnTc2Params g{};
+        g.T_out = T_out; g.V = V; g.K = 1; g.Cin = d.c_in; g.planes = planes;
+        g.identity = 1;
+        g.epi.bias = d.res_b; g.epi.bias_sc = 1; g.epi.bias_sw = 0;
+        g.epi.n_w = d.nr_w; g.epi.n_b = d.nr_b;
+        g.epi.out_f32 = resb;
+        g.epi.relu = 0;
+        g.epi.eps = kEps;
+        g.epi.debug = debug_mode();
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcn_tc2(d.c_out, x, wr16, g, N, T, d.stride, st)) return 1;
+        STGCN_LAUNCH_OK();
+      } else if (res_conv) {
         if (launch_gemm(x, d.res_w, d.res_b, qr, N, T, V, d.c_in, d.c_out, 1, d.stride, st)) return 1;
         FrameArgs a{};
         a.producer = FRAME_LOAD;
@@ -231,10 +269,13 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       tc::TcnTc2Params p{};
       p.T_out = T_out; p.V = V; p.G = d.kernel;
       p.planes = planes;
-      p.bias = d.tcn_b; p.n_w = d.n2_w; p.n_b = d.n2_b;
-      p.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
-      p.out = out;
-      p.eps = kEps;
+      p.epi.bias = d.tcn_b; p.epi.bias_sc = 1; p.epi.bias_sw = 0;
+      p.epi.n_w = d.n2_w; p.epi.n_b = d.n2_b;
+      p.epi.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
+      p.epi.out_f32 = out;
+      p.epi.relu = 1;
+      p.epi.eps = kEps;
+      p.epi.debug = debug_mode();
       ProfScope ps(KC_GEMM_TCN, st);
       if (tc::launch_tcn_tc2(d.c_out, u16, wp16, p, N, T, d.stride, st)) return 1;
       STGCN_LAUNCH_OK();
