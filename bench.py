@@ -42,7 +42,7 @@ def parse():
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     p.add_argument('--trials', type=int, default=256, help='trials per GPU')
     p.add_argument('--frames', type=int, default=4000, help='frames per trial')
-    p.add_argument('--math', default=os.environ.get('STGCN_MATH', 'fp32'), choices=['fp32', 'bf16x3', 'bf16'])
+    p.add_argument('--math', default=os.environ.get('STGCN_MATH', 'bf16x3'), choices=['fp32', 'bf16x3', 'bf16'])
     p.add_argument('--norm', default='LayerNorm', choices=['LayerNorm', 'BatchNorm'])
     p.add_argument('--rt-streams', type=int, default=4096)
     p.add_argument('--rt-steps', type=int, default=200)

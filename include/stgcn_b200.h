@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STGCN_ABI_VERSION 1
+#define STGCN_ABI_VERSION 2
 
 enum { STGCN_NORM_LAYERNORM = 0, STGCN_NORM_BATCHNORM = 1 };
 enum { STGCN_RES_NONE = 0, STGCN_RES_IDENTITY = 1, STGCN_RES_CONV = 2 };
@@ -84,6 +84,11 @@ typedef struct stgcn_model_desc {
   const float *fcn_in_w, *fcn_in_b;
   const float *fcn_out_w, *fcn_out_b;
   const stgcn_layer_desc *layers;   /* HOST pointer to num_layers descriptors */
+  /* Optional: operands prepared once per set of weights by stgcn_model_prepare (bf16 hi/lo
+   * weight planes, adjacency CSR, bias through the adjacency).  NULL: every forward rebuilds
+   * them in its workspace (a few small kernels per layer). */
+  const void *prepared;
+  size_t prepared_bytes;
 } stgcn_model_desc;
 
 /* ---- library ------------------------------------------------------------- */
@@ -127,6 +132,13 @@ size_t stgcn_graphconv_workspace_bytes(int N, int c_in, int c_out, int K, int T,
 int stgcn_graphconv_forward(const float *x, const float *w, const float *bias, const float *A,
                             int a_per_sample, float *y, int N, int c_in, int c_out, int K,
                             int T, int V, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- prepared operands ------------------------------------------------------ */
+/* Bytes of the device buffer stgcn_model_prepare fills (0 if nothing to prepare). */
+size_t stgcn_model_prepare_bytes(const stgcn_model_desc *m);
+/* Fill `prepared` from the parameters the descriptor points at (enqueued on `stream`); then set
+ * m->prepared / m->prepared_bytes.  Must be repeated when a parameter or the adjacency changes. */
+int stgcn_model_prepare(const stgcn_model_desc *m, void *prepared, size_t prepared_bytes, void *stream);
 
 /* ---- ST-GCN layer / model --------------------------------------------------- */
 size_t stgcn_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int N, int T);

@@ -13,6 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, 'csrc', 'libstgcn_b200.so')
 
+ABI_VERSION = 2
 NORM_LAYERNORM, NORM_BATCHNORM = 0, 1
 RES_NONE, RES_IDENTITY, RES_CONV = 0, 1, 2
 MATH_FP32, MATH_BF16X3, MATH_BF16 = 0, 1, 2
@@ -34,7 +35,7 @@ class ModelDesc(ctypes.Structure):
                  'reserved')] + \
                [(n, c_void_p) for n in
                 ('norm_in_w', 'norm_in_b', 'fcn_in_w', 'fcn_in_b', 'fcn_out_w', 'fcn_out_b')] + \
-               [('layers', POINTER(LayerDesc))]
+               [('layers', POINTER(LayerDesc)), ('prepared', c_void_p), ('prepared_bytes', c_size_t)]
 
 
 # name -> (restype, argtypes); every symbol include/stgcn_b200.h declares
@@ -55,6 +56,8 @@ SYMBOLS = {
     'stgcn_graphconv_workspace_bytes': (c_size_t, [c_int] * 6),
     'stgcn_graphconv_forward': (c_int, [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 6 +
                                 [c_void_p, c_size_t, c_void_p]),
+    'stgcn_model_prepare_bytes': (c_size_t, [_P_MODEL]),
+    'stgcn_model_prepare': (c_int, [_P_MODEL, c_void_p, c_size_t, c_void_p]),
     'stgcn_layer_workspace_bytes': (c_size_t, [_P_LAYER, c_int, c_int, c_int, c_int]),
     'stgcn_layer_forward': (c_int, [_P_LAYER, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                     c_void_p, c_size_t, c_void_p]),
@@ -98,7 +101,7 @@ def load():
         fn = getattr(lib, name)           # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.stgcn_abi_version() != 1:
+    if lib.stgcn_abi_version() != ABI_VERSION:
         raise RuntimeError("libstgcn_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -155,3 +158,17 @@ class Workspace:
             self.buf = None
             self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         return self.buf
+
+
+def prepare_model(m, device):
+    """Build the prepared operands (bf16 weight planes, adjacency CSR, ...) for ModelDesc ``m``
+    once; returns the device buffer that must stay alive as long as ``m`` is used."""
+    lib = load()
+    nbytes = lib.stgcn_model_prepare_bytes(ctypes.byref(m))
+    if nbytes == 0 or m.math == MATH_FP32:
+        return None
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    check(lib.stgcn_model_prepare(ctypes.byref(m), ptr(buf), nbytes, stream_ptr(device)))
+    m.prepared = buf.data_ptr()
+    m.prepared_bytes = nbytes
+    return buf

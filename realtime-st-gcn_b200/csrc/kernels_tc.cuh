@@ -68,12 +68,12 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 // Bounded wait: a protocol bug must surface as a trap, never as a hung GPU.  Waiters back off
 // with nanosleep so that spinning warps do not steal issue slots from the working warps
 // (ncu on the first persistent kernel showed ~40% of all issued instructions were wait spins).
-template <int kSleepNs = 64>
+template <int kSleepNs = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   long long t0 = 0;
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  while (!mbar_try_wait(bar, parity)) {
     if (kSleepNs > 0) __nanosleep(kSleepNs);
     if ((++spins & 1023u) == 0) {
       const long long now = clock64();
@@ -159,6 +159,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// store 32 lanes x 16 consecutive fp32 columns (thread i of the warp writes lane base_lane + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float *v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+      "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+      "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+      "r"(__float_as_uint(v[15]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 (1024 B)
 //   [46,48) version = 1 | [49,52) base offset = 0 (all starts are 1024-B-atom aligned + k*32 B)
@@ -172,10 +187,48 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same descriptor split into its constant upper half and the address-dependent lower half,
+// so that an issue loop advances a descriptor with one 32-bit add (32 B along K = +2).
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
+
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// Measurement aid (STGCN_DEBUG & 4): cycles spent per pipeline role / wait, summed by CTA 0.
+//  0 MMA wait TMEM-empty   1 MMA wait A-full     2 MMA wait B-full      3 MMA thread total
+//  4 A/x producer wait     5 B producer wait     6 epilogue wait TMEM   7 epilogue tile work
+//  8 transform wait x-full 9 transform wait A-empty 10 transform compute 11 items (CTA 0)
+__device__ unsigned long long g_dbg[16];
+struct DbgTimer {
+  long long t0;
+  bool on;
+  __device__ __forceinline__ DbgTimer(bool enable) : t0(0), on(enable) {
+    if (on) t0 = clock64();
+  }
+  __device__ __forceinline__ void stop(long long &acc) {
+    if (on) acc += clock64() - t0;
+  }
+};
+__device__ __forceinline__ void dbg_flush(bool on, int cat, long long v) {
+  if (on) atomicAdd(&g_dbg[cat], (unsigned long long)v);
+}
+
+// Streaming 16-B global load: no L1 allocation, so that the per-CTA LayerNorm parameter tables
+// (re-read for every tile) stay L1-resident next to the row streams (residual, FIFO state).
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -208,214 +261,6 @@ __global__ void k_pack_tcn_w_bf16(const float *__restrict__ w, __nv_bfloat16 *__
 }
 
 // --------------------------------------------------------------------------- //
-// Temporal (Gamma x 1, stride 1) convolution as a TMA-fed tcgen05 implicit GEMM, fused with
-// bias + LayerNorm(C,V) + residual + ReLU  (stgcn.py:154-161,193).
-//
-//   out[n,t,v,:] = relu( LN_{C,V}( sum_j Wt[:, :, j] u[n, t+j-pad, v, :] + bt ) + res[n,t,v,:] )
-//
-// One CTA = 8 consecutive output frames of one trial = two 128-row UMMA tiles (4 frames x 32
-// padded joint rows each), all C output channels (so the LayerNorm statistics of a frame are
-// CTA-local: one epilogue warp owns one frame, one lane one joint).  The input window of 16
-// frames is staged ONCE per 64-channel K chunk; every temporal tap reuses it through a
-// descriptor whose start address is shifted by whole frames (32 rows = 4096 B, swizzle-atom
-// aligned).  TMA zero-fills joints 25..31 and frames outside [0,T): the conv's zero padding.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM -> registers -> HBM).
-// --------------------------------------------------------------------------- //
-constexpr int kFrameRows = 32;
-constexpr int kOutFrames = 8;
-constexpr int kInFrames = 16;
-constexpr int kABytes = kInFrames * kFrameRows * 128;  // 65536: one plane, one 64-channel chunk
-constexpr int kTcnThreads = 192;
-
-template <int C>
-struct TcnCfg {
-  static constexpr int kBBytes = C * 128;                               // [C rows][64 ch] bf16
-  static constexpr int kStages = C == 64 ? 8 : (C == 128 ? 5 : 3);
-  static constexpr int kBarBytes = 256;
-  static constexpr int kSmem = 2 * kABytes + kStages * kBBytes + kBarBytes + 1024;  // + align slack
-  static constexpr int kTmemCols = 2 * C < 32 ? 32 : 2 * C;             // 128 / 256 / 512 (powers of two)
-};
-
-struct TcnTcParams {
-  int T, V, G, pad;
-  int planes;           // 1: bf16, 2: bf16x3
-  const float *bias;    // [C]
-  const float *n_w;     // [C][V]
-  const float *n_b;
-  const float *res;     // fp32 [rows][C] or nullptr
-  float *out;           // fp32 [rows][C]
-  float eps;
-};
-
-template <int C>
-__global__ void __launch_bounds__(kTcnThreads, 1)
-    k_tcn_tc(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_w,
-             const TcnTcParams p) {
-  using Cfg = TcnCfg<C>;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + 2 * kABytes;
-  const uint32_t sBar = sB + S * Cfg::kBBytes;
-  // barrier map (8 B each): fullA[2] emptyA[2] fullB[S] emptyB[S] tmem_full, then tmem ptr
-  const uint32_t bFullA = sBar, bEmptyA = sBar + 16, bFullB = sBar + 32, bEmptyB = bFullB + 8 * S;
-  const uint32_t bTmemFull = bEmptyB + 8 * S;
-  const uint32_t sTmemPtr = bTmemFull + 8;
-  uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.y;
-  const int t0 = blockIdx.x * kOutFrames;
-  const int KC = C / 64;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_u);
-    tma_prefetch_desc(&tm_w);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bFullA + 8 * i, 1);
-      mbar_init(bEmptyA + 8 * i, 1);
-    }
-    for (int i = 0; i < S; ++i) {
-      mbar_init(bFullB + 8 * i, 1);
-      mbar_init(bEmptyB + 8 * i, 1);
-    }
-    mbar_init(bTmemFull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(sTmemPtr, Cfg::kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_gen;
-
-  // The K loop is a flat schedule of "A stages" (one plane of one 64-channel chunk of the
-  // 16-frame input window), each followed by the weight tiles multiplied against it:
-  //   A = hi plane: for every tap j: B = hi(j), [B = lo(j)]      (hi*hi, hi*lo)
-  //   A = lo plane: for every tap j: B = hi(j)                   (lo*hi)
-  if (warp == 0) {
-    if (lane == 0) {
-      int a_it = 0, b_it = 0;
-      for (int kc = 0; kc < KC; ++kc) {
-        for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
-          const int as = a_it & 1;
-          mbar_wait(bEmptyA + 8 * as, ((a_it >> 1) & 1) ^ 1);
-          mbar_expect_tx(bFullA + 8 * as, kABytes);
-          tma_load_5d(sA + as * kABytes, &tm_u, bFullA + 8 * as, kc * 64, 0, t0 - p.pad, n, ap);
-          const int nb = (ap == 0) ? p.planes : 1;
-          for (int j = 0; j < p.G; ++j) {
-            for (int bp = 0; bp < nb; ++bp, ++b_it) {
-              const int bs = b_it % S;
-              mbar_wait(bEmptyB + 8 * bs, ((b_it / S) & 1) ^ 1);
-              mbar_expect_tx(bFullB + 8 * bs, Cfg::kBBytes);
-              tma_load_4d(sB + bs * Cfg::kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, j, bp);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, C);
-      int a_it = 0, b_it = 0;
-      uint32_t acc = 0;
-      for (int kc = 0; kc < KC; ++kc) {
-        for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
-          const int as = a_it & 1;
-          mbar_wait(bFullA + 8 * as, (a_it >> 1) & 1);
-          tc_fence_after();
-          const int nb = (ap == 0) ? p.planes : 1;
-          for (int j = 0; j < p.G; ++j) {
-            for (int bp = 0; bp < nb; ++bp, ++b_it) {
-              const int bs = b_it % S;
-              mbar_wait(bFullB + 8 * bs, (b_it / S) & 1);
-              tc_fence_after();
-#pragma unroll
-              for (int m = 0; m < 2; ++m) {
-                const uint32_t a0 = sA + as * kABytes + (4 * m + j) * (kFrameRows * 128);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_bf16(tmem_base + m * C, umma_desc_sw128(a0 + k * 32),
-                            umma_desc_sw128(sB + bs * Cfg::kBBytes + k * 32), idesc, acc | (uint32_t)k);
-                }
-              }
-              acc = 1;
-              umma_commit(bEmptyB + 8 * bs);  // frees the weight stage when these MMAs retire
-            }
-          }
-          umma_commit(bEmptyA + 8 * as);      // frees the input-window stage
-        }
-      }
-      umma_commit(bTmemFull);                 // accumulators complete
-    }
-  } else {
-    // ---- epilogue: warp q owns TMEM lanes [32q, 32q+32) = frame q of each tile; lane = joint ----
-    const int q = warp & 3;
-    mbar_wait(bTmemFull, 0);
-    tc_fence_after();
-    const float inv_n = 1.f / (float)(p.V * C), inv_nm1 = 1.f / (float)(p.V * C - 1);
-#pragma unroll 1
-    for (int m = 0; m < 2; ++m) {
-      const int t = t0 + 4 * m + q;
-      const bool row_ok = (t < p.T) && (lane < p.V);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * C);
-      const long long row = ((long long)n * p.T + t) * p.V + lane;
-      float v[32];
-      float s = 0.f;
-#pragma unroll 1
-      for (int cb = 0; cb < C; cb += 32) {
-        tmem_ld32(taddr + cb, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s += v[i] + __ldg(p.bias + cb + i);
-      }
-      const float mean = warp_sum(row_ok ? s : 0.f) * inv_n;
-      float ss = 0.f;
-#pragma unroll 1
-      for (int cb = 0; cb < C; cb += 32) {
-        tmem_ld32(taddr + cb, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float d = v[i] + __ldg(p.bias + cb + i) - mean;
-          ss = fmaf(d, d, ss);
-        }
-      }
-      const float rstd = 1.f / sqrtf(warp_sum(row_ok ? ss : 0.f) * inv_nm1 + p.eps);
-#pragma unroll 1
-      for (int cb = 0; cb < C; cb += 32) {
-        tmem_ld32(taddr + cb, v);
-        if (row_ok) {
-          float *dst = p.out + row * C + cb;
-          const float *rs = p.res ? p.res + row * C + cb : nullptr;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cb + i + e;
-              o[e] = (v[i + e] + __ldg(p.bias + c) - mean) * rstd * __ldg(p.n_w + c * p.V + lane) +
-                     __ldg(p.n_b + c * p.V + lane);
-            }
-            if (rs) {
-              const float4 r4 = *reinterpret_cast<const float4 *>(rs + i);
-              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-            }
-            *reinterpret_cast<float4 *>(dst + i) =
-                make_float4(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f), fmaxf(o[2], 0.f), fmaxf(o[3], 0.f));
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  }
-}
-
-// --------------------------------------------------------------------------- //
 // Shared LayerNorm epilogue of the persistent kernels.  One thread owns one accumulator row
 // r = (frame r / V, joint r % V) of a 128-row tile held in TMEM (C fp32 columns):
 //   y = LN_{C,V}(acc + bias) * g + b  [+ res]  [relu]  -> fp32 rows or split-bf16 planes.
@@ -423,85 +268,142 @@ __global__ void __launch_bounds__(kTcnThreads, 1)
 // (float[2][128] in shared memory) and named barrier 1 (the 128 epilogue threads).
 // --------------------------------------------------------------------------- //
 struct EpiParams {
-  const float *bias;
-  int bias_sc, bias_sw;          // bias index = c * bias_sc + w * bias_sw
-  const float *n_w, *n_b;        // LayerNorm affine, reference layout (C, V)
+  const float *bias;             // bias index = w * bias_sw + c (contiguous in c)
+  int bias_sw;
+  const float *n_wT, *n_bT;      // LayerNorm affine transposed to (V, C) (k_transpose_affine)
   const float *res;              // fp32 [rows][C] added after the norm, or null
   float *out_f32;                // fp32 [rows][C] or null
   __nv_bfloat16 *out_hi, *out_lo;  // split-bf16 planes [rows][C] or null
   int relu;
   float eps;
   int debug;                     // measurement aid: 1 = skip the epilogue body, 2 = skip transform math
+  // RT-ST-GCN continual step (rtstgcn.py:611-625): per-stream ring FIFO and running accumulators.
+  // fifo [F][rows][C], acc [S][rows][C] (rows = streams * V), one frame counter per stream.
+  float *rt_fifo, *rt_acc;
+  const int *rt_counter;
+  int rt_F, rt_S;
+  long long rt_slot;             // elements per slot = rows * C
 };
 
 // Statistics in ONE pass over TMEM: each row accumulates sum / sum of squares of (x - shift) with
-// shift = its first element (so the squares do not cancel), giving a row mean and a row M2; the V
-// rows of a frame are then merged exactly (Chan et al.):  M2 = sum M2_r + C * sum (m_r - mean)^2.
-// `s_part` is float[2][256]; `tile_parity` alternates the half used so one barrier per tile suffices.
-template <int C>
+// shift = its first element (so the squares do not cancel), giving a partial mean and M2; the
+// partials of a frame (V rows x NH column groups) are then merged exactly (Chan et al.):
+//   M2 = sum M2_p + CH * sum (m_p - mean)^2.
+// NH epilogue warps share one TMEM lane quarter, each owning C/NH of the columns (`h`), so that
+// 128*NH threads keep loads in flight.  `s_part` is float[2][2][NH][128]; `tile_parity` alternates
+// the half used so one named barrier per tile suffices.
+constexpr int kEpiNH = 2;                       // column groups (epilogue warps per TMEM lane quarter)
+constexpr int kEpiThreads = 128 * kEpiNH;
+constexpr int kPartBytes = 2 * 2 * kEpiNH * 128 * 4;
+
+template <int C, int NH>
+__device__ __forceinline__ void frame_stats(const float *sp, int fr, int V, float eps, float &mean, float &rstd) {
+  // one pass over the frame's NH*V partials, shifted by the first partial mean so that the
+  // sum of squares does not cancel; three independent accumulation chains
+  constexpr int CH = C / NH;
+  const float ref = sp[fr * V];
+  float sd = 0.f, sdd = 0.f, sm2 = 0.f;
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    const float *pm = sp + hh * 128 + fr * V;
+    const float *pq = sp + (NH + hh) * 128 + fr * V;
+#pragma unroll 5
+    for (int j = 0; j < V; ++j) {
+      const float d = pm[j] - ref;
+      sd += d;
+      sdd = fmaf(d, d, sdd);
+      sm2 += pq[j];
+    }
+  }
+  const float inv_n = 1.f / (float)(NH * V);
+  mean = ref + sd * inv_n;
+  const float tq = sm2 + (float)CH * fmaxf(sdd - sd * sd * inv_n, 0.f);
+  rstd = 1.f / sqrtf(tq * (1.f / (float)(V * C - 1)) + eps);
+}
+
+template <int C, int NH>
 __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
                                                  int w, bool row_ok, long long row, float *s_part,
-                                                 int tile_parity) {
+                                                 int tile_parity, int h) {
   if (e.debug & 1) return;
-  const float *bias = e.bias + w * e.bias_sw;
-  float *sp = s_part + tile_parity * 256;
+  constexpr int CH = C / NH;
+  const int c0 = h * CH;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias + w * e.bias_sw + c0);
+  float *sp = s_part + tile_parity * (2 * NH * 128);
   float v[16];
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-  for (int cb = 0; cb < C; cb += 16) {
-    tmem_ld16(taddr + cb, v);
-    if (cb == 0) shift = v[0] + __ldg(bias);
+  for (int cb = 0; cb < CH; cb += 16) {
+    tmem_ld16(taddr + c0 + cb, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = __ldg(bias4 + ((e.debug & 16) ? 0 : (cb >> 2) + i));
+      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+    }
+    if (cb == 0) shift = v[0];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float d = v[i] + __ldg(bias + (cb + i) * e.bias_sc) - shift;
+      const float d = v[i] - shift;
       s1 += d;
       s2 = fmaf(d, d, s2);
     }
   }
-  const float m_r = shift + s1 * (1.f / (float)C);
-  const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)C), 0.f);
-  sp[r] = row_ok ? m_r : 0.f;
-  sp[128 + r] = row_ok ? M2_r : 0.f;
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  float mean = 0.f, rstd = 0.f;
-  if (r < RT) {
-    float tm = 0.f, tq = 0.f;
-    for (int j = 0; j < V; ++j) tm += sp[fr * V + j];
-    mean = tm * (1.f / (float)V);
-    for (int j = 0; j < V; ++j) {
-      const float dm = sp[fr * V + j] - mean;
-      tq += sp[128 + fr * V + j] + (float)C * dm * dm;
-    }
-    rstd = 1.f / sqrtf(tq * (1.f / (float)(V * C - 1)) + e.eps);
+  const float m_r = shift + s1 * (1.f / (float)CH);
+  const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)CH), 0.f);
+  sp[h * 128 + r] = row_ok ? m_r : 0.f;
+  sp[(NH + h) * 128 + r] = row_ok ? M2_r : 0.f;
+  // residual rows come from HBM: start the first loads before the barrier
+  const float4 *rs4 = (e.res && row_ok && !(e.debug & 8)) ? reinterpret_cast<const float4 *>(e.res + row * C + c0) : nullptr;
+  float4 rn[4];
+  if (rs4) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rn[i] = rs4[i];
   }
+  asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
+  float mean = 0.f, rstd = 0.f;
+  if (r < RT && !(e.debug & 64)) frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
+  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT + w * C + c0);
+  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT + w * C + c0);
 #pragma unroll 1
-  for (int cb = 0; cb < C; cb += 16) {
-    tmem_ld16(taddr + cb, v);
+  for (int cb = 0; cb < CH; cb += 16) {
+    float4 rc[4];
+    if (rs4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rc[i] = rn[i];
+      if (cb + 16 < CH) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rn[i] = rs4[((cb + 16) >> 2) + i];
+      }
+    }
+    tmem_ld16(taddr + c0 + cb, v);
     if (row_ok) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = cb + i;
-        v[i] = (v[i] + __ldg(bias + c * e.bias_sc) - mean) * rstd * __ldg(e.n_w + c * V + w) +
-               __ldg(e.n_b + c * V + w);
+      for (int i = 0; i < 4; ++i) {
+        const int pi = (e.debug & 16) ? 0 : (cb >> 2) + i;
+        const float4 b4 = __ldg(bias4 + pi);
+        const float4 g4 = __ldg(nw4 + pi);
+        const float4 o4 = __ldg(nb4 + pi);
+        v[4 * i] = (v[4 * i] + b4.x - mean) * rstd * g4.x + o4.x;
+        v[4 * i + 1] = (v[4 * i + 1] + b4.y - mean) * rstd * g4.y + o4.y;
+        v[4 * i + 2] = (v[4 * i + 2] + b4.z - mean) * rstd * g4.z + o4.z;
+        v[4 * i + 3] = (v[4 * i + 3] + b4.w - mean) * rstd * g4.w + o4.w;
       }
-      if (e.res) {
-        const float4 *rs = reinterpret_cast<const float4 *>(e.res + row * C + cb);
+      if (rs4) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 r4 = rs[i];
-          v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+          v[4 * i] += rc[i].x; v[4 * i + 1] += rc[i].y; v[4 * i + 2] += rc[i].z; v[4 * i + 3] += rc[i].w;
         }
       }
       if (e.relu) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
       }
-      if (e.out_f32) {
-        float4 *dst = reinterpret_cast<float4 *>(e.out_f32 + row * C + cb);
+      if (e.out_f32 && !(e.debug & 32)) {
+        float4 *dst = reinterpret_cast<float4 *>(e.out_f32 + row * C + c0 + cb);
 #pragma unroll
         for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
-      if (e.out_hi) {
+      if (e.out_hi && !(e.debug & 32)) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -512,15 +414,126 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
           hi[i] = *reinterpret_cast<uint32_t *>(&hh);
           lo[i] = *reinterpret_cast<uint32_t *>(&ll);
         }
-        uint4 *dh = reinterpret_cast<uint4 *>(e.out_hi + row * C + cb);
+        uint4 *dh = reinterpret_cast<uint4 *>(e.out_hi + row * C + c0 + cb);
         dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
         if (e.out_lo) {
-          uint4 *dl = reinterpret_cast<uint4 *>(e.out_lo + row * C + cb);
+          uint4 *dl = reinterpret_cast<uint4 *>(e.out_lo + row * C + c0 + cb);
           dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
       }
+    }
+  }
+}
+
+// RT-ST-GCN epilogue: the accumulator row holds z_t (graph-convolved frame, before bias).  Per
+// element, in the reference's order (rtstgcn.py:611-612, 621):
+//   acc <- (acc + z_t) + (-fifo[slot]);  fifo[slot] <- z_t;  o = acc
+// then out = relu( relu(LN_{C,V}(o)) + res ) (res optional; rtstgcn.py:548-553).  The updated
+// accumulator row is stashed back into the TMEM columns it came from (tcgen05.st) so that the
+// LayerNorm statistics need no second trip to HBM.  `b` is the stream index of this row.
+template <int C, int NH>
+__device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
+                                                 int w, bool row_ok, long long row, int b, float *s_part,
+                                                 int tile_parity, int h) {
+  if (e.debug & 1) return;
+  constexpr int CH = C / NH;
+  const int c0 = h * CH;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias + w * e.bias_sw + c0);
+  float *sp = s_part + tile_parity * (2 * NH * 128);
+  float v[16];
+  float shift = 0.f, s1 = 0.f, s2 = 0.f;
+  const int cnt = row_ok ? __ldg(e.rt_counter + b) : 0;
+  float4 *f4 = reinterpret_cast<float4 *>(e.rt_fifo + (long long)(cnt % e.rt_F) * e.rt_slot + row * C + c0);
+  float4 *a4 = reinterpret_cast<float4 *>(e.rt_acc + (long long)(cnt % e.rt_S) * e.rt_slot + row * C + c0);
+#pragma unroll 1
+  for (int cb = 0; cb < CH; cb += 16) {
+    float4 fc[4], ac[4];
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        fc[i] = f4[(cb >> 2) + i];
+        ac[i] = a4[(cb >> 2) + i];
+      }
+    }
+    tmem_ld16(taddr + c0 + cb, v);
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b4 = __ldg(bias4 + (cb >> 2) + i);
+        float4 z = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+        float4 a = ac[i];
+        a.x = (a.x + z.x) + (-fc[i].x);
+        a.y = (a.y + z.y) + (-fc[i].y);
+        a.z = (a.z + z.z) + (-fc[i].z);
+        a.w = (a.w + z.w) + (-fc[i].w);
+        f4[(cb >> 2) + i] = z;
+        a4[(cb >> 2) + i] = a;
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    if (cb == 0) shift = v[0];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d = v[i] - shift;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
+    }
+    tmem_st16(taddr + c0 + cb, v);
+  }
+  const float m_r = shift + s1 * (1.f / (float)CH);
+  const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)CH), 0.f);
+  sp[h * 128 + r] = row_ok ? m_r : 0.f;
+  sp[(NH + h) * 128 + r] = row_ok ? M2_r : 0.f;
+  const float4 *rs4 = (e.res && row_ok) ? reinterpret_cast<const float4 *>(e.res + row * C + c0) : nullptr;
+  float4 rn[4];
+  if (rs4) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rn[i] = rs4[i];
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
+  float mean = 0.f, rstd = 0.f;
+  if (r < RT) frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
+  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT + w * C + c0);
+  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT + w * C + c0);
+#pragma unroll 1
+  for (int cb = 0; cb < CH; cb += 16) {
+    float4 rc[4];
+    if (rs4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rc[i] = rn[i];
+      if (cb + 16 < CH) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rn[i] = rs4[((cb + 16) >> 2) + i];
+      }
+    }
+    tmem_ld16(taddr + c0 + cb, v);
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 g4 = __ldg(nw4 + (cb >> 2) + i);
+        const float4 o4 = __ldg(nb4 + (cb >> 2) + i);
+        v[4 * i] = fmaxf((v[4 * i] - mean) * rstd * g4.x + o4.x, 0.f);
+        v[4 * i + 1] = fmaxf((v[4 * i + 1] - mean) * rstd * g4.y + o4.y, 0.f);
+        v[4 * i + 2] = fmaxf((v[4 * i + 2] - mean) * rstd * g4.z + o4.z, 0.f);
+        v[4 * i + 3] = fmaxf((v[4 * i + 3] - mean) * rstd * g4.w + o4.w, 0.f);
+      }
+      if (rs4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[4 * i] = fmaxf(v[4 * i] + rc[i].x, 0.f);
+          v[4 * i + 1] = fmaxf(v[4 * i + 1] + rc[i].y, 0.f);
+          v[4 * i + 2] = fmaxf(v[4 * i + 2] + rc[i].z, 0.f);
+          v[4 * i + 3] = fmaxf(v[4 * i + 3] + rc[i].w, 0.f);
+        }
+      }
+      float4 *dst = reinterpret_cast<float4 *>(e.out_f32 + row * C + c0 + cb);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
   }
 }
@@ -542,11 +555,11 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
 // Stride 2: even and odd input frames are staged as two dense windows through two tensor maps
 // (frame stride 2), so every tap again reads a contiguous window.
 // --------------------------------------------------------------------------- //
-constexpr int kTcn2Threads = 224;   // warps: 0 A producer, 1 MMA, 2 B producer, 3..6 epilogue
+constexpr int kTcn2Threads = 32 * (3 + 4 * kEpiNH);   // warps: 0 A producer, 1 MMA, 2 B producer, 3.. epilogue
 
 struct TcnTc2Params {
   int T_out, V, G, planes;
-  int FT, NT;                 // frames per 128-row tile, tiles per item
+  int FT, NT, tb;             // frames per 128-row tile, tiles per item, TMEM accumulator buffers
   int groups_per_trial, items;
   int a_stage_bytes, b_stages;
   int n_loads;                // TMA loads per A stage (1: stride 1, 2: stride 2 even/odd windows)
@@ -562,16 +575,17 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
     k_tcn_tc2(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__ CUtensorMap tm_u1,
               const __grid_constant__ CUtensorMap tm_w, const TcnTc2Params p) {
   constexpr int kBBytes = C * 128;
-  constexpr int TB = (4 * C <= 512) ? 2 : 1;      // TMEM accumulator buffers (2 tiles each)
-  constexpr int kTmemCols = TB * 2 * C;           // 256 / 512 / 512
+  constexpr int kTmemCols = 512;                  // one CTA per SM: take all of TMEM
+  const int TB = p.tb;                            // accumulator buffers of NT tiles each (NT*C*TB <= 512)
+  const int buf_cols = p.NT * C;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int S = p.b_stages;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + 2 * p.a_stage_bytes;
-  const uint32_t sPart = sB + S * kBBytes;                    // float[2][256]
-  const uint32_t sBar = sPart + 2048;
+  const uint32_t sPart = sB + S * kBBytes;                    // float[2][2][NH][128]
+  const uint32_t sBar = sPart + kPartBytes;
   const uint32_t bFullA = sBar, bEmptyA = sBar + 16, bTmemFull = sBar + 32, bTmemEmpty = sBar + 48;
   const uint32_t bFullB = sBar + 64, bEmptyB = bFullB + 8 * S;
   const uint32_t sTmemPtr = bEmptyB + 8 * S;
@@ -581,6 +595,8 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = C / 64;
   const int RT = p.FT * p.V;                      // useful rows per tile
+  const bool dbg = (p.epi.debug & 4) && blockIdx.x == 0;
+  long long d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_u0);
@@ -590,7 +606,7 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
       mbar_init(bFullA + 8 * i, 1);
       mbar_init(bEmptyA + 8 * i, 1);
       mbar_init(bTmemFull + 8 * i, 1);
-      mbar_init(bTmemEmpty + 8 * i, 4);           // one arrive per epilogue warp
+      mbar_init(bTmemEmpty + 8 * i, 4 * kEpiNH);  // one arrive per epilogue warp
     }
     for (int i = 0; i < S; ++i) {
       mbar_init(bFullB + 8 * i, 1);
@@ -607,101 +623,137 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
   if (warp == 0) {
     // ---- input-window producer (runs ahead by the 2-deep A ring, independent of the weights) ----
     if (lane == 0) {
-      int a_it = 0;
+      int as = 0, a_ph = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int n = item / p.groups_per_trial;
         const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;   // first output frame
         for (int kc = 0; kc < KC; ++kc)
-          for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
-            const int as = a_it & 1;
-            mbar_wait(bEmptyA + 8 * as, ((a_it >> 1) & 1) ^ 1);
+          for (int ap = 0; ap < p.planes; ++ap) {
+            { DbgTimer tm(dbg); mbar_wait(bEmptyA + 8 * as, a_ph ^ 1); tm.stop(d0); }
             mbar_expect_tx(bFullA + 8 * as, (uint32_t)(p.load_bytes[0] + (p.n_loads > 1 ? p.load_bytes[1] : 0)));
             tma_load_5d(sA + as * p.a_stage_bytes + p.load_row[0] * 128, &tm_u0, bFullA + 8 * as, kc * 64, 0,
                         f0 + p.load_f0[0], n, ap);
             if (p.n_loads > 1)
               tma_load_5d(sA + as * p.a_stage_bytes + p.load_row[1] * 128, &tm_u1, bFullA + 8 * as, kc * 64, 0,
                           f0 + p.load_f0[1], n, ap);
+            as ^= 1;
+            if (as == 0) a_ph ^= 1;
           }
       }
+      dbg_flush(dbg, 4, d0);
     }
   } else if (warp == 2) {
     // ---- weight-tile producer ----
     if (lane == 0) {
-      int b_it = 0;
+      int bs = 0, b_ph = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x)
         for (int kc = 0; kc < KC; ++kc)
           for (int ap = 0; ap < p.planes; ++ap) {
             const int nb = (ap == 0) ? p.planes : 1;
             for (int j = 0; j < p.G; ++j)
-              for (int bp = 0; bp < nb; ++bp, ++b_it) {
-                const int bs = b_it % S;
-                mbar_wait(bEmptyB + 8 * bs, ((b_it / S) & 1) ^ 1);
+              for (int bp = 0; bp < nb; ++bp) {
+                { DbgTimer tm(dbg); mbar_wait(bEmptyB + 8 * bs, b_ph ^ 1); tm.stop(d0); }
                 mbar_expect_tx(bFullB + 8 * bs, kBBytes);
                 tma_load_4d(sB + bs * kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, j, bp);
+                if (++bs == S) { bs = 0; b_ph ^= 1; }
               }
           }
+      dbg_flush(dbg, 5, d0);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, C);
-      int a_it = 0, b_it = 0, it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        const int buf = it % TB;
-        mbar_wait(bTmemEmpty + 8 * buf, ((it / TB) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * 2 * C;
-        uint32_t acc = 0;
-        for (int kc = 0; kc < KC; ++kc)
-          for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
-            const int as = a_it & 1;
-            mbar_wait(bFullA + 8 * as, (a_it >> 1) & 1);
-            tc_fence_after();
-            const int nb = (ap == 0) ? p.planes : 1;
-            for (int j = 0; j < p.G; ++j)
-              for (int bp = 0; bp < nb; ++bp, ++b_it) {
-                const int bs = b_it % S;
-                mbar_wait(bFullB + 8 * bs, (b_it / S) & 1);
-                tc_fence_after();
+    // ---- MMA issuer: whole warp walks the schedule (uniform control flow); one elected lane
+    // issues the MMAs and commits ----
+    constexpr uint32_t idesc = umma_idesc_bf16(128, C);
+    int a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, buf = 0, t_ph = 0, it = 0;
+    DbgTimer tall(dbg);
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      { DbgTimer tm(dbg); mbar_wait(bTmemEmpty + 8 * buf, t_ph ^ 1); tm.stop(d0); }
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * buf_cols;
+      uint32_t acc = 0;
+      for (int kc = 0; kc < KC; ++kc)
+        for (int ap = 0; ap < p.planes; ++ap) {
+          { DbgTimer tm(dbg); mbar_wait(bFullA + 8 * a_s, a_ph); tm.stop(d1); }
+          tc_fence_after();
+          const uint32_t a_lo0 = umma_desc_lo(sA + a_s * p.a_stage_bytes);
+          const int nb = (ap == 0) ? p.planes : 1;
+          for (int j = 0; j < p.G; ++j) {
+            const uint32_t a_tap = a_lo0 + (uint32_t)(p.tap_row[j] * 8);        // rows * 128 B >> 4
+            for (int bp = 0; bp < nb; ++bp) {
+              { DbgTimer tm(dbg); mbar_wait(bFullB + 8 * b_s, b_ph); tm.stop(d2); }
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t b_lo = umma_desc_lo(sB + b_s * kBBytes);
                 for (int m = 0; m < p.NT; ++m) {
-                  const uint32_t a0 = sA + as * p.a_stage_bytes + (p.tap_row[j] + m * RT) * 128;
+                  const uint32_t a_lo = a_tap + (uint32_t)(m * RT * 8);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_bf16(tacc + m * C, umma_desc_sw128(a0 + k * 32),
-                              umma_desc_sw128(sB + bs * kBBytes + k * 32), idesc, acc | (uint32_t)k);
+                    umma_bf16(tacc + m * C, umma_desc_join(a_lo + 2 * k), umma_desc_join(b_lo + 2 * k), idesc,
+                              acc | (uint32_t)k);
                 }
-                acc = 1;
-                umma_commit(bEmptyB + 8 * bs);
+                umma_commit(bEmptyB + 8 * b_s);
               }
-            umma_commit(bEmptyA + 8 * as);
+              __syncwarp();
+              acc = 1;
+              if (++b_s == S) { b_s = 0; b_ph ^= 1; }
+            }
           }
-        umma_commit(bTmemFull + 8 * buf);
-      }
+          if (elect_one()) umma_commit(bEmptyA + 8 * a_s);
+          __syncwarp();
+          a_s ^= 1;
+          if (a_s == 0) a_ph ^= 1;
+        }
+      if (elect_one()) umma_commit(bTmemFull + 8 * buf);
+      __syncwarp();
+      if (++buf == TB) { buf = 0; t_ph ^= 1; }
+    }
+    tall.stop(d3);
+    if (lane == 0) {
+      dbg_flush(dbg, 0, d0); dbg_flush(dbg, 1, d1); dbg_flush(dbg, 2, d2); dbg_flush(dbg, 3, d3);
+      dbg_flush(dbg, 11, it);
     }
   } else {
-    // ---- epilogue: thread <-> accumulator row r = 32*(warp&3) + lane = (frame r / V, joint r % V) ----
+    // ---- epilogue: thread <-> accumulator row r = 32*(warp&3) + lane = (frame r / V, joint r % V);
+    // the kEpiNH warps that share a TMEM lane quarter split the channel range between them ----
     const int q = warp & 3;
+    const int h = (warp - 3) >> 2;
     const int r = q * 32 + lane;
     const int fr = r / p.V, w = r - fr * p.V;
-    int it = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const int buf = it % TB;
+    int buf = 0, t_ph = 0, par = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int n = item / p.groups_per_trial;
       const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;
-      mbar_wait(bTmemFull + 8 * buf, (it / TB) & 1);
+      if (p.epi.res && r < RT) {
+        // pull this thread's residual rows towards L2 while the MMAs of the item are still running
+        for (int m = 0; m < p.NT; ++m) {
+          const int t = f0 + m * p.FT + fr;
+          if (t < p.T_out) {
+            const char *rp = reinterpret_cast<const char *>(p.epi.res + (((long long)n * p.T_out + t) * p.V + w) * C +
+                                                            h * (C / kEpiNH));
+#pragma unroll
+            for (int o = 0; o < (C / kEpiNH) * 4; o += 128) prefetch_l2(rp + o);
+          }
+        }
+      }
+      { DbgTimer tm(dbg); mbar_wait(bTmemFull + 8 * buf, t_ph); tm.stop(d0); }
       tc_fence_after();
+      DbgTimer tw(dbg);
 #pragma unroll 1
-      for (int m = 0; m < p.NT; ++m) {
+      for (int m = 0; m < p.NT; ++m, par ^= 1) {
         const int t = f0 + m * p.FT + fr;
         const bool row_ok = (r < RT) && (t < p.T_out);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * C + m * C);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<C>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, s_part, m & 1);
+        ln_epilogue_tile<C, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, s_part, par, h);
       }
       // accumulator buffer drained: hand it back to the MMA issuer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bTmemEmpty + 8 * buf);
+      if (++buf == TB) { buf = 0; t_ph ^= 1; }
+      tw.stop(d1);
     }
+    if (warp == 3 && lane == 0) { dbg_flush(dbg, 6, d0); dbg_flush(dbg, 7, d1); }
   }
   tc_fence_before();
   __syncthreads();
@@ -711,315 +763,8 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
   }
 }
 
-// --------------------------------------------------------------------------- //
-// Graph-convolution stage on tensor cores, fused with LayerNorm(C,V) + ReLU
-// (tgcn.py:70-79 + stgcn.py:152-153):
-//
-//   u[n,t,w,:] = relu( LN_{C,V}( sum_k sum_v A[k,v,w] * (Wg_k x[n,t,v,:] + bg_k) ) )
-//
-// The 1x1 feature transform and the V x V adjacency contraction act on different indices, so
-// they commute: the contraction is applied FIRST, on the C_in-channel input tile staged in
-// shared memory (A is a tree adjacency: ~1 non-zero per (k,w), kept in CSR, dense A still
-// works), producing xa_k[(t,w), ci] = sum_v A[k,v,w] x[(t,v), ci]; then ONE GEMM with
-// K = 3*C_in gives z directly:  z[(t,w), c] = sum_k sum_ci xa_k[(t,w),ci] Wg[k*C_out+c, ci].
-// That keeps the whole z tile (8 frames x C_out) in TMEM, so the LayerNorm statistics are one
-// warp-shuffle reduction per frame in the epilogue, and it needs no 3*C_out-wide intermediate.
-// The bias term flows through A: bz[w,c] = sum_k bg[k*C_out+c] * colsum_k[w] (precomputed).
-//
-// Warp roles: 0 = TMA producer (fp32 input tile + bf16 weight tiles), 1 = MMA issuer,
-// 2..9 = transform warps (contraction + bf16 hi/lo split -> swizzled UMMA A operand in smem),
-// of which 2..5 then run the epilogue.
-// --------------------------------------------------------------------------- //
-constexpr int kGcnThreads = 320;
-constexpr int kGcnXform = 8;                 // transform warps
-constexpr int kGcnAStage = 2 * 128 * 128;    // 2 tiles x 128 rows x 128 B = 32768
-constexpr int kGcnARing = 3;
-constexpr int kGcnCsrMax = 384;              // CSR entries cached in shared memory (tree graphs: ~75)
-constexpr int kGcnCsrBytes = 4096;           // ptr[K*V+1] + kGcnCsrMax (v, a) pairs
-constexpr int kGcnMaxJoints = 4;             // joints per transform warp (V <= 32, 8 warps)
-
-template <int CO>
-struct GcnCfg {
-  static constexpr int kBBytes = CO * 128;
-  static constexpr int kStages = CO == 256 ? 2 : 4;
-  static constexpr int kTmemCols = 2 * CO;
-  // input tile: 8 frames x V joints x 64 fp32 channels, rounded up to 1 KB
-  static int xs_bytes(int V) { return (kOutFrames * V * 64 * 4 + 1023) & ~1023; }
-  static int smem(int V) {
-    return kGcnARing * kGcnAStage + xs_bytes(V) + kStages * kBBytes + kGcnCsrBytes + 256 + 1024;
-  }
-};
-
-struct GcnTcParams {
-  int T, V, K, Cin;
-  int planes;
-  int xs_alloc;         // bytes reserved for the fp32 input tile (GcnCfg::xs_bytes)
-  const int *csr_ptr;   // [K*V + 1], (k,w)-major
-  const int2 *csr_va;   // per entry: (source joint v, bits of A[k,v,w])
-  const float *bzT;     // [CO][V] bias through the adjacency
-  const float *n_w, *n_b;
-  __nv_bfloat16 *out_hi, *out_lo;   // [rows][CO] planes (tensor-core temporal stage) or null
-  float *out_f32;                   // [rows][CO] (CUDA-core temporal stage) or null
-  float eps;
-};
-
-
-template <int CO>
-__global__ void __launch_bounds__(kGcnThreads, 1)
-    k_gcn_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-             const GcnTcParams p) {
-  using Cfg = GcnCfg<CO>;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t sA = smem_base;
-  const uint32_t sXs = sA + kGcnARing * kGcnAStage;
-  const uint32_t sB = sXs + p.xs_alloc;
-  const uint32_t sCsr = sB + S * Cfg::kBBytes;
-  const uint32_t sBar = sCsr + kGcnCsrBytes;
-  const uint32_t bXsFull = sBar, bXsEmpty = sBar + 8;
-  const uint32_t bAFull = sBar + 16, bAEmpty = bAFull + 8 * kGcnARing;
-  const uint32_t bFullB = bAEmpty + 8 * kGcnARing, bEmptyB = bFullB + 8 * S;
-  const uint32_t bTmemFull = bEmptyB + 8 * S;
-  const uint32_t sTmemPtr = bTmemFull + 8;
-  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
-  const float *xs = reinterpret_cast<const float *>(gen_base + (sXs - smem_base));
-  uint8_t *a_gen = gen_base;  // A ring starts at smem_base
-  int *s_ptr = reinterpret_cast<int *>(gen_base + (sCsr - smem_base));          // [K*V + 1]
-  int2 *s_va = reinterpret_cast<int2 *>(gen_base + (sCsr - smem_base) + 1024);  // [kGcnCsrMax]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.y;
-  const int t0 = blockIdx.x * kOutFrames;
-  const int KC = p.Cin / 64;
-  const uint32_t xs_bytes = (uint32_t)(kOutFrames * p.V * 64 * 4);
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_x);
-    tma_prefetch_desc(&tm_w);
-    mbar_init(bXsFull, 1);
-    mbar_init(bXsEmpty, kGcnXform);
-    for (int i = 0; i < kGcnARing; ++i) {
-      mbar_init(bAFull + 8 * i, kGcnXform);
-      mbar_init(bAEmpty + 8 * i, 1);
-    }
-    for (int i = 0; i < S; ++i) {
-      mbar_init(bFullB + 8 * i, 1);
-      mbar_init(bEmptyB + 8 * i, 1);
-    }
-    mbar_init(bTmemFull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(sTmemPtr, Cfg::kTmemCols);
-  const int nnz = __ldg(p.csr_ptr + p.K * p.V);
-  const bool csr_smem = nnz <= kGcnCsrMax && p.K * p.V + 1 <= 256;
-  if (csr_smem) {
-    for (int i = threadIdx.x; i <= p.K * p.V; i += blockDim.x) s_ptr[i] = __ldg(p.csr_ptr + i);
-    for (int i = threadIdx.x; i < nnz; i += blockDim.x) s_va[i] = __ldg(p.csr_va + i);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_gen;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int b_it = 0;
-      for (int kc = 0; kc < KC; ++kc) {
-        mbar_wait(bXsEmpty, (kc & 1) ^ 1);
-        mbar_expect_tx(bXsFull, xs_bytes);
-        tma_load_4d(sXs, &tm_x, bXsFull, kc * 64, 0, t0, n);
-        for (int k = 0; k < p.K; ++k)
-          for (int ap = 0; ap < p.planes; ++ap) {
-            const int nb = (ap == 0) ? p.planes : 1;
-            for (int bp = 0; bp < nb; ++bp, ++b_it) {
-              const int bs = b_it % S;
-              mbar_wait(bEmptyB + 8 * bs, ((b_it / S) & 1) ^ 1);
-              mbar_expect_tx(bFullB + 8 * bs, Cfg::kBBytes);
-              tma_load_4d(sB + bs * Cfg::kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, k, bp);
-            }
-          }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, CO);
-      int a_it = 0, b_it = 0;
-      uint32_t acc = 0;
-      for (int kc = 0; kc < KC; ++kc)
-        for (int k = 0; k < p.K; ++k)
-          for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
-            const int as = a_it % kGcnARing;
-            mbar_wait(bAFull + 8 * as, (a_it / kGcnARing) & 1);
-            tc_fence_after();
-            const int nb = (ap == 0) ? p.planes : 1;
-            for (int bp = 0; bp < nb; ++bp, ++b_it) {
-              const int bs = b_it % S;
-              mbar_wait(bFullB + 8 * bs, (b_it / S) & 1);
-              tc_fence_after();
-#pragma unroll
-              for (int m = 0; m < 2; ++m) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16(tmem_base + m * CO, umma_desc_sw128(sA + as * kGcnAStage + m * 16384 + kk * 32),
-                            umma_desc_sw128(sB + bs * Cfg::kBBytes + kk * 32), idesc, acc | (uint32_t)kk);
-              }
-              acc = 1;
-              umma_commit(bEmptyB + 8 * bs);
-            }
-            umma_commit(bAEmpty + 8 * as);
-          }
-      umma_commit(bTmemFull);
-    }
-  } else {
-    // ---- transform warps: xa_k = A_k-contraction of the staged fp32 tile -> bf16 planes ----
-    // Warp tw owns joints w = tw, tw+8, ... for all 8 frames (the 8 frames share every CSR
-    // entry, giving 8 independent shared-memory loads per entry); lane owns channels 2l, 2l+1.
-    // The fp32 results stay in registers between the hi-plane and the lo-plane stage.
-    const int tw = warp - 2;
-    int a_it = 0;
-    float2 xa[kGcnMaxJoints][kOutFrames];
-    for (int kc = 0; kc < KC; ++kc) {
-      mbar_wait(bXsFull, kc & 1);
-      for (int k = 0; k < p.K; ++k)
-        for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
-          const int as = a_it % kGcnARing;
-          if (ap == 0) {
-#pragma unroll
-            for (int jw = 0; jw < kGcnMaxJoints; ++jw) {
-              const int w = tw + jw * kGcnXform;
-#pragma unroll
-              for (int f = 0; f < kOutFrames; ++f) xa[jw][f] = make_float2(0.f, 0.f);
-              if (w < p.V) {
-                const int e0 = csr_smem ? s_ptr[k * p.V + w] : __ldg(p.csr_ptr + k * p.V + w);
-                const int e1 = csr_smem ? s_ptr[k * p.V + w + 1] : __ldg(p.csr_ptr + k * p.V + w + 1);
-                for (int e = e0; e < e1; ++e) {
-                  const int2 va = csr_smem ? s_va[e] : __ldg(p.csr_va + e);
-                  const float a = __int_as_float(va.y);
-                  const float *xr = xs + va.x * 64 + 2 * lane;
-#pragma unroll
-                  for (int f = 0; f < kOutFrames; ++f) {
-                    const float2 xv = *reinterpret_cast<const float2 *>(xr + f * p.V * 64);
-                    xa[jw][f].x = fmaf(a, xv.x, xa[jw][f].x);
-                    xa[jw][f].y = fmaf(a, xv.y, xa[jw][f].y);
-                  }
-                }
-              }
-            }
-          }
-          mbar_wait(bAEmpty + 8 * as, ((a_it / kGcnARing) & 1) ^ 1);
-          uint8_t *stage = a_gen + as * kGcnAStage;
-#pragma unroll
-          for (int jw = 0; jw < kGcnMaxJoints; ++jw) {
-            const int w = tw + jw * kGcnXform;
-            if (w < p.V) {
-#pragma unroll
-              for (int f = 0; f < kOutFrames; ++f) {
-                __nv_bfloat16 hx, lx, hy, ly;
-                split_bf16(xa[jw][f].x, hx, lx);
-                split_bf16(xa[jw][f].y, hy, ly);
-                const __nv_bfloat162 pk = ap == 0 ? __nv_bfloat162(hx, hy) : __nv_bfloat162(lx, ly);
-                const int R = f * kFrameRows + w;               // row in the 256-row stage
-                const int chunk = (lane >> 2) ^ (R & 7);        // 128B swizzle: 16B chunk ^ (row % 8)
-                *reinterpret_cast<__nv_bfloat162 *>(stage + R * 128 + chunk * 16 + (lane & 3) * 4) = pk;
-              }
-            }
-          }
-          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bAFull + 8 * as);
-        }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bXsEmpty);
-    }
-    if (warp < 6) {
-      // ---- epilogue (warps 2..5): one frame per warp, one joint per lane ----
-      const int q = warp & 3;
-      mbar_wait(bTmemFull, 0);
-      tc_fence_after();
-      const float inv_n = 1.f / (float)(p.V * CO), inv_nm1 = 1.f / (float)(p.V * CO - 1);
-      const int lv = lane < p.V ? lane : 0;
-#pragma unroll 1
-      for (int m = 0; m < 2; ++m) {
-        const int t = t0 + 4 * m + q;
-        const bool row_ok = (t < p.T) && (lane < p.V);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * CO);
-        const long long row = ((long long)n * p.T + t) * p.V + lane;
-        float v[32];
-        float s = 0.f;
-#pragma unroll 1
-        for (int cb = 0; cb < CO; cb += 32) {
-          tmem_ld32(taddr + cb, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s += v[i] + __ldg(p.bzT + (cb + i) * p.V + lv);
-        }
-        const float mean = warp_sum(row_ok ? s : 0.f) * inv_n;
-        float ss = 0.f;
-#pragma unroll 1
-        for (int cb = 0; cb < CO; cb += 32) {
-          tmem_ld32(taddr + cb, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float d = v[i] + __ldg(p.bzT + (cb + i) * p.V + lv) - mean;
-            ss = fmaf(d, d, ss);
-          }
-        }
-        const float rstd = 1.f / sqrtf(warp_sum(row_ok ? ss : 0.f) * inv_nm1 + p.eps);
-#pragma unroll 1
-        for (int cb = 0; cb < CO; cb += 32) {
-          tmem_ld32(taddr + cb, v);
-          if (row_ok) {
-            float o[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = cb + i;
-              const float y = (v[i] + __ldg(p.bzT + c * p.V + lane) - mean) * rstd * __ldg(p.n_w + c * p.V + lane) +
-                              __ldg(p.n_b + c * p.V + lane);
-              o[i] = fmaxf(y, 0.f);
-            }
-            if (p.out_f32) {
-              float *dst = p.out_f32 + row * CO + cb;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4 *>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-            }
-            if (p.out_hi) {
-              uint32_t hi[16], lo[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(o[2 * i], h0, l0);
-                split_bf16(o[2 * i + 1], h1, l1);
-                __nv_bfloat162 hh(h0, h1), ll(l0, l1);
-                hi[i] = *reinterpret_cast<uint32_t *>(&hh);
-                lo[i] = *reinterpret_cast<uint32_t *>(&ll);
-              }
-              uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + row * CO + cb);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              if (p.out_lo) {
-                uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + row * CO + cb);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  }
-}
-
 // adjacency CSR ordered by (k, w): ptr[k*V + w] .. ptr[k*V + w + 1] -> (v, A[k,v,w]); and the bias
-// that flows through A, transposed for coalesced epilogue reads: bzT[c][w].
+// that flows through A: bz[w][c] = sum_k bg[k*CO + c] * colsum_k[w].
 __global__ void k_build_adj_csr_kw(const float *__restrict__ A, int K, int V, int *__restrict__ ptr,
                                    int2 *__restrict__ va) {
   extern __shared__ int s_cnt[];  // K*V + 1
@@ -1059,7 +804,7 @@ __global__ void k_bias_through_adj(const float *__restrict__ A, const float *__r
                                    int CO, float *__restrict__ bzT) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= CO * V) return;
-  const int c = i / V, w = i - c * V;
+  const int w = i / CO, c = i - w * CO;            // output layout [V][CO]: contiguous in c
   float s = 0.f;
   for (int k = 0; k < K; ++k) {
     float col = 0.f;
@@ -1067,6 +812,15 @@ __global__ void k_bias_through_adj(const float *__restrict__ A, const float *__r
     s = fmaf(bg[k * CO + c], col, s);
   }
   bzT[i] = s;
+}
+
+// LayerNorm affine (C, 1, V) -> (V, C), so that an epilogue thread (one joint, 16 channels at a
+// time) reads it with 16-B loads
+__global__ void k_transpose_affine(const float *__restrict__ src, float *__restrict__ dst, int C, int V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * V) return;
+  const int w = i / C, c = i - w * C;
+  dst[i] = src[c * V + w];
 }
 
 // 1x1 weights (K*c_out, c_in) fp32 -> bf16 planes [2][K][c_out][c_in] (same order, split only)
@@ -1086,13 +840,13 @@ __global__ void k_split_bf16(const float *__restrict__ w, __nv_bfloat16 *__restr
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2..9 transform (contraction + bf16 split into the
 // swizzled A ring), 10..13 epilogue (TMEM double buffered for C <= 128).
 // --------------------------------------------------------------------------- //
-constexpr int kGcn2Threads = 480;   // + warp 14: weight-tile producer
+constexpr int kGcn2Threads = 32 * (10 + 4 * kEpiNH);   // 0 producers, 1 MMA, 2..9 transform, 10.. epilogue
 constexpr int kGcn2Csr = 2048;               // ptr[<=128] + 192 entries
 constexpr int kGcn2CsrMax = 192;
 
 struct GcnTc2Params {
   int T_out, V, K, Cin, planes;
-  int FT, NT, groups_per_trial, items;
+  int FT, NT, tb, groups_per_trial, items;
   int a_stage_bytes, a_ring, xs_alloc, xs_tx, xs_bufs, b_stages;
   int identity;
   const int *csr_ptr;
@@ -1100,13 +854,14 @@ struct GcnTc2Params {
   EpiParams epi;
 };
 
-template <int CO>
+template <int CO, bool kRt>
 __global__ void __launch_bounds__(kGcn2Threads, 1)
     k_gcn_tc2(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
               const GcnTc2Params p) {
   constexpr int kBBytes = CO * 128;
-  constexpr int TB = (4 * CO <= 512) ? 2 : 1;
-  constexpr int kTmemCols = TB * 2 * CO;
+  constexpr int kTmemCols = 512;
+  const int TB = p.tb;
+  const int buf_cols = p.NT * CO;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1116,7 +871,7 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
   const uint32_t sB = sXs + XB * p.xs_alloc;
   const uint32_t sCsr = sB + S * kBBytes;
   const uint32_t sPart = sCsr + kGcn2Csr;
-  const uint32_t sBar = sPart + 2048;
+  const uint32_t sBar = sPart + kPartBytes;
   const uint32_t bXsFull = sBar, bXsEmpty = sBar + 16, bTmemFull = sBar + 32, bTmemEmpty = sBar + 48;
   const uint32_t bAFull = sBar + 64, bAEmpty = sBar + 96;
   const uint32_t bFullB = sBar + 128, bEmptyB = bFullB + 8 * S;
@@ -1130,6 +885,8 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
   const int KC = p.Cin / 64;
   const int RT = p.FT * p.V;
   const int rows_item = p.NT * RT;
+  const bool dbg = (p.epi.debug & 4) && blockIdx.x == 0;
+  long long d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
@@ -1138,7 +895,7 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
       mbar_init(bXsFull + 8 * i, 1);
       mbar_init(bXsEmpty + 8 * i, 8);
       mbar_init(bTmemFull + 8 * i, 1);
-      mbar_init(bTmemEmpty + 8 * i, 4);
+      mbar_init(bTmemEmpty + 8 * i, 4 * kEpiNH);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bAFull + 8 * i, 8);
@@ -1166,175 +923,251 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
-    // ---- fp32 input-tile producer ----
+    // ---- producers: lane 0 streams the fp32 input tiles, lane 1 the weight tiles (two
+    // independent threads of one warp: each waits on its own ring) ----
     if (lane == 0) {
-      int x_it = 0;
+      int xb = 0, x_ph = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int n = item / p.groups_per_trial;
         const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;
-        for (int kc = 0; kc < KC; ++kc, ++x_it) {
-          const int xb = x_it % XB;
-          mbar_wait(bXsEmpty + 8 * xb, ((x_it / XB) & 1) ^ 1);
+        for (int kc = 0; kc < KC; ++kc) {
+          { DbgTimer tm(dbg); mbar_wait(bXsEmpty + 8 * xb, x_ph ^ 1); tm.stop(d0); }
           mbar_expect_tx(bXsFull + 8 * xb, (uint32_t)p.xs_tx);
           tma_load_4d(sXs + xb * p.xs_alloc, &tm_x, bXsFull + 8 * xb, kc * 64, 0, f0, n);
           tma_load_4d(sXs + xb * p.xs_alloc + p.xs_alloc / 2, &tm_x, bXsFull + 8 * xb, kc * 64 + 32, 0, f0, n);
+          if (++xb == XB) { xb = 0; x_ph ^= 1; }
         }
       }
-    }
-  } else if (warp == 14) {
-    // ---- weight-tile producer ----
-    if (lane == 0) {
-      int b_it = 0;
+      dbg_flush(dbg, 4, d0);
+    } else if (lane == 1) {
+      int bs = 0, b_ph = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x)
         for (int kc = 0; kc < KC; ++kc)
           for (int k = 0; k < p.K; ++k)
             for (int ap = 0; ap < p.planes; ++ap) {
               const int nb = (ap == 0) ? p.planes : 1;
-              for (int bp = 0; bp < nb; ++bp, ++b_it) {
-                const int bs = b_it % S;
-                mbar_wait(bEmptyB + 8 * bs, ((b_it / S) & 1) ^ 1);
+              for (int bp = 0; bp < nb; ++bp) {
+                { DbgTimer tm(dbg); mbar_wait(bEmptyB + 8 * bs, b_ph ^ 1); tm.stop(d0); }
                 mbar_expect_tx(bFullB + 8 * bs, kBBytes);
                 tma_load_4d(sB + bs * kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, k, bp);
+                if (++bs == S) { bs = 0; b_ph ^= 1; }
               }
             }
+      dbg_flush(dbg, 5, d0);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, CO);
-      int a_it = 0, b_it = 0, it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        const int buf = it % TB;
-        mbar_wait(bTmemEmpty + 8 * buf, ((it / TB) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * 2 * CO;
-        uint32_t acc = 0;
-        for (int kc = 0; kc < KC; ++kc)
-          for (int k = 0; k < p.K; ++k)
-            for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
-              const int as = a_it % AR;
-              mbar_wait(bAFull + 8 * as, (a_it / AR) & 1);
+    // ---- MMA issuer: the whole warp walks the schedule (uniform control flow, so descriptors and
+    // barrier addresses live in uniform registers); one elected lane issues MMAs and commits ----
+    constexpr uint32_t idesc = umma_idesc_bf16(128, CO);
+    int a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, buf = 0, t_ph = 0, it = 0;
+    DbgTimer tall(dbg);
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      { DbgTimer tm(dbg); mbar_wait(bTmemEmpty + 8 * buf, t_ph ^ 1); tm.stop(d0); }
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * buf_cols;
+      uint32_t acc = 0;
+      for (int kc = 0; kc < KC; ++kc)
+        for (int k = 0; k < p.K; ++k)
+          for (int ap = 0; ap < p.planes; ++ap) {
+            { DbgTimer tm(dbg); mbar_wait(bAFull + 8 * a_s, a_ph); tm.stop(d1); }
+            tc_fence_after();
+            const uint32_t a_lo0 = umma_desc_lo(sA + a_s * p.a_stage_bytes);
+            const int nb = (ap == 0) ? p.planes : 1;
+            for (int bp = 0; bp < nb; ++bp) {
+              { DbgTimer tm(dbg); mbar_wait(bFullB + 8 * b_s, b_ph); tm.stop(d2); }
               tc_fence_after();
-              const int nb = (ap == 0) ? p.planes : 1;
-              for (int bp = 0; bp < nb; ++bp, ++b_it) {
-                const int bs = b_it % S;
-                mbar_wait(bFullB + 8 * bs, (b_it / S) & 1);
-                tc_fence_after();
+              if (elect_one()) {
+                const uint32_t b_lo = umma_desc_lo(sB + b_s * kBBytes);
                 for (int m = 0; m < p.NT; ++m) {
-                  const uint32_t a0 = sA + as * p.a_stage_bytes + m * RT * 128;
+                  const uint32_t a_lo = a_lo0 + (uint32_t)(m * RT * 8);      // rows * 128 B >> 4
 #pragma unroll
                   for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tacc + m * CO, umma_desc_sw128(a0 + kk * 32),
-                              umma_desc_sw128(sB + bs * kBBytes + kk * 32), idesc, acc | (uint32_t)kk);
+                    umma_bf16(tacc + m * CO, umma_desc_join(a_lo + 2 * kk), umma_desc_join(b_lo + 2 * kk), idesc,
+                              acc | (uint32_t)kk);
                 }
-                acc = 1;
-                umma_commit(bEmptyB + 8 * bs);
+                umma_commit(bEmptyB + 8 * b_s);
               }
-              umma_commit(bAEmpty + 8 * as);
+              __syncwarp();
+              acc = 1;
+              if (++b_s == S) { b_s = 0; b_ph ^= 1; }
             }
-        umma_commit(bTmemFull + 8 * buf);
-      }
+            if (elect_one()) umma_commit(bAEmpty + 8 * a_s);
+            __syncwarp();
+            if (++a_s == AR) { a_s = 0; a_ph ^= 1; }
+          }
+      if (elect_one()) umma_commit(bTmemFull + 8 * buf);
+      __syncwarp();
+      if (++buf == TB) { buf = 0; t_ph ^= 1; }
+    }
+    tall.stop(d3);
+    if (lane == 0) {
+      dbg_flush(dbg, 0, d0); dbg_flush(dbg, 1, d1); dbg_flush(dbg, 2, d2); dbg_flush(dbg, 3, d3);
+      dbg_flush(dbg, 11, it);
     }
   } else if (warp < 10) {
-    // ---- transform warps: ONE THREAD PER ROW (256 threads >= rows of an item) ----
-    // The fp32 input tile is staged as two 32-channel sub-tiles with the 128-B TMA swizzle, so
-    // threads of a warp (consecutive rows) read 16-B chunks from distinct banks.  Each thread
-    // walks its row in groups of 4 channels: gather-sum over the CSR entries of (k, joint),
-    // split into bf16 hi/lo, store hi as 8 B into the swizzled UMMA A stage and keep lo packed
-    // in registers for the following lo-plane stage.
-    const int r = (warp - 2) * 32 + lane;
+    // ---- transform warps: the adjacency contraction on the staged fp32 tile, then the bf16
+    // hi/lo split into the swizzled UMMA A ring ----
+    // NT == 2: one thread per row (256 threads >= rows of an item); NT == 1: two threads per
+    // row, one 32-channel sub-tile each.  The fp32 input tile is staged as two 32-channel
+    // sub-tiles with the 128-B TMA swizzle, so threads of a warp (consecutive rows) read 16-B
+    // chunks from distinct banks.  Per (k, sub-tile) a thread accumulates its row's 8 float4
+    // groups over the CSR entries of (k, joint) -- entries outer, groups inner, so an entry's
+    // address arithmetic is done once -- splits them into bf16 hi/lo, stores hi as 16-B chunks
+    // into the A stage and keeps lo packed in registers for the following lo-plane stage.
+    const int tid = (warp - 2) * 32 + lane;
+    const bool split = rows_item <= 128;
+    const int r = split ? (tid & 127) : tid;
+    const int my_sub = tid >> 7;                        // used when split
     const bool r_ok = r < rows_item;
     const int f = r / p.V, w = r - f * p.V;
     const int src_base = f * p.V;                       // first source row of this row's frame
-    int a_it = 0, x_it = 0;
-    uint2 lo_stash[16];
+    const int sw = (r & 7) << 4;
+    int as = 0, a_ph = 0, xb = 0, x_ph = 0;
+    uint4 lo_stash[8];
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      for (int kc = 0; kc < KC; ++kc, ++x_it) {
-        const int xb = x_it % XB;
-        mbar_wait(bXsFull + 8 * xb, (x_it / XB) & 1);
+      if (kRt && r_ok && (!split || my_sub == 0)) {
+        // RT step: start pulling this row's FIFO slot and accumulator into L2 now; the epilogue
+        // reaches them only after the MMAs of this item, and would otherwise wait on HBM latency.
+        const int n_ = item / p.groups_per_trial;
+        const int b = (item - n_ * p.groups_per_trial) * p.NT * p.FT + f;
+        if (b < p.T_out) {
+          const int cnt = __ldg(p.epi.rt_counter + b);
+          const long long ro = ((long long)b * p.V + w) * CO;
+          const char *fp = reinterpret_cast<const char *>(p.epi.rt_fifo + (long long)(cnt % p.epi.rt_F) * p.epi.rt_slot + ro);
+          const char *ap = reinterpret_cast<const char *>(p.epi.rt_acc + (long long)(cnt % p.epi.rt_S) * p.epi.rt_slot + ro);
+#pragma unroll
+          for (int o = 0; o < CO * 4; o += 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + o));
+          }
+        }
+      }
+      for (int kc = 0; kc < KC; ++kc) {
+        { DbgTimer tm(dbg); mbar_wait(bXsFull + 8 * xb, x_ph); tm.stop(d0); }
         const uint8_t *xs = gen_base + (sXs - smem_base) + xb * p.xs_alloc;
         const int half = p.xs_alloc / 2;
-        for (int k = 0; k < p.K; ++k)
-          for (int ap = 0; ap < p.planes; ++ap, ++a_it) {
-            const int as = a_it % AR;
-            int e0 = 0, e1 = 0;
-            if (ap == 0 && r_ok && !p.identity) {
-              e0 = csr_smem ? s_ptr[k * p.V + w] : __ldg(p.csr_ptr + k * p.V + w);
-              e1 = csr_smem ? s_ptr[k * p.V + w + 1] : __ldg(p.csr_ptr + k * p.V + w + 1);
-            }
-            mbar_wait(bAEmpty + 8 * as, ((a_it / AR) & 1) ^ 1);
+        for (int k = 0; k < p.K; ++k) {
+          int e0 = 0, e1 = 0;
+          if (r_ok && !p.identity) {
+            e0 = csr_smem ? s_ptr[k * p.V + w] : __ldg(p.csr_ptr + k * p.V + w);
+            e1 = csr_smem ? s_ptr[k * p.V + w + 1] : __ldg(p.csr_ptr + k * p.V + w + 1);
+          }
+          {
+            { DbgTimer tm(dbg); mbar_wait(bAEmpty + 8 * as, a_ph ^ 1); tm.stop(d1); }
+            DbgTimer tcomp(dbg);
             uint8_t *dst_row = gen_base + as * p.a_stage_bytes + r * 128;
             if (r_ok && !(p.epi.debug & 2)) {
-              if (ap == 0) {
 #pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                  const int sub = g >> 3, j = g & 7;           // 32-channel sub-tile, 16-B chunk
-                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (p.identity) {
-                    acc = *reinterpret_cast<const float4 *>(xs + sub * half + r * 128 + ((j ^ (r & 7)) << 4));
-                  } else {
-                    for (int e = e0; e < e1; ++e) {
-                      const int2 va = csr_smem ? s_va[e] : __ldg(p.csr_va + e);
-                      const float a = __int_as_float(va.y);
-                      const int rs = src_base + va.x;
-                      const float4 xv =
-                          *reinterpret_cast<const float4 *>(xs + sub * half + rs * 128 + ((j ^ (rs & 7)) << 4));
-                      acc.x = fmaf(a, xv.x, acc.x);
-                      acc.y = fmaf(a, xv.y, acc.y);
-                      acc.z = fmaf(a, xv.z, acc.z);
-                      acc.w = fmaf(a, xv.w, acc.w);
+              for (int sub = 0; sub < 2; ++sub) {
+                if (split && sub != my_sub) continue;
+                float4 acc[8];
+                if (p.identity) {
+                  const uint8_t *b0 = xs + sub * half + r * 128;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[j] = *reinterpret_cast<const float4 *>(b0 + ((j << 4) ^ sw));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int e = e0; e < e1; ++e) {
+                    const int2 va = csr_smem ? s_va[e] : __ldg(p.csr_va + e);
+                    const float a = __int_as_float(va.y);
+                    const int rs = src_base + va.x;
+                    const uint8_t *b0 = xs + sub * half + rs * 128;
+                    const int ssw = (rs & 7) << 4;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float4 xv = *reinterpret_cast<const float4 *>(b0 + ((j << 4) ^ ssw));
+                      acc[j].x = fmaf(a, xv.x, acc[j].x);
+                      acc[j].y = fmaf(a, xv.y, acc[j].y);
+                      acc[j].z = fmaf(a, xv.z, acc[j].z);
+                      acc[j].w = fmaf(a, xv.w, acc[j].w);
                     }
                   }
-                  const __nv_bfloat162 h01 = __floats2bfloat162_rn(acc.x, acc.y);
-                  const __nv_bfloat162 h23 = __floats2bfloat162_rn(acc.z, acc.w);
-                  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-                  const __nv_bfloat162 l01 = __floats2bfloat162_rn(acc.x - f01.x, acc.y - f01.y);
-                  const __nv_bfloat162 l23 = __floats2bfloat162_rn(acc.z - f23.x, acc.w - f23.y);
-                  lo_stash[g] = make_uint2(*reinterpret_cast<const uint32_t *>(&l01),
-                                           *reinterpret_cast<const uint32_t *>(&l23));
-                  *reinterpret_cast<uint2 *>(dst_row + ((((sub << 2) | (j >> 1)) ^ (r & 7)) << 4) + ((j & 1) << 3)) =
-                      make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
                 }
-              } else {
 #pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                  const int sub = g >> 3, j = g & 7;
-                  *reinterpret_cast<uint2 *>(dst_row + ((((sub << 2) | (j >> 1)) ^ (r & 7)) << 4) + ((j & 1) << 3)) =
-                      lo_stash[g];
+                for (int jj = 0; jj < 4; ++jj) {
+                  uint32_t hi[4], lo[4];
+#pragma unroll
+                  for (int u = 0; u < 2; ++u) {
+                    const float4 q = acc[2 * jj + u];
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(q.x, q.y);
+                    const __nv_bfloat162 h23 = __floats2bfloat162_rn(q.z, q.w);
+                    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(q.x - f01.x, q.y - f01.y);
+                    const __nv_bfloat162 l23 = __floats2bfloat162_rn(q.z - f23.x, q.w - f23.y);
+                    hi[2 * u] = *reinterpret_cast<const uint32_t *>(&h01);
+                    hi[2 * u + 1] = *reinterpret_cast<const uint32_t *>(&h23);
+                    lo[2 * u] = *reinterpret_cast<const uint32_t *>(&l01);
+                    lo[2 * u + 1] = *reinterpret_cast<const uint32_t *>(&l23);
+                  }
+                  // channels sub*32 + jj*8 .. +8 = 16-B chunk (sub*4 + jj) of the 128-B row
+                  *reinterpret_cast<uint4 *>(dst_row + ((((sub << 2) | jj) << 4) ^ sw)) =
+                      make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  lo_stash[sub * 4 + jj] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
               }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bAFull + 8 * as);
+            if (++as == AR) { as = 0; a_ph ^= 1; }
+            tcomp.stop(d2);
           }
+          if (p.planes == 2) {
+            mbar_wait(bAEmpty + 8 * as, a_ph ^ 1);
+            uint8_t *dst_row = gen_base + as * p.a_stage_bytes + r * 128;
+            if (r_ok && !(p.epi.debug & 2)) {
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub) {
+                if (split && sub != my_sub) continue;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                  *reinterpret_cast<uint4 *>(dst_row + ((((sub << 2) | jj) << 4) ^ sw)) = lo_stash[sub * 4 + jj];
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bAFull + 8 * as);
+            if (++as == AR) { as = 0; a_ph ^= 1; }
+          }
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(bXsEmpty + 8 * xb);
+        if (++xb == XB) { xb = 0; x_ph ^= 1; }
       }
     }
-  } else if (warp < 14) {
-    // ---- epilogue warps 10..13 ----
+    if (warp == 2 && lane == 0) { dbg_flush(dbg, 8, d0); dbg_flush(dbg, 9, d1); dbg_flush(dbg, 10, d2); }
+  } else {
+    // ---- epilogue warps 10.. (kEpiNH per TMEM lane quarter, splitting the channel range) ----
     const int q = warp & 3;
+    const int h = (warp - 10) >> 2;
     const int r = q * 32 + lane;
     const int fr = r / p.V, w = r - fr * p.V;
-    int it = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const int buf = it % TB;
+    int buf = 0, t_ph = 0, par = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int n = item / p.groups_per_trial;
       const int f0 = (item - n * p.groups_per_trial) * p.NT * p.FT;
-      mbar_wait(bTmemFull + 8 * buf, (it / TB) & 1);
+      { DbgTimer tm(dbg); mbar_wait(bTmemFull + 8 * buf, t_ph); tm.stop(d0); }
       tc_fence_after();
+      DbgTimer tw(dbg);
 #pragma unroll 1
-      for (int m = 0; m < p.NT; ++m) {
+      for (int m = 0; m < p.NT; ++m, par ^= 1) {
         const int t = f0 + m * p.FT + fr;
         const bool row_ok = (r < RT) && (t < p.T_out);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * CO + m * CO);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * CO);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<CO>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, s_part, m & 1);
+        if (kRt)
+          rt_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, t, s_part, par, h);
+        else
+          ln_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, s_part, par, h);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bTmemEmpty + 8 * buf);
+      if (++buf == TB) { buf = 0; t_ph ^= 1; }
+      tw.stop(d1);
     }
+    if (warp == 10 && lane == 0) { dbg_flush(dbg, 6, d0); dbg_flush(dbg, 7, d1); }
   }
   tc_fence_before();
   __syncthreads();
@@ -1411,62 +1244,6 @@ inline bool gcn_tc_supported(int c_in, int c_out, int V, int K) {
          V >= 2 && K >= 1 && K * V + 1 <= 256;
 }
 
-// x: fp32 [N][T][V][c_in]; wp: bf16 [2][K][c_out][c_in]
-template <int CO>
-int launch_gcn_tc_c(const float *x, const __nv_bfloat16 *wp, const GcnTcParams &p, int N, cudaStream_t st) {
-  CUtensorMap tm_x, tm_w;
-  const uint64_t xd[4] = {(uint64_t)p.Cin, (uint64_t)p.V, (uint64_t)p.T, (uint64_t)N};
-  const uint64_t xst[3] = {(uint64_t)p.Cin * 4, (uint64_t)p.V * p.Cin * 4, (uint64_t)p.T * p.V * p.Cin * 4};
-  const uint32_t xb[4] = {64, (uint32_t)p.V, kOutFrames, 1};
-  if (make_tmap_f32_noswizzle(&tm_x, x, 4, xd, xst, xb)) return 1;
-  const uint64_t wd[4] = {(uint64_t)p.Cin, (uint64_t)CO, (uint64_t)p.K, 2};
-  const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)p.K * CO * p.Cin * 2};
-  const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
-  if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
-  GcnTcParams q = p;
-  q.xs_alloc = GcnCfg<CO>::xs_bytes(p.V);
-  const int smem = GcnCfg<CO>::smem(p.V);
-  if (smem > 232448) return fail("gcn tensor-core kernel: %d joints need %d B of shared memory", p.V, smem);
-  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn_tc<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid((p.T + kOutFrames - 1) / kOutFrames, N);
-  k_gcn_tc<CO><<<grid, kGcnThreads, smem, st>>>(tm_x, tm_w, q);
-  return 0;
-}
-
-inline int launch_gcn_tc(int CO, const float *x, const __nv_bfloat16 *wp, const GcnTcParams &p, int N,
-                         cudaStream_t st) {
-  switch (CO) {
-    case 64: return launch_gcn_tc_c<64>(x, wp, p, N, st);
-    case 128: return launch_gcn_tc_c<128>(x, wp, p, N, st);
-    case 256: return launch_gcn_tc_c<256>(x, wp, p, N, st);
-  }
-  return fail("gcn tensor-core kernel: unsupported channel count %d", CO);
-}
-
-inline bool tcn_tc_supported(int C, int V, int G, int stride) {
-  return (C == 64 || C == 128 || C == 256) && V <= kFrameRows && G <= 9 && (G & 1) && stride == 1;
-}
-
-// u planes: bf16 [planes][N][T][V][C]; wp: bf16 [2][G][C][C]
-template <int C>
-int launch_tcn_tc_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTcParams &p, int N,
-                    cudaStream_t st) {
-  CUtensorMap tm_u, tm_w;
-  const uint64_t ud[5] = {(uint64_t)C, (uint64_t)p.V, (uint64_t)p.T, (uint64_t)N, (uint64_t)p.planes};
-  const uint64_t us[4] = {(uint64_t)C * 2, (uint64_t)p.V * C * 2, (uint64_t)p.T * p.V * C * 2,
-                          (uint64_t)N * p.T * p.V * C * 2};
-  const uint32_t ub[5] = {64, kFrameRows, kInFrames, 1, 1};
-  if (make_tmap_bf16(&tm_u, u, 5, ud, us, ub)) return 1;
-  const uint64_t wd[4] = {(uint64_t)C, (uint64_t)C, (uint64_t)p.G, 2};
-  const uint64_t wst[3] = {(uint64_t)C * 2, (uint64_t)C * C * 2, (uint64_t)p.G * C * C * 2};
-  const uint32_t wb[4] = {64, (uint32_t)C, 1, 1};
-  if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
-  STGCN_CUDA_OK(cudaFuncSetAttribute(k_tcn_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcnCfg<C>::kSmem));
-  dim3 grid((p.T + kOutFrames - 1) / kOutFrames, N);
-  k_tcn_tc<C><<<grid, kTcnThreads, TcnCfg<C>::kSmem, st>>>(tm_u, tm_w, p);
-  return 0;
-}
-
 inline int num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -1485,13 +1262,14 @@ int launch_gcn_tc2_c(const float *x, const __nv_bfloat16 *wp, GcnTc2Params p, in
                      cudaStream_t st) {
   const int V = p.V, kMaxSmem = 232448;
   p.FT = 128 / V;
-  p.NT = 2;
+  p.NT = CO >= 256 ? 1 : 2;                          // tiles per item; NT * CO * tb <= 512 TMEM columns
+  p.tb = 512 / (p.NT * CO) >= 2 ? 2 : 1;
   if (p.FT < 1) return fail("gcn tensor-core kernel: %d joints do not fit a 128-row tile", V);
   const int RT = p.FT * V;
   p.a_stage_bytes = ((p.NT * RT + 128 - RT) * 128 + 1023) & ~1023;
   p.xs_tx = p.NT * p.FT * V * 64 * 4;
   p.xs_alloc = 2 * ((p.NT * p.FT * V * 128 + 1023) & ~1023);   // two 32-channel swizzled sub-tiles
-  const int fixed = kGcn2Csr + 2048 + 512 + 1024;
+  const int fixed = kGcn2Csr + kPartBytes + 512 + 1024;
   // prefer: double-buffered input tile, 3-deep A ring, >= 2 weight stages; back off as smem requires
   const int tries[4][2] = {{2, 3}, {2, 2}, {1, 3}, {1, 2}};
   int ok = 0;
@@ -1517,9 +1295,14 @@ int launch_gcn_tc2_c(const float *x, const __nv_bfloat16 *wp, GcnTc2Params p, in
   const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)p.K * CO * p.Cin * 2};
   const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
   if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
-  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn_tc2<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  k_gcn_tc2<CO><<<grid, kGcn2Threads, smem, st>>>(tm_x, tm_w, p);
+  if (p.epi.rt_fifo) {
+    STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn_tc2<CO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_gcn_tc2<CO, true><<<grid, kGcn2Threads, smem, st>>>(tm_x, tm_w, p);
+  } else {
+    STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn_tc2<CO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_gcn_tc2<CO, false><<<grid, kGcn2Threads, smem, st>>>(tm_x, tm_w, p);
+  }
   return 0;
 }
 
@@ -1551,7 +1334,8 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
   for (;; --FT) {
     if (FT < 1) return fail("tcn tensor-core kernel: %d joints do not fit a 128-row tile", V);
     p.FT = FT;
-    p.NT = 2;
+    p.NT = C >= 256 ? 1 : 2;
+    p.tb = 512 / (p.NT * C) >= 2 ? 2 : 1;
     const int out_f = p.NT * FT, spill = 128 - FT * V;
     if (stride == 1) {
       const int wf = out_f + 2 * pad;
@@ -1585,14 +1369,14 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
       a_rows = (nf[0] + nf[1]) * V + spill;
     }
     p.a_stage_bytes = (a_rows * 128 + 1023) & ~1023;
-    const int left = kMaxSmem - 2 * p.a_stage_bytes - 2048 - 512 - 1024;
+    const int left = kMaxSmem - 2 * p.a_stage_bytes - kPartBytes - 512 - 1024;
     p.b_stages = left / (C * 128);
     if (p.b_stages > 8) p.b_stages = 8;
     if (p.b_stages >= 2) break;
   }
   p.groups_per_trial = (p.T_out + p.NT * p.FT - 1) / (p.NT * p.FT);
   p.items = N * p.groups_per_trial;
-  const int smem = 2 * p.a_stage_bytes + p.b_stages * C * 128 + 2048 + 512 + 1024;
+  const int smem = 2 * p.a_stage_bytes + p.b_stages * C * 128 + kPartBytes + 512 + 1024;
 
   CUtensorMap tm_u0, tm_u1, tm_w;
   const uint64_t plane_stride = (uint64_t)N * T * V * C * 2;
@@ -1627,16 +1411,6 @@ inline int launch_tcn_tc2(int C, const __nv_bfloat16 *u, const __nv_bfloat16 *wp
     case 64: return launch_tcn_tc2_c<64>(u, wp, p, N, T, stride, st);
     case 128: return launch_tcn_tc2_c<128>(u, wp, p, N, T, stride, st);
     case 256: return launch_tcn_tc2_c<256>(u, wp, p, N, T, stride, st);
-  }
-  return fail("tcn tensor-core kernel: unsupported channel count %d", C);
-}
-
-inline int launch_tcn_tc(int C, const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTcParams &p, int N,
-                         cudaStream_t st) {
-  switch (C) {
-    case 64: return launch_tcn_tc_c<64>(u, wp, p, N, st);
-    case 128: return launch_tcn_tc_c<128>(u, wp, p, N, st);
-    case 256: return launch_tcn_tc_c<256>(u, wp, p, N, st);
   }
   return fail("tcn tensor-core kernel: unsupported channel count %d", C);
 }

@@ -24,6 +24,23 @@ inline int debug_mode() {
   return m;
 }
 
+// STGCN_DEBUG & 4: after a tensor-core launch, synchronise and print CTA 0's role/wait cycle counters
+int debug_dump(const char *what, int c, cudaStream_t st) {
+  if (!(debug_mode() & 4)) return 0;
+  unsigned long long h[16];
+  STGCN_CUDA_OK(cudaStreamSynchronize(st));
+  STGCN_CUDA_OK(cudaMemcpyFromSymbol(h, tc::g_dbg, sizeof(h)));
+  static const char *names[12] = {"mma_wait_tmem", "mma_wait_A", "mma_wait_B", "mma_total", "xA_prod_wait",
+                                  "B_prod_wait", "epi_wait_tmem", "epi_work", "xf_wait_x", "xf_wait_Aempty",
+                                  "xf_compute", "items"};
+  fprintf(stderr, "[dbg] %s<%d>:", what, c);
+  for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
+  fprintf(stderr, "\n");
+  memset(h, 0, sizeof(h));
+  STGCN_CUDA_OK(cudaMemcpyToSymbol(tc::g_dbg, h, sizeof(h)));
+  return 0;
+}
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int round4(int x) { return (x + 3) & ~3; }
 
@@ -126,60 +143,126 @@ int check_layer(const stgcn_layer_desc &d) {
   return 0;
 }
 
+// ---- per-layer prepared operands of the tensor-core kernels ----------------------
+// bf16 hi/lo weight planes, the (k,w)-ordered adjacency CSR and the bias that flows through the
+// adjacency.  They depend only on the parameters, so a model prepares them once
+// (stgcn_model_prepare) and every forward reuses them; the layer-level entry points build them
+// per call in the workspace.
+struct LayerPrep {
+  bool gcn = false, tcn = false, res = false;
+  int *kw_ptr = nullptr;
+  int2 *kw_va = nullptr;
+  float *bzT = nullptr;
+  __nv_bfloat16 *wg16 = nullptr, *wp16 = nullptr, *wr16 = nullptr;
+  float *zero = nullptr;  // c_out zeros: bias of the bias-free RT residual conv (rtstgcn.py:503)
+  float *n1T = nullptr, *n2T = nullptr, *nrT = nullptr;  // LayerNorm affine (V, C): weight then bias
+};
+
+LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws) {
+  LayerPrep P;
+  const bool ln = d.norm == STGCN_NORM_LAYERNORM;
+  P.gcn = ln && !d.a_per_sample && tc::gcn_tc_supported(d.c_in, d.c_out, V, K);
+  P.tcn = ln && !d.rt && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, 2);
+  P.res = ln && d.residual == STGCN_RES_CONV && tc::gcn_tc_supported(d.c_in, d.c_out, V, 1);
+  if (P.gcn) {
+    P.kw_ptr = ws.take<int>((size_t)K * V + 1);
+    P.kw_va = ws.take<int2>((size_t)K * V * V);
+    P.bzT = ws.take<float>((size_t)d.c_out * V);
+    P.wg16 = ws.take<__nv_bfloat16>((size_t)2 * K * d.c_out * d.c_in);
+  }
+  if (P.tcn) P.wp16 = ws.take<__nv_bfloat16>((size_t)2 * d.c_out * d.c_out * d.kernel);
+  if (P.res) {
+    P.wr16 = ws.take<__nv_bfloat16>((size_t)2 * d.c_out * d.c_in);
+    P.zero = ws.take<float>((size_t)d.c_out);
+    P.nrT = ws.take<float>((size_t)2 * d.c_out * V);
+  }
+  if (P.gcn) P.n1T = ws.take<float>((size_t)2 * d.c_out * V);
+  if (P.tcn) P.n2T = ws.take<float>((size_t)2 * d.c_out * V);
+  return P;
+}
+
+int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaStream_t st) {
+  ProfScope ps(KC_MISC, st);
+  if (P.gcn) {
+    const long long nw = (long long)K * d.c_out * d.c_in;
+    tc::k_build_adj_csr_kw<<<1, 128, (K * V + 1) * sizeof(int), st>>>(d.a_eff, K, V, P.kw_ptr, P.kw_va);
+    STGCN_LAUNCH_OK();
+    tc::k_bias_through_adj<<<cdiv((long long)d.c_out * V, 256), 256, 0, st>>>(d.a_eff, d.gcn_b, K, V, d.c_out,
+                                                                              P.bzT);
+    STGCN_LAUNCH_OK();
+    tc::k_split_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.gcn_w, P.wg16, nw);
+    STGCN_LAUNCH_OK();
+  }
+  if (P.tcn) {
+    const long long nw = (long long)d.c_out * d.c_out * d.kernel;
+    tc::k_pack_tcn_w_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.tcn_w, P.wp16, d.c_out, d.c_out, d.kernel);
+    STGCN_LAUNCH_OK();
+  }
+  if (P.res) {
+    const long long nwr = (long long)d.c_out * d.c_in;
+    tc::k_split_bf16<<<cdiv(nwr, 256), 256, 0, st>>>(d.res_w, P.wr16, nwr);
+    STGCN_LAUNCH_OK();
+    STGCN_CUDA_OK(cudaMemsetAsync(P.zero, 0, sizeof(float) * d.c_out, st));
+  }
+  const int cv = d.c_out * V;
+  const float *src[3][2] = {{d.n1_w, d.n1_b}, {d.n2_w, d.n2_b}, {d.nr_w, d.nr_b}};
+  float *dst[3] = {P.n1T, P.n2T, P.nrT};
+  for (int i = 0; i < 3; ++i)
+    if (dst[i])
+      for (int j = 0; j < 2; ++j) {
+        tc::k_transpose_affine<<<cdiv(cv, 256), 256, 0, st>>>(src[i][j], dst[i] + (size_t)j * cv, d.c_out, V);
+        STGCN_LAUNCH_OK();
+      }
+  return 0;
+}
+
 // ---- ST-GCN layer on channels-last activations --------------------------------
 // x [N*T*V, c_in] -> out [N*T_out*V, c_out].  Scratch comes from `ws` (released on return).
+// `pp`: prepared operands (model path) or null (built here, per call).
 int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
-                       int N, int T, Bump &ws, cudaStream_t st) {
+                       int N, int T, Bump &ws, cudaStream_t st, const LayerPrep *pp = nullptr) {
   if (check_layer(d)) return 1;
   const size_t mark = ws.mark();
   const int T_out = (T - 1) / d.stride + 1;
   const long long rows = (long long)N * T * V, rows_out = (long long)N * T_out * V;
   const bool bn = d.norm == STGCN_NORM_BATCHNORM;
-  // tensor-core temporal stage: LayerNorm, stride 1, identity/no residual, C in {64,128,256}
-  const bool tc_tcn = math != STGCN_MATH_FP32 && !bn && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, T);
+  LayerPrep local;
+  if (!pp && math != STGCN_MATH_FP32) {
+    local = prep_take(d, K, V, ws);
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer operands)");
+      if (prep_run(d, K, V, local, st)) return 1;
+    }
+    pp = &local;
+  }
+  // tensor-core temporal stage: LayerNorm, stride 1/2, C in {64,128,256}
+  const bool tc_tcn = math != STGCN_MATH_FP32 && pp && pp->tcn &&
+                      tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, T);
   const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
-
   // tensor-core graph-convolution stage: LayerNorm, shared adjacency, C_in % 64 == 0
-  const bool tc_gcn = math != STGCN_MATH_FP32 && !bn && !d.a_per_sample &&
-                      tc::gcn_tc_supported(d.c_in, d.c_out, V, K);
+  const bool tc_gcn = math != STGCN_MATH_FP32 && pp && pp->gcn;
 
   float *u = tc_tcn ? nullptr : ws.take<float>((size_t)rows * d.c_out);
   __nv_bfloat16 *u16 = tc_tcn ? ws.take<__nv_bfloat16>((size_t)planes * rows * d.c_out) : nullptr;
   __nv_bfloat16 *u16_lo = (tc_tcn && planes == 2 && u16) ? u16 + (size_t)rows * d.c_out : nullptr;
   double *sums = bn ? ws.take<double>((size_t)4 * d.c_out) : nullptr;
   if (tc_gcn) {
-    const size_t m2 = ws.mark();
-    const long long nw = (long long)K * d.c_out * d.c_in;
-    int *kw_ptr = ws.take<int>((size_t)K * V + 1);
-    int2 *kw_va = ws.take<int2>((size_t)K * V * V);
-    float *bzT = ws.take<float>((size_t)d.c_out * V);
-    __nv_bfloat16 *wg16 = ws.take<__nv_bfloat16>((size_t)2 * nw);
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
-      {
-        ProfScope ps(KC_MISC, st);
-        tc::k_build_adj_csr_kw<<<1, 128, (K * V + 1) * sizeof(int), st>>>(d.a_eff, K, V, kw_ptr, kw_va);
-        STGCN_LAUNCH_OK();
-        tc::k_bias_through_adj<<<cdiv((long long)d.c_out * V, 256), 256, 0, st>>>(d.a_eff, d.gcn_b, K, V,
-                                                                                  d.c_out, bzT);
-        STGCN_LAUNCH_OK();
-        tc::k_split_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.gcn_w, wg16, nw);
-        STGCN_LAUNCH_OK();
-      }
       tc::GcnTc2Params g{};
       g.T_out = T; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
-      g.csr_ptr = kw_ptr; g.csr_va = kw_va;
-      g.epi.bias = bzT; g.epi.bias_sc = V; g.epi.bias_sw = 1;
-      g.epi.n_w = d.n1_w; g.epi.n_b = d.n1_b;
+      g.csr_ptr = pp->kw_ptr; g.csr_va = pp->kw_va;
+      g.epi.bias = pp->bzT; g.epi.bias_sw = d.c_out;
+      g.epi.n_wT = pp->n1T; g.epi.n_bT = pp->n1T + (size_t)d.c_out * V;
       g.epi.out_hi = u16; g.epi.out_lo = u16_lo; g.epi.out_f32 = u;
       g.epi.relu = 1;
       g.epi.eps = kEps;
       g.epi.debug = debug_mode();
       ProfScope ps(KC_GEMM_1X1, st);
-      if (tc::launch_gcn_tc2(d.c_out, x, wg16, g, N, T, 1, st)) return 1;
+      if (tc::launch_gcn_tc2(d.c_out, x, pp->wg16, g, N, T, 1, st)) return 1;
       STGCN_LAUNCH_OK();
+      if (debug_dump("gcn", d.c_out, st)) return 1;
     }
-    ws.release(m2);
   } else {
     AdjCsr csr;
     if (build_csr(d.a_eff, d.a_per_sample, N, K, V, d.c_out, ws, csr, st)) return 1;
@@ -219,39 +302,25 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     ws.release(m2);
   }
   if (tc_tcn) {
-    const long long nw = (long long)d.c_out * d.c_out * d.kernel;
-    __nv_bfloat16 *wp16 = ws.take<__nv_bfloat16>((size_t)2 * nw);
     // channel-changing / strided residual: LN_R(conv1x1_stride(x)) precomputed into `resb`
     const bool res_conv = d.residual == STGCN_RES_CONV;
-    const bool res_tc = res_conv && tc::gcn_tc_supported(d.c_in, d.c_out, V, 1);
-    const long long nwr = (long long)d.c_out * d.c_in;
+    const bool res_tc = res_conv && pp->res;
     float *resb = res_conv ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
     float *qr = (res_conv && !res_tc) ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
-    __nv_bfloat16 *wr16 = res_tc ? ws.take<__nv_bfloat16>((size_t)2 * nwr) : nullptr;
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
-      {
-        ProfScope ps(KC_MISC, st);
-        tc::k_pack_tcn_w_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.tcn_w, wp16, d.c_out, d.c_out, d.kernel);
-        STGCN_LAUNCH_OK();
-      }
       if (res_tc) {
-        {
-          ProfScope ps(KC_MISC, st);
-          tc::k_split_bf16<<<cdiv(nwr, 256), 256, 0, st>>>(d.res_w, wr16, nwr);
-          STGCN_LAUNCH_OK();
-        }
         tc::GcnTc2Params g{};
         g.T_out = T_out; g.V = V; g.K = 1; g.Cin = d.c_in; g.planes = planes;
         g.identity = 1;
-        g.epi.bias = d.res_b; g.epi.bias_sc = 1; g.epi.bias_sw = 0;
-        g.epi.n_w = d.nr_w; g.epi.n_b = d.nr_b;
+        g.epi.bias = d.res_b; g.epi.bias_sw = 0;
+        g.epi.n_wT = pp->nrT; g.epi.n_bT = pp->nrT + (size_t)d.c_out * V;
         g.epi.out_f32 = resb;
         g.epi.relu = 0;
         g.epi.eps = kEps;
         g.epi.debug = debug_mode();
         ProfScope ps(KC_GEMM_1X1, st);
-        if (tc::launch_gcn_tc2(d.c_out, x, wr16, g, N, T, d.stride, st)) return 1;
+        if (tc::launch_gcn_tc2(d.c_out, x, pp->wr16, g, N, T, d.stride, st)) return 1;
         STGCN_LAUNCH_OK();
       } else if (res_conv) {
         if (launch_gemm(x, d.res_w, d.res_b, qr, N, T, V, d.c_in, d.c_out, 1, d.stride, st)) return 1;
@@ -269,16 +338,17 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       tc::TcnTc2Params p{};
       p.T_out = T_out; p.V = V; p.G = d.kernel;
       p.planes = planes;
-      p.epi.bias = d.tcn_b; p.epi.bias_sc = 1; p.epi.bias_sw = 0;
-      p.epi.n_w = d.n2_w; p.epi.n_b = d.n2_b;
+      p.epi.bias = d.tcn_b; p.epi.bias_sw = 0;
+      p.epi.n_wT = pp->n2T; p.epi.n_bT = pp->n2T + (size_t)d.c_out * V;
       p.epi.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
       p.epi.out_f32 = out;
       p.epi.relu = 1;
       p.epi.eps = kEps;
       p.epi.debug = debug_mode();
       ProfScope ps(KC_GEMM_TCN, st);
-      if (tc::launch_tcn_tc2(d.c_out, u16, wp16, p, N, T, d.stride, st)) return 1;
+      if (tc::launch_tcn_tc2(d.c_out, u16, pp->wp16, p, N, T, d.stride, st)) return 1;
       STGCN_LAUNCH_OK();
+      if (debug_dump("tcn", d.c_out, st)) return 1;
     }
     ws.release(mark);
     return 0;
@@ -334,12 +404,64 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
 // ---- RT online layer on channels-last frames -----------------------------------
 // x [B*V, c_in] -> out [B*V, c_out]; fifo [F][B][V][C], acc [S][B][V][C]; counter[B].
 int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
-                       float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st) {
-  (void)math;
+                       float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st,
+                       const LayerPrep *pp = nullptr) {
   if (check_layer(d)) return 1;
   STGCN_REQUIRE(d.norm == STGCN_NORM_LAYERNORM,
                 "continual inference needs LayerNorm: batch statistics of a single frame are undefined "
                 "(reference raises at models/utils/batchnorm.py:20)");
+  LayerPrep local;
+  const size_t mark0 = ws.mark();
+  if (!pp && math != STGCN_MATH_FP32) {
+    local = prep_take(d, K, V, ws);
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer operands)");
+      if (prep_run(d, K, V, local, st)) return 1;
+    }
+    pp = &local;
+  }
+  if (math != STGCN_MATH_FP32 && pp && pp->gcn && (d.residual != STGCN_RES_CONV || pp->res)) {
+    // ---- tensor-core step: the B streams form one "trial" of B frames (rows (b, w)) ----
+    const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
+    const long long rows = (long long)B * V;
+    float *resb = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows * d.c_out) : nullptr;
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer)");
+      if (resb) {
+        // residual branch LN_R(conv1x1(x)): no bias, no stride (rtstgcn.py:503)
+        tc::GcnTc2Params g{};
+        g.T_out = B; g.V = V; g.K = 1; g.Cin = d.c_in; g.planes = planes;
+        g.identity = 1;
+        g.epi.bias = pp->zero; g.epi.bias_sw = 0;
+        g.epi.n_wT = pp->nrT; g.epi.n_bT = pp->nrT + (size_t)d.c_out * V;
+        g.epi.out_f32 = resb;
+        g.epi.relu = 0;
+        g.epi.eps = kEps;
+        g.epi.debug = debug_mode();
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcn_tc2(d.c_out, x, pp->wr16, g, 1, B, 1, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      tc::GcnTc2Params g{};
+      g.T_out = B; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
+      g.csr_ptr = pp->kw_ptr; g.csr_va = pp->kw_va;
+      g.epi.bias = pp->bzT; g.epi.bias_sw = d.c_out;
+      g.epi.n_wT = pp->n1T; g.epi.n_bT = pp->n1T + (size_t)d.c_out * V;
+      g.epi.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
+      g.epi.out_f32 = out;
+      g.epi.eps = kEps;
+      g.epi.debug = debug_mode();
+      g.epi.rt_fifo = fifo; g.epi.rt_acc = acc; g.epi.rt_counter = counter;
+      g.epi.rt_F = d.stride * (d.kernel - 1) + 1;
+      g.epi.rt_S = d.stride;
+      g.epi.rt_slot = rows * d.c_out;
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_gcn_tc2(d.c_out, x, pp->wg16, g, 1, B, 1, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    ws.release(mark0);
+    return 0;
+  }
   const size_t mark = ws.mark();
   AdjCsr csr;
   if (build_csr(d.a_eff, 0, B, K, V, d.c_out, ws, csr, st)) return 1;
@@ -370,7 +492,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     a.S = d.stride;
     if (launch_frame(a, st)) return 1;
   }
-  ws.release(mark);
+  ws.release(mark0);
   return 0;
 }
 
@@ -429,6 +551,21 @@ int check_model(const stgcn_model_desc *m) {
   return 0;
 }
 
+size_t model_prepare_layout(const stgcn_model_desc &m, void *base, size_t cap, LayerPrep *out);
+inline bool use_prepared(const stgcn_model_desc &m) {
+  return m.prepared != nullptr && m.math != STGCN_MATH_FP32 &&
+         m.prepared_bytes >= model_prepare_layout(m, nullptr, 0, nullptr);
+}
+
+size_t model_prepare_layout(const stgcn_model_desc &m, void *base, size_t cap, LayerPrep *out) {
+  Bump pb(base, cap);
+  for (int i = 0; i < m.num_layers; ++i) {
+    LayerPrep P = prep_take(m.layers[i], m.partitions, m.num_joints, pb);
+    if (out) out[i] = P;
+  }
+  return pb.peak;
+}
+
 // ST-GCN model on `n` trials (one chunk).  logits [n, classes]; features optional (NCTV).
 int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float *features, int n, int T,
                 Bump &ws, cudaStream_t st) {
@@ -445,11 +582,15 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
   if (embed(m, x, buf[0], n, T, ws, st)) return 1;
   int cur = 0;
   t = T;
+  Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
     STGCN_REQUIRE(!d.rt, "stgcn_model_forward needs ST-GCN layers (rt == 0)");
     STGCN_REQUIRE(!d.a_per_sample, "per-sample adjacency is only supported by the layer-level API");
-    if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st)) return 1;
+    LayerPrep P;
+    const bool have = use_prepared(m);
+    if (have) P = prep_take(d, K, V, pb);
+    if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st, have ? &P : nullptr)) return 1;
     t = (t - 1) / d.stride + 1;
     cur ^= 1;
   }
@@ -521,12 +662,18 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
   char *sb = static_cast<char *>(state);
   int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters);
   int cur = 0;
+  Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
     STGCN_REQUIRE(d.rt, "rtstgcn_step needs online layers (rt == 1)");
     float *fifo = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.fifo[i]);
     float *acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]);
-    if (rt_layer_step_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], fifo, acc, counter, B, ws, st)) return 1;
+    LayerPrep P;
+    const bool have = use_prepared(m);
+    if (have) P = prep_take(d, K, V, pb);
+    if (rt_layer_step_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], fifo, acc, counter, B, ws, st,
+                           have ? &P : nullptr))
+      return 1;
     cur ^= 1;
   }
   const int c_last = m.layers[m.num_layers - 1].c_out;
@@ -707,6 +854,26 @@ int stgcn_graphconv_forward(const float *x, const float *w, const float *bias, c
   return to_nctv(z, y, N, c_out, (long long)T * V, c_out, st);
 }
 
+// ---- prepared operands -----------------------------------------------------------------
+size_t stgcn_model_prepare_bytes(const stgcn_model_desc *m) {
+  if (check_model(m)) return 0;
+  return model_prepare_layout(*m, nullptr, 0, nullptr);
+}
+
+int stgcn_model_prepare(const stgcn_model_desc *m, void *prepared, size_t prepared_bytes, void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(m->num_layers <= 64, "too many layers");
+  const size_t need = model_prepare_layout(*m, nullptr, 0, nullptr);
+  if (need == 0) return 0;
+  STGCN_REQUIRE(prepared && prepared_bytes >= need, "prepare: buffer too small (%zu B given, %zu B needed)",
+                prepared_bytes, need);
+  LayerPrep P[64];
+  model_prepare_layout(*m, prepared, prepared_bytes, P);
+  for (int i = 0; i < m->num_layers; ++i)
+    if (prep_run(m->layers[i], m->partitions, m->num_joints, P[i], as_stream(stream))) return 1;
+  return 0;
+}
+
 // ---- ST-GCN layer (stgcn.py:181-193) --------------------------------------------
 size_t stgcn_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int N, int T) {
   if (!d) return 0;
@@ -714,7 +881,11 @@ size_t stgcn_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int 
   const int T_out = (T - 1) / d->stride + 1;
   ws.take<float>((size_t)N * T * V * d->c_in);
   ws.take<float>((size_t)N * T_out * V * d->c_out);
-  layer_forward_ntvc(*d, K, V, 0, nullptr, nullptr, N, T, ws, nullptr);
+  const size_t m0 = ws.mark();
+  for (int math = STGCN_MATH_FP32; math <= STGCN_MATH_BF16X3; ++math) {  // largest over arithmetic modes
+    layer_forward_ntvc(*d, K, V, math, nullptr, nullptr, N, T, ws, nullptr);
+    ws.release(m0);
+  }
   return ws.peak;
 }
 
@@ -822,7 +993,11 @@ size_t rtstgcn_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, in
   Bump ws(nullptr, 0);
   ws.take<float>((size_t)B * V * d->c_in);
   ws.take<float>((size_t)B * V * d->c_out);
-  rt_layer_step_ntvc(*d, K, V, 0, nullptr, nullptr, nullptr, nullptr, nullptr, B, ws, nullptr);
+  const size_t m0 = ws.mark();
+  for (int math = STGCN_MATH_FP32; math <= STGCN_MATH_BF16X3; ++math) {
+    rt_layer_step_ntvc(*d, K, V, math, nullptr, nullptr, nullptr, nullptr, nullptr, B, ws, nullptr);
+    ws.release(m0);
+  }
   return ws.peak;
 }
 

@@ -59,6 +59,8 @@ class Model(nn.Module):
         self._desc = None
         self._state = None
         self._state_streams = 0
+        self._graph_on = False
+        self._graph = None
 
     def _layer_kwargs(self, i, num_joints):
         c = self.conf
@@ -94,7 +96,8 @@ class Model(nn.Module):
 
     # ------------------------------------------------------------------ #
     def _fingerprint(self):
-        extra = tuple(l.aggregate.A.data_ptr() for l in self.st_gcn) if self.is_online else ()
+        extra = tuple((l.aggregate.A.data_ptr(), l.aggregate.A._version) for l in self.st_gcn) \
+            if self.is_online else ()
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + extra + (self.math,)
 
     def _descriptor(self):
@@ -121,6 +124,8 @@ class Model(nn.Module):
         m.fcn_out_w, m.fcn_out_b = self.fcn_out.weight.data_ptr(), self.fcn_out.bias.data_ptr()
         m.layers = ctypes.cast(layers, ctypes.POINTER(_lib.LayerDesc))
         keep.append(layers)
+        if self.fcn_in.weight.is_cuda:
+            keep.append(_lib.prepare_model(m, self.fcn_in.weight.device))
         self._desc = (fp, (m, keep))
         return self._desc[1]
 
@@ -143,22 +148,61 @@ class Model(nn.Module):
             ctypes.byref(m), _lib.ptr(self._state), self._state_streams, first, count,
             _lib.stream_ptr(self._state.device)))
 
+    def _launch_step(self, frame, logits, b, dev):
+        lib = _lib.load()
+        m, _ = self._descriptor()
+        state = self._ensure_state(b, dev)
+        ws = self._ws.get(lib.rtstgcn_step_workspace_bytes(ctypes.byref(m), b), dev)
+        _lib.check(lib.rtstgcn_step(ctypes.byref(m), _lib.ptr(frame), _lib.ptr(state), _lib.ptr(logits), b,
+                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+
     @torch.no_grad()
     def step(self, frame):
-        """One continual step: ``frame (B, C_in, 1, V)`` -> logits ``(B, num_classes, 1)``."""
+        """One continual step: ``frame (B, C_in, 1, V)`` -> logits ``(B, num_classes, 1)``.
+
+        With ``cuda_graph=True`` (set by ``enable_cuda_graph``) the step's kernel sequence is
+        captured once per stream count and replayed: the per-frame cost at batch 1 is launch
+        latency, and a graph replay issues the whole sequence with one driver call."""
         b, c, l, v = frame.shape
         if l != 1:
             raise RuntimeError("step() takes exactly one frame per stream")
         frame = frame.contiguous()
         dev = _lib.require_cuda(frame, self.A, self.fcn_in.weight)
-        lib = _lib.load()
-        m, _ = self._descriptor()
-        state = self._ensure_state(b, dev)
-        ws = self._ws.get(lib.rtstgcn_step_workspace_bytes(ctypes.byref(m), b), dev)
+        if self._graph_on:
+            g = self._graph
+            if g is None or g['b'] != b or g['fp'] != self._fingerprint() or g['dev'] != dev:
+                g = self._capture(frame, b, dev)
+            g['x'].copy_(frame)
+            g['graph'].replay()
+            return g['logits'].clone().unsqueeze(-1)
         logits = torch.empty((b, self.num_classes), device=dev, dtype=torch.float32)
-        _lib.check(lib.rtstgcn_step(ctypes.byref(m), _lib.ptr(frame), _lib.ptr(state), _lib.ptr(logits), b,
-                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        self._launch_step(frame, logits, b, dev)
         return logits.unsqueeze(-1)
+
+    def enable_cuda_graph(self, on=True):
+        """Replay the continual step from a captured CUDA graph (state, workspace and the static
+        input/output buffers stay owned by this module)."""
+        self._graph_on = bool(on)
+        self._graph = None
+        return self
+
+    def _capture(self, frame, b, dev):
+        x = torch.zeros_like(frame)
+        logits = torch.zeros((b, self.num_classes), device=dev, dtype=torch.float32)
+        self._descriptor()                       # prepared operands are built outside the capture
+        state = self._ensure_state(b, dev)
+        saved = state.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):            # warm-up launches (function attributes, tensor maps)
+            self._launch_step(x, logits, b, dev)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._launch_step(x, logits, b, dev)
+        state.copy_(saved)                       # the warm-up step must not advance the streams
+        self._graph = dict(graph=graph, x=x, logits=logits, b=b, dev=dev, fp=self._fingerprint())
+        return self._graph
 
     @torch.no_grad()
     def forward(self, x):

@@ -89,6 +89,8 @@ class Model(nn.Module):
         m.fcn_out_w, m.fcn_out_b = self.fcn_out.weight.data_ptr(), self.fcn_out.bias.data_ptr()
         m.layers = ctypes.cast(layers, ctypes.POINTER(_lib.LayerDesc))
         keep.append(layers)
+        if self.fcn_in.weight.is_cuda:
+            keep.append(_lib.prepare_model(m, self.fcn_in.weight.device))
         self._desc = (fp, (m, keep))
         return self._desc[1]
 

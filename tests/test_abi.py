@@ -21,13 +21,13 @@ def test_header_symbols_exported(pkg):
     for n in names:
         assert hasattr(raw, n), "missing export: " + n
     assert set(names) == set(pkg._lib.SYMBOLS), "ctypes table out of sync with the header"
-    assert lib.stgcn_abi_version() == 1
+    assert lib.stgcn_abi_version() == 2
 
 
 def test_struct_layout_matches_header(pkg):
-    # 8 int32 + 13 pointers / 8 int32 + 6 pointers + 1 pointer (LP64)
+    # 8 int32 + 13 pointers / 8 int32 + 6 pointers + layers + prepared + prepared_bytes (LP64)
     assert ctypes.sizeof(pkg._lib.LayerDesc) == 8 * 4 + 13 * 8
-    assert ctypes.sizeof(pkg._lib.ModelDesc) == 8 * 4 + 7 * 8
+    assert ctypes.sizeof(pkg._lib.ModelDesc) == 8 * 4 + 9 * 8
 
 
 def test_sizing_calls_run_without_gpu(pkg, syn):

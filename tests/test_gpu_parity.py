@@ -345,3 +345,63 @@ def test_stgcn_model_c1_tensor_core(pkg, syn, cuda, math, tol):
     assert e_f < tol and e_l < tol
     if math == 'bf16':
         assert logits.argmax(1).item() == a['logits'].argmax(1).item()
+
+
+# ------------------------------------------------------------------ RT continual step on tensor cores
+def _rt_case(pkg, syn, cuda, tag, math):
+    a, _ = load_golden('rtstgcn_' + tag)
+    kw = {} if tag == 'pku' else dict(graph='imu_fogit_ABCD', in_feat=6, num_classes=8)
+    cfg = syn.arch_config('rt-st-gcn', **kw)
+    sd = syn.synth_state_dict(pkg.RtStgcn(**cfg).state_dict(), int(a['seeds'][0]))
+    cfg['math'] = math
+    m = pkg.RtStgcn(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(cuda)
+    m.prepare_benchmark({})
+    x = syn.synth_input((2, cfg['in_feat'], 48, cfg['graph']['num_node']), int(a['seeds'][1])).to(cuda)
+    return m.eval(), x, a['logits']
+
+
+@pytest.mark.parametrize('tag', ['pku', 'imu'])
+@pytest.mark.parametrize('math,tol', [('bf16x3', TOL), ('bf16', BF16_TOL)])
+def test_rt_full_tensor_core(pkg, syn, cuda, tag, math, tol):
+    """BASELINE configs 2/5: the continual step with the tcgen05 feature transform and the FIFO /
+    accumulator update fused into its epilogue, vs the reference's own continual loop (48 frames)."""
+    m, x, ref = _rt_case(pkg, syn, cuda, tag, math)
+    out = m(x)
+    err = rel_err(out, ref)
+    print("rt %s math=%s rel_err %.3e" % (tag, math, err))
+    assert err < tol, err
+    if math == 'bf16':
+        agree = (out.cpu().argmax(1) == ref.argmax(1)).float().mean().item()
+        assert agree >= 0.95, agree          # stated bf16 tolerance: top-1 agreement with fp32
+
+
+def test_rt_cuda_graph_and_many_streams_tensor_core(pkg, syn, cuda):
+    """Graph-replayed steps equal eagerly launched ones bit for bit; 600 streams (several tiles per
+    CTA, ragged last tile) agree with the oracle on a sampled subset; per-stream reset works."""
+    cfg = syn.arch_config('rt-st-gcn', num_classes=12, in_ch=[64, 64, 128], out_ch=[64, 128, 128],
+                          stride=[1, 2, 1])
+    sd = syn.synth_state_dict(pkg.RtStgcn(**cfg).state_dict(), 11)
+    cfg['math'] = 'bf16x3'
+    B, L = 600, 24
+    x = syn.synth_input((B, 3, L, 25), 12)
+    outs = []
+    for graph in (False, True):
+        m = pkg.RtStgcn(**cfg)
+        m.load_state_dict(sd)
+        m = m.to(cuda)
+        m.prepare_benchmark({})
+        m.enable_cuda_graph(graph)
+        outs.append(m(x.to(cuda)).cpu())
+    assert torch.equal(outs[0], outs[1])
+    ocfg = dict(layers=3, stride=[1, 2, 1], residual=[1, 1, 1], importance=True, kernel=9, out_ch=[64, 128, 128])
+    pick = [0, 4, 5, 299, 599]
+    ref = O.rt_model_run(x[pick], sd, ocfg)
+    assert rel_err(outs[1][pick], ref) < TOL
+    # per-stream reset under graph replay: stream 5 restarts, stream 4 continues
+    m.reset_streams(5, 1)
+    out2 = m(x[:, :, :3].to(cuda)).cpu()
+    assert rel_err(out2[5], ref[2][:, :3]) < TOL
+    cont = O.rt_model_run(torch.cat([x[4:5], x[4:5, :, :3]], dim=2), sd, ocfg)[:, :, L:]
+    assert rel_err(out2[4:5], cont) < TOL
