@@ -154,6 +154,33 @@ int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits
                         float *features, int N, int T, void *workspace,
                         size_t workspace_bytes, void *stream);
 
+/* ---- T-split: one long trial partitioned along time across ranks ----------------- */
+/* Every rank holds a contiguous chunk of T_local frames (a multiple of the trunk's total temporal
+ * stride on every rank but the last).  All stages of a layer are frame-local except the Gamma x 1
+ * temporal convolution, whose input u = relu(norm1(gcn(x))) needs (kernel-1)/2 frames of the
+ * neighbouring chunks (reference: the zero padding of tcn.2, stgcn.py:154-159; the reference's own
+ * long-sequence mechanism recomputes a 72-frame halo instead, utils/segment_generator.py:49-54).
+ * Between the two stages of every layer the library packs its boundary frames of u into
+ * send_left/send_right, calls `exchange(ctx, layer, bytes)` on the host -- which must enqueue, in
+ * stream order, send_left -> left rank's recv_right and send_right -> right rank's recv_left (NCCL
+ * send/recv) -- and unpacks recv_left/recv_right into the halo frames.  A rank without a left (right)
+ * neighbour zero-fills that halo: the convolution's zero padding.  LayerNorm only. */
+typedef struct stgcn_halo_desc {
+  int32_t has_left, has_right;
+  void *send_left, *send_right, *recv_left, *recv_right;   /* device, >= capacity bytes each */
+  size_t capacity;
+  int (*exchange)(void *ctx, int layer, size_t bytes);     /* host callback, 0 = success */
+  void *ctx;
+} stgcn_halo_desc;
+/* Bytes each of the four staging buffers must hold for N trials. */
+size_t stgcn_model_halo_bytes(const stgcn_model_desc *m, int N);
+size_t stgcn_model_tsplit_workspace_bytes(const stgcn_model_desc *m, int N, int T_local);
+/* x (N,in_feat,T_local,V) -> pooled_sums (N, c_last): sums over this rank's final frames and joints.
+ * The caller all-reduces them, divides by (T_final_total * V) and applies fcn_out (stgcn.py:92-95). */
+int stgcn_model_forward_tsplit(const stgcn_model_desc *m, const float *x, float *pooled_sums, int N,
+                               int T_local, const stgcn_halo_desc *halo, void *workspace,
+                               size_t workspace_bytes, void *stream);
+
 /* ---- RT-ST-GCN continual step ----------------------------------------------- */
 /* Per-stream FIFO/accumulator state for B concurrent streams (fp32):
  * per layer fifo[F][B][V][c_out] (F = stride*(kernel-1)+1) and acc[stride][B][V][c_out],

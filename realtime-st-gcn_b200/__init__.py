@@ -10,6 +10,7 @@ import it with ``importlib.import_module('realtime-st-gcn_b200')`` or through th
 from . import _lib            # noqa: F401
 from . import synthetic       # noqa: F401
 from . import skeletons       # noqa: F401
+from . import tsplit          # noqa: F401
 from .models import MODELS, Stgcn, RtStgcn   # noqa: F401
 
-__all__ = ['MODELS', 'Stgcn', 'RtStgcn', 'synthetic', 'skeletons']
+__all__ = ['MODELS', 'Stgcn', 'RtStgcn', 'synthetic', 'skeletons', 'tsplit']

@@ -693,6 +693,16 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+__global__ void k_pool_sum(const float *__restrict__ part, int nchunk, int C, int N, float *__restrict__ sums) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * C) return;
+  const long long n = i / C;
+  const int c = (int)(i - n * C);
+  float s = 0.f;
+  for (int k = 0; k < nchunk; ++k) s += part[(n * nchunk + k) * C + c];
+  sums[i] = s;
+}
+
 __global__ void __launch_bounds__(256)
     k_pool_fc(const float *__restrict__ part, int nchunk, int C, float inv_R, const float *__restrict__ W,
               const float *__restrict__ bias, int classes, float *__restrict__ logits) {

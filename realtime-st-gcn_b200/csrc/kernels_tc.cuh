@@ -274,6 +274,8 @@ struct EpiParams {
   const float *res;              // fp32 [rows][C] added after the norm, or null
   float *out_f32;                // fp32 [rows][C] or null
   __nv_bfloat16 *out_hi, *out_lo;  // split-bf16 planes [rows][C] or null
+  int out_T, out_t0;             // frames per trial of the plane buffer and frame offset of t = 0
+                                 // (T-split: the planes carry halo frames on both sides); 0,0 = same as rows
   int relu;
   float eps;
   int debug;                     // measurement aid: 1 = skip the epilogue body, 2 = skip transform math
@@ -323,8 +325,8 @@ __device__ __forceinline__ void frame_stats(const float *sp, int fr, int V, floa
 
 template <int C, int NH>
 __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
-                                                 int w, bool row_ok, long long row, float *s_part,
-                                                 int tile_parity, int h) {
+                                                 int w, bool row_ok, long long row, long long row_o,
+                                                 float *s_part, int tile_parity, int h) {
   if (e.debug & 1) return;
   constexpr int CH = C / NH;
   const int c0 = h * CH;
@@ -414,11 +416,11 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
           hi[i] = *reinterpret_cast<uint32_t *>(&hh);
           lo[i] = *reinterpret_cast<uint32_t *>(&ll);
         }
-        uint4 *dh = reinterpret_cast<uint4 *>(e.out_hi + row * C + c0 + cb);
+        uint4 *dh = reinterpret_cast<uint4 *>(e.out_hi + row_o * C + c0 + cb);
         dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
         if (e.out_lo) {
-          uint4 *dl = reinterpret_cast<uint4 *>(e.out_lo + row * C + c0 + cb);
+          uint4 *dl = reinterpret_cast<uint4 *>(e.out_lo + row_o * C + c0 + cb);
           dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
@@ -744,7 +746,7 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
         const bool row_ok = (r < RT) && (t < p.T_out);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<C, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, s_part, par, h);
+        ln_epilogue_tile<C, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h);
       }
       // accumulator buffer drained: hand it back to the MMA issuer
       tc_fence_before();
@@ -1159,7 +1161,11 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
         if (kRt)
           rt_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, t, s_part, par, h);
         else
-          ln_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, s_part, par, h);
+        {
+          const long long row_o =
+              p.epi.out_T ? ((long long)n * p.epi.out_T + t + p.epi.out_t0) * p.V + w : row;
+          ln_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row_o, s_part, par, h);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1323,9 +1329,12 @@ inline bool tcn_tc2_supported(int C, int V, int G, int stride, int T) {
 }
 
 // u planes: bf16 [planes][N][T][V][C] (T = input frames); wp: bf16 [2][G][C][C]; out/res rows over T_out
+// `halo`: the plane buffer holds `halo` extra frames before and after the T frames of every trial
+// (T-split: filled by the neighbouring ranks, or zeros at the sequence ends); output frame tau
+// still reads input frames stride*tau + j - pad of the T-frame sequence.
 template <int C>
 int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Params p, int N, int T, int stride,
-                     cudaStream_t st) {
+                     int halo, cudaStream_t st) {
   const int V = p.V, pad = (p.G - 1) / 2;
   const int kMaxSmem = 232448;
   // frames per tile: as many whole frames as fit 128 rows; shrink for the big stride-2 case
@@ -1379,6 +1388,11 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
   const int smem = 2 * p.a_stage_bytes + p.b_stages * C * 128 + kPartBytes + 512 + 1024;
 
   CUtensorMap tm_u0, tm_u1, tm_w;
+  if (halo) {
+    if (halo % stride) return fail("tcn tensor-core kernel: halo must be a multiple of the stride");
+    T += 2 * halo;                                   // frames per trial in the buffer
+    for (int q = 0; q < p.n_loads; ++q) p.load_f0[q] += halo / stride;
+  }
   const uint64_t plane_stride = (uint64_t)N * T * V * C * 2;
   if (stride == 1) {
     const uint64_t ud[5] = {(uint64_t)C, (uint64_t)V, (uint64_t)T, (uint64_t)N, (uint64_t)p.planes};
@@ -1406,11 +1420,11 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
 }
 
 inline int launch_tcn_tc2(int C, const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTc2Params &p, int N,
-                          int T, int stride, cudaStream_t st) {
+                          int T, int stride, int halo, cudaStream_t st) {
   switch (C) {
-    case 64: return launch_tcn_tc2_c<64>(u, wp, p, N, T, stride, st);
-    case 128: return launch_tcn_tc2_c<128>(u, wp, p, N, T, stride, st);
-    case 256: return launch_tcn_tc2_c<256>(u, wp, p, N, T, stride, st);
+    case 64: return launch_tcn_tc2_c<64>(u, wp, p, N, T, stride, halo, st);
+    case 128: return launch_tcn_tc2_c<128>(u, wp, p, N, T, stride, halo, st);
+    case 256: return launch_tcn_tc2_c<256>(u, wp, p, N, T, stride, halo, st);
   }
   return fail("tcn tensor-core kernel: unsupported channel count %d", C);
 }

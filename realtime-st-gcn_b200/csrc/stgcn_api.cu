@@ -219,8 +219,11 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
 // ---- ST-GCN layer on channels-last activations --------------------------------
 // x [N*T*V, c_in] -> out [N*T_out*V, c_out].  Scratch comes from `ws` (released on return).
 // `pp`: prepared operands (model path) or null (built here, per call).
+constexpr int kHalo = 4;   // halo frames carried on each side of the temporal-conv input in T-split mode
+
 int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
-                       int N, int T, Bump &ws, cudaStream_t st, const LayerPrep *pp = nullptr) {
+                       int N, int T, Bump &ws, cudaStream_t st, const LayerPrep *pp = nullptr,
+                       const stgcn_halo_desc *halo = nullptr, int layer_index = 0) {
   if (check_layer(d)) return 1;
   const size_t mark = ws.mark();
   const int T_out = (T - 1) / d.stride + 1;
@@ -242,9 +245,16 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   // tensor-core graph-convolution stage: LayerNorm, shared adjacency, C_in % 64 == 0
   const bool tc_gcn = math != STGCN_MATH_FP32 && pp && pp->gcn;
 
+  const int hf = halo ? kHalo : 0;                          // halo frames per side
+  if (halo) {
+    STGCN_REQUIRE(tc_gcn && tc_tcn, "T-split needs the tensor-core path (LayerNorm, math != fp32, C in {64,128,256})");
+    STGCN_REQUIRE((d.kernel - 1) / 2 <= kHalo && T >= kHalo, "T-split: kernel %d / chunk of %d frames unsupported",
+                  d.kernel, T);
+  }
+  const long long rows_u = (long long)N * (T + 2 * hf) * V;  // rows of the temporal-conv input buffer
   float *u = tc_tcn ? nullptr : ws.take<float>((size_t)rows * d.c_out);
-  __nv_bfloat16 *u16 = tc_tcn ? ws.take<__nv_bfloat16>((size_t)planes * rows * d.c_out) : nullptr;
-  __nv_bfloat16 *u16_lo = (tc_tcn && planes == 2 && u16) ? u16 + (size_t)rows * d.c_out : nullptr;
+  __nv_bfloat16 *u16 = tc_tcn ? ws.take<__nv_bfloat16>((size_t)planes * rows_u * d.c_out) : nullptr;
+  __nv_bfloat16 *u16_lo = (tc_tcn && planes == 2 && u16) ? u16 + (size_t)rows_u * d.c_out : nullptr;
   double *sums = bn ? ws.take<double>((size_t)4 * d.c_out) : nullptr;
   if (tc_gcn) {
     if (!ws.measuring()) {
@@ -255,6 +265,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       g.epi.bias = pp->bzT; g.epi.bias_sw = d.c_out;
       g.epi.n_wT = pp->n1T; g.epi.n_bT = pp->n1T + (size_t)d.c_out * V;
       g.epi.out_hi = u16; g.epi.out_lo = u16_lo; g.epi.out_f32 = u;
+      if (hf) { g.epi.out_T = T + 2 * hf; g.epi.out_t0 = hf; }
       g.epi.relu = 1;
       g.epi.eps = kEps;
       g.epi.debug = debug_mode();
@@ -335,6 +346,34 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
         a.out = resb;
         if (launch_frame(a, st)) return 1;
       }
+      if (halo) {
+        // boundary frames of u: pack -> exchange with the neighbouring ranks -> unpack (or zero padding)
+        const size_t frame_b = (size_t)V * d.c_out * sizeof(__nv_bfloat16);
+        const size_t pitch = (size_t)(T + 2 * hf) * frame_b, width = (size_t)hf * frame_b;
+        const size_t segs = (size_t)planes * N, bytes = width * segs;
+        STGCN_REQUIRE(bytes <= halo->capacity, "T-split: halo staging buffers too small (%zu B needed)", bytes);
+        char *ub = reinterpret_cast<char *>(u16);
+        if (halo->has_left)
+          STGCN_CUDA_OK(cudaMemcpy2DAsync(halo->send_left, width, ub + (size_t)hf * frame_b, pitch, width, segs,
+                                          cudaMemcpyDeviceToDevice, st));
+        if (halo->has_right)
+          STGCN_CUDA_OK(cudaMemcpy2DAsync(halo->send_right, width, ub + (size_t)T * frame_b, pitch, width, segs,
+                                          cudaMemcpyDeviceToDevice, st));
+        if (halo->has_left || halo->has_right) {
+          STGCN_REQUIRE(halo->exchange, "T-split: exchange callback missing");
+          STGCN_REQUIRE(halo->exchange(halo->ctx, layer_index, bytes) == 0, "T-split: halo exchange failed (layer %d)",
+                        layer_index);
+        }
+        if (halo->has_left)
+          STGCN_CUDA_OK(cudaMemcpy2DAsync(ub, pitch, halo->recv_left, width, width, segs, cudaMemcpyDeviceToDevice, st));
+        else
+          STGCN_CUDA_OK(cudaMemset2DAsync(ub, pitch, 0, width, segs, st));
+        char *right = ub + (size_t)(hf + T) * frame_b;
+        if (halo->has_right)
+          STGCN_CUDA_OK(cudaMemcpy2DAsync(right, pitch, halo->recv_right, width, width, segs, cudaMemcpyDeviceToDevice, st));
+        else
+          STGCN_CUDA_OK(cudaMemset2DAsync(right, pitch, 0, width, segs, st));
+      }
       tc::TcnTc2Params p{};
       p.T_out = T_out; p.V = V; p.G = d.kernel;
       p.planes = planes;
@@ -346,7 +385,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       p.epi.eps = kEps;
       p.epi.debug = debug_mode();
       ProfScope ps(KC_GEMM_TCN, st);
-      if (tc::launch_tcn_tc2(d.c_out, u16, pp->wp16, p, N, T, d.stride, st)) return 1;
+      if (tc::launch_tcn_tc2(d.c_out, u16, pp->wp16, p, N, T, d.stride, hf, st)) return 1;
       STGCN_LAUNCH_OK();
       if (debug_dump("tcn", d.c_out, st)) return 1;
     }
@@ -496,8 +535,9 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   return 0;
 }
 
+// pooled_sums != null: write the per-trial channel sums (N, C) instead of the classifier output
 int pool_fc(const float *x, int N, long long R, int C, const float *W, const float *bias, int classes,
-            float *logits, Bump &ws, cudaStream_t st) {
+            float *logits, Bump &ws, cudaStream_t st, float *pooled_sums = nullptr) {
   const int rpc = 512;
   const int nchunk = cdiv(R, rpc);
   float *part = ws.take<float>((size_t)N * nchunk * C);
@@ -506,6 +546,11 @@ int pool_fc(const float *x, int N, long long R, int C, const float *W, const flo
   ProfScope ps(KC_POOL, st);
   k_pool_partial<<<dim3(nchunk, N), 256, 0, st>>>(x, R, C, rpc, nchunk, part);
   STGCN_LAUNCH_OK();
+  if (pooled_sums) {
+    k_pool_sum<<<cdiv((long long)N * C, 256), 256, 0, st>>>(part, nchunk, C, N, pooled_sums);
+    STGCN_LAUNCH_OK();
+    return 0;
+  }
   k_pool_fc<<<N, 256, C * sizeof(float), st>>>(part, nchunk, C, 1.f / (float)R, W, bias, classes, logits);
   STGCN_LAUNCH_OK();
   return 0;
@@ -568,7 +613,7 @@ size_t model_prepare_layout(const stgcn_model_desc &m, void *base, size_t cap, L
 
 // ST-GCN model on `n` trials (one chunk).  logits [n, classes]; features optional (NCTV).
 int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float *features, int n, int T,
-                Bump &ws, cudaStream_t st) {
+                Bump &ws, cudaStream_t st, const stgcn_halo_desc *halo = nullptr, float *pooled_sums = nullptr) {
   const int V = m.num_joints, K = m.partitions;
   // ping-pong activation buffers sized for the largest layer interface
   size_t max_act = (size_t)n * T * V * m.layers[0].c_in;
@@ -590,14 +635,16 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     LayerPrep P;
     const bool have = use_prepared(m);
     if (have) P = prep_take(d, K, V, pb);
-    if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st, have ? &P : nullptr)) return 1;
+    if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st, have ? &P : nullptr, halo, i))
+      return 1;
     t = (t - 1) / d.stride + 1;
     cur ^= 1;
   }
   const int c_last = m.layers[m.num_layers - 1].c_out;
   if (features && !ws.measuring())
     if (to_nctv(buf[cur], features, n, c_last, (long long)t * V, c_last, st)) return 1;
-  if (pool_fc(buf[cur], n, (long long)t * V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, ws, st))
+  if (pool_fc(buf[cur], n, (long long)t * V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, ws, st,
+              pooled_sums))
     return 1;
   return 0;
 }
@@ -934,6 +981,37 @@ int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits
       return 1;
   }
   return 0;
+}
+
+// ---- T-split forward -----------------------------------------------------------------------
+size_t stgcn_model_halo_bytes(const stgcn_model_desc *m, int N) {
+  if (check_model(m)) return 0;
+  int cmax = 0;
+  for (int i = 0; i < m->num_layers; ++i) cmax = m->layers[i].c_out > cmax ? m->layers[i].c_out : cmax;
+  return (size_t)2 * N * kHalo * m->num_joints * cmax * sizeof(__nv_bfloat16);
+}
+
+size_t stgcn_model_tsplit_workspace_bytes(const stgcn_model_desc *m, int N, int T_local) {
+  if (check_model(m)) return 0;
+  Bump ws(nullptr, 0);
+  stgcn_halo_desc h{};
+  model_chunk(*m, nullptr, nullptr, nullptr, N, T_local, ws, nullptr, &h, nullptr);
+  return ws.peak;
+}
+
+int stgcn_model_forward_tsplit(const stgcn_model_desc *m, const float *x, float *pooled_sums, int N, int T_local,
+                               const stgcn_halo_desc *halo, void *workspace, size_t workspace_bytes,
+                               void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(halo && pooled_sums && workspace && N > 0 && T_local > 0, "tsplit: null argument or empty chunk");
+  STGCN_REQUIRE(m->norm == STGCN_NORM_LAYERNORM && m->math != STGCN_MATH_FP32,
+                "tsplit: needs LayerNorm and a tensor-core math mode (batch statistics would span ranks)");
+  int total_stride = 1;
+  for (int i = 0; i < m->num_layers; ++i) total_stride *= m->layers[i].stride;
+  STGCN_REQUIRE(!halo->has_right || T_local % total_stride == 0,
+                "tsplit: every chunk but the last must hold a multiple of %d frames (got %d)", total_stride, T_local);
+  Bump ws(workspace, workspace_bytes);
+  return model_chunk(*m, x, nullptr, nullptr, N, T_local, ws, as_stream(stream), halo, pooled_sums);
 }
 
 // ---- RT-ST-GCN continual step (rtstgcn.py:137-157, 528-553, 591-627) ---------------

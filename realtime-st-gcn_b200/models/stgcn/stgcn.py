@@ -121,6 +121,42 @@ class Model(nn.Module):
     def prepare_benchmark(self, arch_conf):
         return arch_conf
 
+    # ------------------------------------------------------------------ #
+    @torch.no_grad()
+    def forward_tsplit(self, x_local, total_frames, exchange):
+        """T-split forward (BASELINE config 4): ``x_local (N, in_feat, T_local, V)`` is this rank's
+        contiguous chunk of a ``total_frames``-frame trial (chunking: ``tsplit.chunk_bounds``);
+        ``exchange`` is a ``tsplit.DistExchange`` (or compatible) that swaps the per-layer halo
+        frames with the ring neighbours and all-reduces the pooled sums.  Returns the full-trial
+        logits ``(N, num_classes, 1)`` on every rank."""
+        from ... import tsplit
+        n, c, t, v = x_local.shape
+        x_local = x_local.contiguous()
+        dev = _lib.require_cuda(x_local, self.A, self.fcn_in.weight)
+        if self.normalization != 'LayerNorm' or self.math == 'fp32':
+            raise RuntimeError("T-split needs LayerNorm and math in {'bf16x3','bf16'}: batch statistics "
+                               "would span ranks, and the halo lives in the tensor-core operand layout")
+        lib = _lib.load()
+        m, _ = self._descriptor()
+        need = lib.stgcn_model_halo_bytes(ctypes.byref(m), n)
+        if exchange.capacity < need:
+            raise RuntimeError("halo staging buffers too small: %d < %d bytes" % (exchange.capacity, need))
+        hd, keep = exchange.descriptor()
+        ws = self._ws.get(lib.stgcn_model_tsplit_workspace_bytes(ctypes.byref(m), n, t), dev)
+        c_last = self.gcn_networks[-1].out_channels
+        sums = torch.empty((n, c_last), device=dev, dtype=torch.float32)
+        exchange.error = None
+        rc = lib.stgcn_model_forward_tsplit(ctypes.byref(m), _lib.ptr(x_local), _lib.ptr(sums), n, t,
+                                            ctypes.byref(hd), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        if rc != 0 and getattr(exchange, 'error', None) is not None:
+            raise exchange.error
+        _lib.check(rc)
+        del keep
+        exchange.all_reduce_sum(sums)
+        t_final = tsplit.frames_after(total_frames, [g.stride for g in self.gcn_networks])
+        pooled = (sums / float(t_final * v)).view(n, c_last, 1, 1)
+        return self.fcn_out(pooled).squeeze(-1)          # (N, classes, 1), stgcn.py:95-97
+
 
 class StgcnLayer(nn.Module):
     """One st_gcn block: ``relu(norm2(conv_Gx1(relu(norm1(gcn(x, A))))) + res(x))``

@@ -405,3 +405,108 @@ def test_rt_cuda_graph_and_many_streams_tensor_core(pkg, syn, cuda):
     assert rel_err(out2[5], ref[2][:, :3]) < TOL
     cont = O.rt_model_run(torch.cat([x[4:5], x[4:5, :, :3]], dim=2), sd, ocfg)[:, :, L:]
     assert rel_err(out2[4:5], cont) < TOL
+
+
+# ------------------------------------------------------------------ T-split (BASELINE config 4)
+class _LocalExchange:
+    """Two (or more) ranks emulated as threads on ONE GPU: same staging buffers and callback
+    contract as tsplit.DistExchange, the swap done by device copies behind a thread barrier."""
+
+    def __init__(self, rank, world, capacity, device, shared):
+        import threading  # noqa: F401
+        self.rank, self.world, self.capacity, self.shared = rank, world, capacity, shared
+        self.has_left, self.has_right = rank > 0, rank < world - 1
+        mk = lambda: torch.zeros(capacity, dtype=torch.uint8, device=device)   # noqa: E731
+        self.send_left, self.send_right, self.recv_left, self.recv_right = mk(), mk(), mk(), mk()
+        self.calls = 0
+        shared['ex'][rank] = self
+
+    def __call__(self, layer, nbytes):
+        torch.cuda.current_stream().synchronize()
+        self.shared['barrier'].wait()
+        peers = self.shared['ex']
+        if self.has_left:
+            self.recv_left[:nbytes].copy_(peers[self.rank - 1].send_right[:nbytes])
+        if self.has_right:
+            self.recv_right[:nbytes].copy_(peers[self.rank + 1].send_left[:nbytes])
+        torch.cuda.current_stream().synchronize()
+        self.shared['barrier'].wait()
+        self.calls += 1
+        return 0
+
+    def all_reduce_sum(self, t):
+        torch.cuda.current_stream().synchronize()
+        self.shared['sums'][self.rank] = t.clone()
+        self.shared['barrier'].wait()
+        total = sum(self.shared['sums'][r] for r in range(self.world))
+        self.shared['barrier'].wait()
+        t.copy_(total)
+        return t
+
+    def descriptor(self):
+        import importlib
+        ts = importlib.import_module('realtime-st-gcn_b200').tsplit
+
+        def cb(_ctx, layer, nbytes):
+            try:
+                return int(self(layer, nbytes))
+            except Exception as e:
+                self.error = e
+                return 1
+        fn = ts.EXCHANGE_FN(cb)
+        d = ts.HaloDesc()
+        d.has_left, d.has_right = int(self.has_left), int(self.has_right)
+        d.send_left, d.send_right = self.send_left.data_ptr(), self.send_right.data_ptr()
+        d.recv_left, d.recv_right = self.recv_left.data_ptr(), self.recv_right.data_ptr()
+        d.capacity, d.exchange, d.ctx = self.capacity, fn, None
+        return d, fn
+
+
+@pytest.mark.parametrize('world,total_frames,math,tol', [(2, 64, 'bf16x3', TOL), (3, 93, 'bf16x3', TOL),
+                                                         (2, 40, 'bf16', BF16_TOL)])
+def test_tsplit_emulated_ranks(pkg, syn, cuda, world, total_frames, math, tol):
+    """T-split forward through the C ABI: per-layer halo frames packed, swapped and unpacked in the
+    tensor-core operand layout (stride-1 and stride-2 layers, channel-changing layers), pooled sums
+    all-reduced; vs the full-sequence oracle."""
+    import threading
+    kw = dict(num_classes=12, in_ch=[64, 64, 128, 128], out_ch=[64, 128, 128, 256], stride=[1, 2, 1, 2])
+    cfg = syn.arch_config('st-gcn', **kw)
+    sd = syn.synth_state_dict(pkg.Stgcn(**cfg).state_dict(), 31)
+    cfg['math'] = math
+    x = syn.synth_input((2, 3, total_frames, 25), 32)
+    bounds = pkg.tsplit.chunk_bounds(total_frames, world, 4)
+    shared = dict(ex=[None] * world, sums=[None] * world, barrier=threading.Barrier(world))
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(cuda)
+            m = pkg.Stgcn(**cfg)
+            m.load_state_dict(sd)
+            m = m.to(cuda).eval()
+            need = pkg._lib.load().stgcn_model_halo_bytes(ctypes.byref(m._descriptor()[0]), 2)
+            ex = _LocalExchange(rank, world, need, cuda, shared)
+            shared['barrier'].wait()
+            a, b = bounds[rank]
+            with torch.cuda.stream(torch.cuda.Stream(device=cuda)):
+                out[rank] = m.forward_tsplit(x[:, :, a:b].to(cuda), total_frames, ex).cpu()
+            assert ex.calls == 4
+        except Exception as e:                                  # pragma: no cover
+            errs.append(e)
+            shared['barrier'].abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+    ref = O.stgcn_model(x, sd, dict(layers=4, stride=kw['stride'], residual=[1] * 4, normalization='LayerNorm'))
+    for r in range(world):
+        assert rel_err(out[r], ref) < tol, (r, rel_err(out[r], ref))
+    # and a single rank without neighbours equals the ordinary forward
+    m = pkg.Stgcn(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    shared1 = dict(ex=[None], sums=[None], barrier=threading.Barrier(1))
+    ex = _LocalExchange(0, 1, pkg._lib.load().stgcn_model_halo_bytes(ctypes.byref(m._descriptor()[0]), 2), cuda, shared1)
+    single = m.forward_tsplit(x.to(cuda), total_frames, ex)
+    assert rel_err(single, m(x.to(cuda))) < 1e-6
