@@ -268,9 +268,12 @@ __global__ void k_pack_tcn_w_bf16(const float *__restrict__ w, __nv_bfloat16 *__
 // (float[2][128] in shared memory) and named barrier 1 (the 128 epilogue threads).
 // --------------------------------------------------------------------------- //
 struct EpiParams {
-  const float *bias;             // bias index = w * bias_sw + c (contiguous in c)
+  // Per-(joint, channel) tables use the layout [C/4][V][4]: the float4 of channel group g and joint
+  // w is at (g*V + w)*4, so the 32 rows of a warp (consecutive joints) read ~4 cache lines per load
+  // instruction instead of 32.
+  const float *bias;             // bias_sw = 1: [C/4][V][4] table; bias_sw = 0: plain [C] vector
   int bias_sw;
-  const float *n_wT, *n_bT;      // LayerNorm affine transposed to (V, C) (k_transpose_affine)
+  const float *n_wT, *n_bT;      // LayerNorm affine in [C/4][V][4] (k_transpose_affine)
   const float *res;              // fp32 [rows][C] added after the norm, or null
   float *out_f32;                // fp32 [rows][C] or null
   __nv_bfloat16 *out_hi, *out_lo;  // split-bf16 planes [rows][C] or null
@@ -297,6 +300,9 @@ struct EpiParams {
 constexpr int kEpiNH = 2;                       // column groups (epilogue warps per TMEM lane quarter)
 constexpr int kEpiThreads = 128 * kEpiNH;
 constexpr int kPartBytes = 2 * 2 * kEpiNH * 128 * 4;
+constexpr int kPatchPitch = 144;                           // 128 B of data + 16 B: conflict-free own-row access
+constexpr int kPatchBytes = 32 * kPatchPitch;              // one epilogue warp's staging patch
+constexpr int kPatchTotal = 4 * kEpiNH * kPatchBytes;
 
 template <int C, int NH>
 __device__ __forceinline__ void frame_stats(const float *sp, int fr, int V, float eps, float &mean, float &rstd) {
@@ -326,20 +332,25 @@ __device__ __forceinline__ void frame_stats(const float *sp, int fr, int V, floa
 template <int C, int NH>
 __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
                                                  int w, bool row_ok, long long row, long long row_o,
-                                                 float *s_part, int tile_parity, int h) {
+                                                 float *s_part, int tile_parity, int h, uint8_t *patch) {
   if (e.debug & 1) return;
   constexpr int CH = C / NH;
+  static_assert(CH % 32 == 0, "epilogue works in 32-column super-chunks");
   const int c0 = h * CH;
-  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias + w * e.bias_sw + c0);
+  // float4 index of channel group g: table -> g*V + w, plain vector -> g
+  const int pstep = e.bias_sw ? V : 1;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
   float *sp = s_part + tile_parity * (2 * NH * 128);
   float v[16];
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
+  const bool tdbg = (e.debug & 4) && blockIdx.x == 0 && r == 0 && h == 0;
+  long long tq0 = tdbg ? clock64() : 0;
 #pragma unroll 1
   for (int cb = 0; cb < CH; cb += 16) {
     tmem_ld16(taddr + c0 + cb, v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = __ldg(bias4 + ((e.debug & 16) ? 0 : (cb >> 2) + i));
+      const float4 b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
       v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
     }
     if (cb == 0) shift = v[0];
@@ -354,78 +365,119 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
   const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)CH), 0.f);
   sp[h * 128 + r] = row_ok ? m_r : 0.f;
   sp[(NH + h) * 128 + r] = row_ok ? M2_r : 0.f;
-  // residual rows come from HBM: start the first loads before the barrier
-  const float4 *rs4 = (e.res && row_ok && !(e.debug & 8)) ? reinterpret_cast<const float4 *>(e.res + row * C + c0) : nullptr;
-  float4 rn[4];
-  if (rs4) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) rn[i] = rs4[i];
-  }
+  long long tq1 = tdbg ? clock64() : 0;
   asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
   float mean = 0.f, rstd = 0.f;
   if (r < RT && !(e.debug & 64)) frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
-  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT + w * C + c0);
-  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT + w * C + c0);
+  long long tq2 = tdbg ? clock64() : 0;
+  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT) + (c0 >> 2) * V + w;
+  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT) + (c0 >> 2) * V + w;
+  // Pass 2 works in 32-column super-chunks through this warp's shared-memory patch [32 rows][144 B]:
+  // the residual block is loaded and the output block stored COOPERATIVELY (8 lanes per row, whole
+  // 128-B lines, 4 rows per instruction) instead of 32 different rows per instruction; in between
+  // every lane touches only its own patch row.
+  const int lane = threadIdx.x & 31;
+  const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+  const long long row0 = __shfl_sync(0xffffffffu, row, 0);        // rows of a warp are contiguous
+  const long long rowo0 = __shfl_sync(0xffffffffu, row_o, 0);
+  uint8_t *mine = patch + lane * kPatchPitch;
+  const bool use_res = e.res != nullptr && !(e.debug & 8);
 #pragma unroll 1
-  for (int cb = 0; cb < CH; cb += 16) {
-    float4 rc[4];
-    if (rs4) {
+  for (int sb = 0; sb < CH; sb += 32) {
+    if (use_res) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) rc[i] = rn[i];
-      if (cb + 16 < CH) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rn[i] = rs4[((cb + 16) >> 2) + i];
+      for (int i = 0; i < 8; ++i) {
+        const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
+        if ((okmask >> rr) & 1)
+          *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + qq * 16) =
+              *reinterpret_cast<const float4 *>(e.res + (row0 + rr) * C + c0 + sb + qq * 4);
       }
+      __syncwarp();
     }
-    tmem_ld16(taddr + c0 + cb, v);
-    if (row_ok) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pi = (e.debug & 16) ? 0 : (cb >> 2) + i;
-        const float4 b4 = __ldg(bias4 + pi);
-        const float4 g4 = __ldg(nw4 + pi);
-        const float4 o4 = __ldg(nb4 + pi);
-        v[4 * i] = (v[4 * i] + b4.x - mean) * rstd * g4.x + o4.x;
-        v[4 * i + 1] = (v[4 * i + 1] + b4.y - mean) * rstd * g4.y + o4.y;
-        v[4 * i + 2] = (v[4 * i + 2] + b4.z - mean) * rstd * g4.z + o4.z;
-        v[4 * i + 3] = (v[4 * i + 3] + b4.w - mean) * rstd * g4.w + o4.w;
-      }
-      if (rs4) {
+    for (int half = 0; half < 2; ++half) {
+      const int cb = sb + half * 16;
+      tmem_ld16(taddr + c0 + cb, v);
+      if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          v[4 * i] += rc[i].x; v[4 * i + 1] += rc[i].y; v[4 * i + 2] += rc[i].z; v[4 * i + 3] += rc[i].w;
+          const int pi = (cb >> 2) + i;
+          const float4 b4 = __ldg(bias4 + pi * pstep);
+          const float4 g4 = __ldg(nw4 + pi * V);
+          const float4 o4 = __ldg(nb4 + pi * V);
+          v[4 * i] = (v[4 * i] + b4.x - mean) * rstd * g4.x + o4.x;
+          v[4 * i + 1] = (v[4 * i + 1] + b4.y - mean) * rstd * g4.y + o4.y;
+          v[4 * i + 2] = (v[4 * i + 2] + b4.z - mean) * rstd * g4.z + o4.z;
+          v[4 * i + 3] = (v[4 * i + 3] + b4.w - mean) * rstd * g4.w + o4.w;
         }
-      }
-      if (e.relu) {
+        if (use_res) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (e.out_f32 && !(e.debug & 32)) {
-        float4 *dst = reinterpret_cast<float4 *>(e.out_f32 + row * C + c0 + cb);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      }
-      if (e.out_hi && !(e.debug & 32)) {
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[2 * i], h0, l0);
-          split_bf16(v[2 * i + 1], h1, l1);
-          __nv_bfloat162 hh(h0, h1), ll(l0, l1);
-          hi[i] = *reinterpret_cast<uint32_t *>(&hh);
-          lo[i] = *reinterpret_cast<uint32_t *>(&ll);
+          for (int i = 0; i < 4; ++i) {
+            const float4 r4 = *reinterpret_cast<const float4 *>(mine + half * 64 + i * 16);
+            v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+          }
         }
-        uint4 *dh = reinterpret_cast<uint4 *>(e.out_hi + row_o * C + c0 + cb);
-        dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        if (e.out_lo) {
-          uint4 *dl = reinterpret_cast<uint4 *>(e.out_lo + row_o * C + c0 + cb);
-          dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        if (e.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (e.out_f32) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4 *>(mine + half * 64 + i * 16) =
+                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[2 * i], h0, l0);
+            split_bf16(v[2 * i + 1], h1, l1);
+            __nv_bfloat162 hh(h0, h1), ll(l0, l1);
+            hi[i] = *reinterpret_cast<uint32_t *>(&hh);
+            lo[i] = *reinterpret_cast<uint32_t *>(&ll);
+          }
+          // patch row: [hi of 32 columns: 64 B][lo of 32 columns: 64 B]
+          uint4 *ph = reinterpret_cast<uint4 *>(mine + half * 32);
+          ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          uint4 *pl = reinterpret_cast<uint4 *>(mine + 64 + half * 32);
+          pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
       }
     }
+    __syncwarp();
+    if (!(e.debug & 32)) {
+      if (e.out_f32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
+          if ((okmask >> rr) & 1)
+            *reinterpret_cast<float4 *>(e.out_f32 + (row0 + rr) * C + c0 + sb + qq * 4) =
+                *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + qq * 16);
+        }
+      } else if (e.out_hi) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
+          if ((okmask >> rr) & 1) {
+            *reinterpret_cast<uint4 *>(e.out_hi + (rowo0 + rr) * C + c0 + sb + qq * 8) =
+                *reinterpret_cast<const uint4 *>(patch + rr * kPatchPitch + qq * 16);
+            if (e.out_lo)
+              *reinterpret_cast<uint4 *>(e.out_lo + (rowo0 + rr) * C + c0 + sb + qq * 8) =
+                  *reinterpret_cast<const uint4 *>(patch + rr * kPatchPitch + 64 + qq * 16);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (tdbg) {
+    const long long tq3 = clock64();
+    atomicAdd(&g_dbg[12], (unsigned long long)(tq1 - tq0));
+    atomicAdd(&g_dbg[13], (unsigned long long)(tq2 - tq1));
+    atomicAdd(&g_dbg[14], (unsigned long long)(tq3 - tq2));
   }
 }
 
@@ -442,7 +494,8 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
   if (e.debug & 1) return;
   constexpr int CH = C / NH;
   const int c0 = h * CH;
-  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias + w * e.bias_sw + c0);
+  const int pstep = e.bias_sw ? V : 1;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
   float *sp = s_part + tile_parity * (2 * NH * 128);
   float v[16];
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
@@ -463,7 +516,7 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
     if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 b4 = __ldg(bias4 + (cb >> 2) + i);
+        const float4 b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
         float4 z = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
         float4 a = ac[i];
         a.x = (a.x + z.x) + (-fc[i].x);
@@ -500,8 +553,8 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
   asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
   float mean = 0.f, rstd = 0.f;
   if (r < RT) frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
-  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT + w * C + c0);
-  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT + w * C + c0);
+  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT) + (c0 >> 2) * V + w;
+  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT) + (c0 >> 2) * V + w;
 #pragma unroll 1
   for (int cb = 0; cb < CH; cb += 16) {
     float4 rc[4];
@@ -517,8 +570,8 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
     if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 g4 = __ldg(nw4 + (cb >> 2) + i);
-        const float4 o4 = __ldg(nb4 + (cb >> 2) + i);
+        const float4 g4 = __ldg(nw4 + ((cb >> 2) + i) * V);
+        const float4 o4 = __ldg(nb4 + ((cb >> 2) + i) * V);
         v[4 * i] = fmaxf((v[4 * i] - mean) * rstd * g4.x + o4.x, 0.f);
         v[4 * i + 1] = fmaxf((v[4 * i + 1] - mean) * rstd * g4.y + o4.y, 0.f);
         v[4 * i + 2] = fmaxf((v[4 * i + 2] - mean) * rstd * g4.z + o4.z, 0.f);
@@ -587,12 +640,14 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + 2 * p.a_stage_bytes;
   const uint32_t sPart = sB + S * kBBytes;                    // float[2][2][NH][128]
-  const uint32_t sBar = sPart + kPartBytes;
+  const uint32_t sPatch = sPart + kPartBytes;                 // epilogue staging patches
+  const uint32_t sBar = sPatch + kPatchTotal;
   const uint32_t bFullA = sBar, bEmptyA = sBar + 16, bTmemFull = sBar + 32, bTmemEmpty = sBar + 48;
   const uint32_t bFullB = sBar + 64, bEmptyB = bFullB + 8 * S;
   const uint32_t sTmemPtr = bEmptyB + 8 * S;
   volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
   float *s_part = reinterpret_cast<float *>(gen_base + (sPart - smem_base));
+  uint8_t *s_patch = gen_base + (sPatch - smem_base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = C / 64;
@@ -746,7 +801,8 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
         const bool row_ok = (r < RT) && (t < p.T_out);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<C, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h);
+        ln_epilogue_tile<C, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h,
+                                    s_patch + (warp - 3) * kPatchBytes);
       }
       // accumulator buffer drained: hand it back to the MMA issuer
       tc_fence_before();
@@ -806,7 +862,7 @@ __global__ void k_bias_through_adj(const float *__restrict__ A, const float *__r
                                    int CO, float *__restrict__ bzT) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= CO * V) return;
-  const int w = i / CO, c = i - w * CO;            // output layout [V][CO]: contiguous in c
+  const int e4 = i & 3, w = (i >> 2) % V, c = ((i >> 2) / V) * 4 + e4;   // output layout [CO/4][V][4]
   float s = 0.f;
   for (int k = 0; k < K; ++k) {
     float col = 0.f;
@@ -816,12 +872,12 @@ __global__ void k_bias_through_adj(const float *__restrict__ A, const float *__r
   bzT[i] = s;
 }
 
-// LayerNorm affine (C, 1, V) -> (V, C), so that an epilogue thread (one joint, 16 channels at a
-// time) reads it with 16-B loads
+// LayerNorm affine (C, 1, V) -> [C/4][V][4]: an epilogue thread (one joint, 4 channels per load)
+// reads 16 B, and the consecutive joints of a warp share cache lines
 __global__ void k_transpose_affine(const float *__restrict__ src, float *__restrict__ dst, int C, int V) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * V) return;
-  const int w = i / C, c = i - w * C;
+  const int e4 = i & 3, w = (i >> 2) % V, c = ((i >> 2) / V) * 4 + e4;   // [C/4][V][4]
   dst[i] = src[c * V + w];
 }
 
@@ -873,7 +929,8 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
   const uint32_t sB = sXs + XB * p.xs_alloc;
   const uint32_t sCsr = sB + S * kBBytes;
   const uint32_t sPart = sCsr + kGcn2Csr;
-  const uint32_t sBar = sPart + kPartBytes;
+  const uint32_t sPatch = sPart + kPartBytes;
+  const uint32_t sBar = sPatch + kPatchTotal;
   const uint32_t bXsFull = sBar, bXsEmpty = sBar + 16, bTmemFull = sBar + 32, bTmemEmpty = sBar + 48;
   const uint32_t bAFull = sBar + 64, bAEmpty = sBar + 96;
   const uint32_t bFullB = sBar + 128, bEmptyB = bFullB + 8 * S;
@@ -882,6 +939,7 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
   int *s_ptr = reinterpret_cast<int *>(gen_base + (sCsr - smem_base));
   int2 *s_va = reinterpret_cast<int2 *>(gen_base + (sCsr - smem_base) + 512);
   float *s_part = reinterpret_cast<float *>(gen_base + (sPart - smem_base));
+  uint8_t *s_patch = gen_base + (sPatch - smem_base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.Cin / 64;
@@ -1164,7 +1222,8 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
         {
           const long long row_o =
               p.epi.out_T ? ((long long)n * p.epi.out_T + t + p.epi.out_t0) * p.V + w : row;
-          ln_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row_o, s_part, par, h);
+          ln_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row_o, s_part, par, h,
+                                       s_patch + (warp - 10) * kPatchBytes);
         }
       }
       tc_fence_before();
@@ -1275,7 +1334,7 @@ int launch_gcn_tc2_c(const float *x, const __nv_bfloat16 *wp, GcnTc2Params p, in
   p.a_stage_bytes = ((p.NT * RT + 128 - RT) * 128 + 1023) & ~1023;
   p.xs_tx = p.NT * p.FT * V * 64 * 4;
   p.xs_alloc = 2 * ((p.NT * p.FT * V * 128 + 1023) & ~1023);   // two 32-channel swizzled sub-tiles
-  const int fixed = kGcn2Csr + kPartBytes + 512 + 1024;
+  const int fixed = kGcn2Csr + kPartBytes + kPatchTotal + 512 + 1024;
   // prefer: double-buffered input tile, 3-deep A ring, >= 2 weight stages; back off as smem requires
   const int tries[4][2] = {{2, 3}, {2, 2}, {1, 3}, {1, 2}};
   int ok = 0;
@@ -1378,14 +1437,14 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
       a_rows = (nf[0] + nf[1]) * V + spill;
     }
     p.a_stage_bytes = (a_rows * 128 + 1023) & ~1023;
-    const int left = kMaxSmem - 2 * p.a_stage_bytes - kPartBytes - 512 - 1024;
+    const int left = kMaxSmem - 2 * p.a_stage_bytes - kPartBytes - kPatchTotal - 512 - 1024;
     p.b_stages = left / (C * 128);
     if (p.b_stages > 8) p.b_stages = 8;
     if (p.b_stages >= 2) break;
   }
   p.groups_per_trial = (p.T_out + p.NT * p.FT - 1) / (p.NT * p.FT);
   p.items = N * p.groups_per_trial;
-  const int smem = 2 * p.a_stage_bytes + p.b_stages * C * 128 + kPartBytes + 512 + 1024;
+  const int smem = 2 * p.a_stage_bytes + p.b_stages * C * 128 + kPartBytes + kPatchTotal + 512 + 1024;
 
   CUtensorMap tm_u0, tm_u1, tm_w;
   if (halo) {

@@ -30,11 +30,11 @@ int debug_dump(const char *what, int c, cudaStream_t st) {
   unsigned long long h[16];
   STGCN_CUDA_OK(cudaStreamSynchronize(st));
   STGCN_CUDA_OK(cudaMemcpyFromSymbol(h, tc::g_dbg, sizeof(h)));
-  static const char *names[12] = {"mma_wait_tmem", "mma_wait_A", "mma_wait_B", "mma_total", "xA_prod_wait",
+  static const char *names[15] = {"mma_wait_tmem", "mma_wait_A", "mma_wait_B", "mma_total", "xA_prod_wait",
                                   "B_prod_wait", "epi_wait_tmem", "epi_work", "xf_wait_x", "xf_wait_Aempty",
-                                  "xf_compute", "items"};
+                                  "xf_compute", "items", "epi_pass1", "epi_bar_stats", "epi_pass2"};
   fprintf(stderr, "[dbg] %s<%d>:", what, c);
-  for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
+  for (int i = 0; i < 15; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
   fprintf(stderr, "\n");
   memset(h, 0, sizeof(h));
   STGCN_CUDA_OK(cudaMemcpyToSymbol(tc::g_dbg, h, sizeof(h)));
@@ -262,7 +262,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       tc::GcnTc2Params g{};
       g.T_out = T; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
       g.csr_ptr = pp->kw_ptr; g.csr_va = pp->kw_va;
-      g.epi.bias = pp->bzT; g.epi.bias_sw = d.c_out;
+      g.epi.bias = pp->bzT; g.epi.bias_sw = 1;
       g.epi.n_wT = pp->n1T; g.epi.n_bT = pp->n1T + (size_t)d.c_out * V;
       g.epi.out_hi = u16; g.epi.out_lo = u16_lo; g.epi.out_f32 = u;
       if (hf) { g.epi.out_T = T + 2 * hf; g.epi.out_t0 = hf; }
@@ -484,7 +484,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       tc::GcnTc2Params g{};
       g.T_out = B; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
       g.csr_ptr = pp->kw_ptr; g.csr_va = pp->kw_va;
-      g.epi.bias = pp->bzT; g.epi.bias_sw = d.c_out;
+      g.epi.bias = pp->bzT; g.epi.bias_sw = 1;
       g.epi.n_wT = pp->n1T; g.epi.n_bT = pp->n1T + (size_t)d.c_out * V;
       g.epi.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
       g.epi.out_f32 = out;
