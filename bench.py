@@ -131,6 +131,17 @@ def trunk_flops(T, V=25, K=3, gamma=9, in_feat=3, classes=52):
     return f
 
 
+def ncu_traffic(kernel_class):
+    """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/r01_ncu_top_kernel.json, written by tools/ncu_summary.py), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r01_ncu_top_kernel.json')
+    try:
+        d = json.load(open(path))
+        return d.get(kernel_class, {}).get('dram_bytes_per_launch')
+    except (OSError, ValueError):
+        return None
+
+
 def oracle_cfg(syn, norm):
     return dict(layers=9, stride=syn.TRUNK_STRIDE, residual=[1] * 9, importance=True, normalization=norm)
 
@@ -173,7 +184,7 @@ def run_reference(args):
     }))
 
 
-def rt_latency(pkg, dev, streams, steps, graph_kw, math):
+def rt_latency(pkg, dev, streams, steps, graph_kw, math, hbm_gbs=None, cuda_graph=True):
     """RT-ST-GCN continual step latency (one frame for every stream), CUDA-event timed per step."""
     syn = pkg.synthetic
     cfg = syn.arch_config('rt-st-gcn', **graph_kw)
@@ -182,6 +193,7 @@ def rt_latency(pkg, dev, streams, steps, graph_kw, math):
     m.load_state_dict(syn.synth_state_dict(m.state_dict(), 61))
     m = m.to(dev)
     m.prepare_benchmark({})
+    m.enable_cuda_graph(cuda_graph)
     v, c = cfg['graph']['num_node'], cfg['in_feat']
     frames = torch.randn(8, streams, c, 1, v, device=dev)
     for i in range(20):                                       # FIFO fill is 17 frames
@@ -195,8 +207,15 @@ def rt_latency(pkg, dev, streams, steps, graph_kw, math):
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     p50 = ms[len(ms) // 2]
-    return {"streams": streams, "p50_ms": p50, "p90_ms": ms[int(len(ms) * 0.9)],
-            "stream_frames_per_s": streams / (p50 * 1e-3)}
+    # state traffic per stream-frame = 4 * sum(C_out) * V * 4 B (read slot, write slot, read+write acc)
+    state_bytes = 4 * sum(cfg['rt-st-gcn']['out_ch']) * v * 4 * streams
+    out = {"streams": streams, "p50_ms": p50, "p90_ms": ms[int(len(ms) * 0.9)],
+           "stream_frames_per_s": streams / (p50 * 1e-3), "cuda_graph": bool(cuda_graph),
+           "state_gb_per_step": state_bytes / 1e9, "achieved_gbs": state_bytes / (p50 * 1e-3) / 1e9}
+    if hbm_gbs:
+        out["roofline"] = {"bound": "hbm", "achieved": out["achieved_gbs"], "peak": hbm_gbs, "unit": "GB/s",
+                           "frac": out["achieved_gbs"] / hbm_gbs}
+    return out
 
 
 def main():
@@ -301,8 +320,14 @@ def main():
         dom_flops = flops.get(dom, 0.0) * N                    # algorithmic FLOPs of that class per step
         i = pkg._lib.KERNEL_CLASSES.index(dom)
         ach = dom_flops / (cls_ms[i] * 1e-3) / 1e12
+        mma_per_product = {'bf16x3': 3, 'bf16': 1, 'fp32': 0}[args.math]
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk['bf16_tflops_sustained'],
-                    "unit": "TFLOP/s", "frac": ach / pk['bf16_tflops_sustained'], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / pk['bf16_tflops_sustained'], "traffic": ncu_traffic(dom),
+                    "mma_per_product": mma_per_product,
+                    "tensor_pipe_frac": (ach * mma_per_product / pk['bf16_tflops_sustained']) if mma_per_product else None,
+                    "note": "achieved = algorithmic FLOPs (SURVEY 8d) of this kernel class / its CUDA-event time; "
+                            "fp32-parity mode issues 3 bf16 MMAs per product, so the tensor pipe is busy "
+                            "tensor_pipe_frac of the measured peak",
                     "peak_source": pk['source'] + " bf16 sustained (kernel timed inside a long step)",
                     "launches": int(cls_n[i]), "avg_launch_ms": cls_ms[i] / max(cls_n[i], 1),
                     "share_of_step": cls_ms[i] / total if total else None,
@@ -313,8 +338,14 @@ def main():
     if rank == 0 and world == 1 and not args.no_rt:
         del x
         torch.cuda.empty_cache()
-        rt = {"pku_fp32": [rt_latency(pkg, dev, b, args.rt_steps, {}, args.math) for b in (1, args.rt_streams)]}
-        rt["note"] = "per-frame step for all streams, LayerNorm, fp32 FIFO state; p50 over %d steps" % args.rt_steps
+        imu = dict(graph='imu_fogit_ABCD', in_feat=6, num_classes=8)
+        rt = {"pku": [rt_latency(pkg, dev, b, args.rt_steps, {}, args.math, pk['hbm_gbs'])
+                      for b in (1, args.rt_streams)],
+              "imu_bf16": [rt_latency(pkg, dev, b, args.rt_steps, imu, 'bf16', pk['hbm_gbs'])
+                           for b in (1, args.rt_streams)]}
+        rt["note"] = ("BASELINE configs 2 and 5: one continual step for all streams (LayerNorm, fp32 FIFO/accumulator "
+                      "state, CUDA-graph replay), p50 over %d steps after a 20-step FIFO fill; pku math=%s, imu "
+                      "math=bf16 (stated tolerance 3e-2 rel., tests/test_gpu_parity.py)" % (args.rt_steps, args.math))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

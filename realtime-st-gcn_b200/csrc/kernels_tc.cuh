@@ -329,53 +329,34 @@ __device__ __forceinline__ void frame_stats(const float *sp, int fr, int V, floa
   rstd = 1.f / sqrtf(tq * (1.f / (float)(V * C - 1)) + eps);
 }
 
+// Second half of both epilogues: publish this thread's partial statistics, merge the frame's
+// partials, then normalise / add the residual / activate the accumulator rows (re-read from TMEM)
+// and write them out.  `add_bias`: the accumulator still lacks the bias (ST-GCN); the RT path has
+// already folded it into the stashed accumulator.
+// Pass 2 works in 32-column super-chunks through this warp's shared-memory patch [32 rows][144 B]:
+// the residual block is loaded and the output block stored COOPERATIVELY (8 lanes per row, whole
+// 128-B lines, 4 rows per instruction) instead of 32 different rows per instruction; in between
+// every lane touches only its own patch row.
 template <int C, int NH>
-__device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
-                                                 int w, bool row_ok, long long row, long long row_o,
-                                                 float *s_part, int tile_parity, int h, uint8_t *patch) {
-  if (e.debug & 1) return;
+__device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr, int w,
+                                           bool row_ok, long long row, long long row_o, float *s_part,
+                                           int tile_parity, int h, uint8_t *patch, float shift, float s1, float s2,
+                                           bool add_bias, bool relu_mid) {
   constexpr int CH = C / NH;
-  static_assert(CH % 32 == 0, "epilogue works in 32-column super-chunks");
   const int c0 = h * CH;
-  // float4 index of channel group g: table -> g*V + w, plain vector -> g
   const int pstep = e.bias_sw ? V : 1;
   const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
   float *sp = s_part + tile_parity * (2 * NH * 128);
   float v[16];
-  float shift = 0.f, s1 = 0.f, s2 = 0.f;
-  const bool tdbg = (e.debug & 4) && blockIdx.x == 0 && r == 0 && h == 0;
-  long long tq0 = tdbg ? clock64() : 0;
-#pragma unroll 1
-  for (int cb = 0; cb < CH; cb += 16) {
-    tmem_ld16(taddr + c0 + cb, v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
-      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-    }
-    if (cb == 0) shift = v[0];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float d = v[i] - shift;
-      s1 += d;
-      s2 = fmaf(d, d, s2);
-    }
-  }
   const float m_r = shift + s1 * (1.f / (float)CH);
   const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)CH), 0.f);
   sp[h * 128 + r] = row_ok ? m_r : 0.f;
   sp[(NH + h) * 128 + r] = row_ok ? M2_r : 0.f;
-  long long tq1 = tdbg ? clock64() : 0;
   asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
   float mean = 0.f, rstd = 0.f;
   if (r < RT && !(e.debug & 64)) frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
-  long long tq2 = tdbg ? clock64() : 0;
   const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT) + (c0 >> 2) * V + w;
   const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT) + (c0 >> 2) * V + w;
-  // Pass 2 works in 32-column super-chunks through this warp's shared-memory patch [32 rows][144 B]:
-  // the residual block is loaded and the output block stored COOPERATIVELY (8 lanes per row, whole
-  // 128-B lines, 4 rows per instruction) instead of 32 different rows per instruction; in between
-  // every lane touches only its own patch row.
   const int lane = threadIdx.x & 31;
   const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
   const long long row0 = __shfl_sync(0xffffffffu, row, 0);        // rows of a warp are contiguous
@@ -402,13 +383,18 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int pi = (cb >> 2) + i;
-          const float4 b4 = __ldg(bias4 + pi * pstep);
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (add_bias) b4 = __ldg(bias4 + pi * pstep);
           const float4 g4 = __ldg(nw4 + pi * V);
           const float4 o4 = __ldg(nb4 + pi * V);
           v[4 * i] = (v[4 * i] + b4.x - mean) * rstd * g4.x + o4.x;
           v[4 * i + 1] = (v[4 * i + 1] + b4.y - mean) * rstd * g4.y + o4.y;
           v[4 * i + 2] = (v[4 * i + 2] + b4.z - mean) * rstd * g4.z + o4.z;
           v[4 * i + 3] = (v[4 * i + 3] + b4.w - mean) * rstd * g4.w + o4.w;
+        }
+        if (relu_mid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (use_res) {
 #pragma unroll
@@ -473,12 +459,40 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
     }
     __syncwarp();
   }
-  if (tdbg) {
-    const long long tq3 = clock64();
-    atomicAdd(&g_dbg[12], (unsigned long long)(tq1 - tq0));
-    atomicAdd(&g_dbg[13], (unsigned long long)(tq2 - tq1));
-    atomicAdd(&g_dbg[14], (unsigned long long)(tq3 - tq2));
+}
+
+// ST-GCN epilogue: y = LN_{C,V}(acc + bias) * g + b [+ res] [relu].
+template <int C, int NH>
+__device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
+                                                 int w, bool row_ok, long long row, long long row_o,
+                                                 float *s_part, int tile_parity, int h, uint8_t *patch) {
+  if (e.debug & 1) return;
+  constexpr int CH = C / NH;
+  static_assert(CH % 32 == 0, "epilogue works in 32-column super-chunks");
+  const int c0 = h * CH;
+  // float4 index of channel group g: table -> g*V + w, plain vector -> g
+  const int pstep = e.bias_sw ? V : 1;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
+  float v[16];
+  float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < CH; cb += 16) {
+    tmem_ld16(taddr + c0 + cb, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
+      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+    }
+    if (cb == 0) shift = v[0];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d = v[i] - shift;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
+    }
   }
+  epi_finish<C, NH>(e, taddr, r, RT, V, fr, w, row_ok, row, row_o, s_part, tile_parity, h, patch, shift, s1, s2,
+                    true, false);
 }
 
 // RT-ST-GCN epilogue: the accumulator row holds z_t (graph-convolved frame, before bias).  Per
@@ -486,45 +500,57 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
 //   acc <- (acc + z_t) + (-fifo[slot]);  fifo[slot] <- z_t;  o = acc
 // then out = relu( relu(LN_{C,V}(o)) + res ) (res optional; rtstgcn.py:548-553).  The updated
 // accumulator row is stashed back into the TMEM columns it came from (tcgen05.st) so that the
-// LayerNorm statistics need no second trip to HBM.  `b` is the stream index of this row.
+// LayerNorm statistics need no second trip to HBM.  `b` is the stream index of this row; streams
+// may sit at different ring positions (independent resets), so slot indices travel by shuffle.
+// The FIFO slot and accumulator rows move through the warp's patch ([64 B fifo | 64 B acc] per
+// row and 16-column chunk) so that global loads and stores cover whole 64-B row segments.
 template <int C, int NH>
 __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
                                                  int w, bool row_ok, long long row, int b, float *s_part,
-                                                 int tile_parity, int h) {
+                                                 int tile_parity, int h, uint8_t *patch) {
   if (e.debug & 1) return;
   constexpr int CH = C / NH;
   const int c0 = h * CH;
   const int pstep = e.bias_sw ? V : 1;
   const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
-  float *sp = s_part + tile_parity * (2 * NH * 128);
   float v[16];
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
+  const int lane = threadIdx.x & 31;
   const int cnt = row_ok ? __ldg(e.rt_counter + b) : 0;
-  float4 *f4 = reinterpret_cast<float4 *>(e.rt_fifo + (long long)(cnt % e.rt_F) * e.rt_slot + row * C + c0);
-  float4 *a4 = reinterpret_cast<float4 *>(e.rt_acc + (long long)(cnt % e.rt_S) * e.rt_slot + row * C + c0);
+  const int my_fi = cnt % e.rt_F, my_ai = cnt % e.rt_S;
+  const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+  const long long row0 = __shfl_sync(0xffffffffu, row, 0);
+  uint8_t *mine = patch + lane * kPatchPitch;
 #pragma unroll 1
   for (int cb = 0; cb < CH; cb += 16) {
-    float4 fc[4], ac[4];
-    if (row_ok) {
+    // cooperative load: 4 lanes per row (64 B of FIFO slot, 64 B of accumulator), 8 rows per instruction
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        fc[i] = f4[(cb >> 2) + i];
-        ac[i] = a4[(cb >> 2) + i];
+    for (int i = 0; i < 4; ++i) {
+      const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
+      const int fi = __shfl_sync(0xffffffffu, my_fi, rr), ai = __shfl_sync(0xffffffffu, my_ai, rr);
+      if ((okmask >> rr) & 1) {
+        const long long off = (row0 + rr) * C + c0 + cb + qq * 4;
+        *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + qq * 16) =
+            *reinterpret_cast<const float4 *>(e.rt_fifo + (long long)fi * e.rt_slot + off);
+        *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + 64 + qq * 16) =
+            *reinterpret_cast<const float4 *>(e.rt_acc + (long long)ai * e.rt_slot + off);
       }
     }
+    __syncwarp();
     tmem_ld16(taddr + c0 + cb, v);
     if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
-        float4 z = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
-        float4 a = ac[i];
-        a.x = (a.x + z.x) + (-fc[i].x);
-        a.y = (a.y + z.y) + (-fc[i].y);
-        a.z = (a.z + z.z) + (-fc[i].z);
-        a.w = (a.w + z.w) + (-fc[i].w);
-        f4[(cb >> 2) + i] = z;
-        a4[(cb >> 2) + i] = a;
+        const float4 old = *reinterpret_cast<const float4 *>(mine + i * 16);
+        float4 a = *reinterpret_cast<const float4 *>(mine + 64 + i * 16);
+        const float4 z = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+        a.x = (a.x + z.x) + (-old.x);
+        a.y = (a.y + z.y) + (-old.y);
+        a.z = (a.z + z.z) + (-old.z);
+        a.w = (a.w + z.w) + (-old.w);
+        *reinterpret_cast<float4 *>(mine + i * 16) = z;
+        *reinterpret_cast<float4 *>(mine + 64 + i * 16) = a;
         v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
       }
     } else {
@@ -539,58 +565,23 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
       s2 = fmaf(d, d, s2);
     }
     tmem_st16(taddr + c0 + cb, v);
-  }
-  const float m_r = shift + s1 * (1.f / (float)CH);
-  const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)CH), 0.f);
-  sp[h * 128 + r] = row_ok ? m_r : 0.f;
-  sp[(NH + h) * 128 + r] = row_ok ? M2_r : 0.f;
-  const float4 *rs4 = (e.res && row_ok) ? reinterpret_cast<const float4 *>(e.res + row * C + c0) : nullptr;
-  float4 rn[4];
-  if (rs4) {
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rn[i] = rs4[i];
-  }
-  asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
-  float mean = 0.f, rstd = 0.f;
-  if (r < RT) frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
-  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT) + (c0 >> 2) * V + w;
-  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT) + (c0 >> 2) * V + w;
-#pragma unroll 1
-  for (int cb = 0; cb < CH; cb += 16) {
-    float4 rc[4];
-    if (rs4) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rc[i] = rn[i];
-      if (cb + 16 < CH) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rn[i] = rs4[((cb + 16) >> 2) + i];
+    for (int i = 0; i < 4; ++i) {
+      const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
+      const int fi = __shfl_sync(0xffffffffu, my_fi, rr), ai = __shfl_sync(0xffffffffu, my_ai, rr);
+      if ((okmask >> rr) & 1) {
+        const long long off = (row0 + rr) * C + c0 + cb + qq * 4;
+        *reinterpret_cast<float4 *>(e.rt_fifo + (long long)fi * e.rt_slot + off) =
+            *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + qq * 16);
+        *reinterpret_cast<float4 *>(e.rt_acc + (long long)ai * e.rt_slot + off) =
+            *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + 64 + qq * 16);
       }
     }
-    tmem_ld16(taddr + c0 + cb, v);
-    if (row_ok) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 g4 = __ldg(nw4 + ((cb >> 2) + i) * V);
-        const float4 o4 = __ldg(nb4 + ((cb >> 2) + i) * V);
-        v[4 * i] = fmaxf((v[4 * i] - mean) * rstd * g4.x + o4.x, 0.f);
-        v[4 * i + 1] = fmaxf((v[4 * i + 1] - mean) * rstd * g4.y + o4.y, 0.f);
-        v[4 * i + 2] = fmaxf((v[4 * i + 2] - mean) * rstd * g4.z + o4.z, 0.f);
-        v[4 * i + 3] = fmaxf((v[4 * i + 3] - mean) * rstd * g4.w + o4.w, 0.f);
-      }
-      if (rs4) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[4 * i] = fmaxf(v[4 * i] + rc[i].x, 0.f);
-          v[4 * i + 1] = fmaxf(v[4 * i + 1] + rc[i].y, 0.f);
-          v[4 * i + 2] = fmaxf(v[4 * i + 2] + rc[i].z, 0.f);
-          v[4 * i + 3] = fmaxf(v[4 * i + 3] + rc[i].w, 0.f);
-        }
-      }
-      float4 *dst = reinterpret_cast<float4 *>(e.out_f32 + row * C + c0 + cb);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    }
+    __syncwarp();
   }
+  epi_finish<C, NH>(e, taddr, r, RT, V, fr, w, row_ok, row, row, s_part, tile_parity, h, patch, shift, s1, s2,
+                    false, true);
 }
 
 // --------------------------------------------------------------------------- //
@@ -1217,7 +1208,8 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * CO);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
         if (kRt)
-          rt_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, t, s_part, par, h);
+          rt_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, t, s_part, par, h,
+                                       s_patch + (warp - 10) * kPatchBytes);
         else
         {
           const long long row_o =

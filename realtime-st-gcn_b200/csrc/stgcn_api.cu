@@ -30,11 +30,11 @@ int debug_dump(const char *what, int c, cudaStream_t st) {
   unsigned long long h[16];
   STGCN_CUDA_OK(cudaStreamSynchronize(st));
   STGCN_CUDA_OK(cudaMemcpyFromSymbol(h, tc::g_dbg, sizeof(h)));
-  static const char *names[15] = {"mma_wait_tmem", "mma_wait_A", "mma_wait_B", "mma_total", "xA_prod_wait",
+  static const char *names[12] = {"mma_wait_tmem", "mma_wait_A", "mma_wait_B", "mma_total", "xA_prod_wait",
                                   "B_prod_wait", "epi_wait_tmem", "epi_work", "xf_wait_x", "xf_wait_Aempty",
-                                  "xf_compute", "items", "epi_pass1", "epi_bar_stats", "epi_pass2"};
+                                  "xf_compute", "items"};
   fprintf(stderr, "[dbg] %s<%d>:", what, c);
-  for (int i = 0; i < 15; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
+  for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
   fprintf(stderr, "\n");
   memset(h, 0, sizeof(h));
   STGCN_CUDA_OK(cudaMemcpyToSymbol(tc::g_dbg, h, sizeof(h)));
@@ -488,6 +488,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       g.epi.n_wT = pp->n1T; g.epi.n_bT = pp->n1T + (size_t)d.c_out * V;
       g.epi.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
       g.epi.out_f32 = out;
+      g.epi.relu = 1;                       // relu(relu(LN(o)) + res); idempotent without a residual
       g.epi.eps = kEps;
       g.epi.debug = debug_mode();
       g.epi.rt_fifo = fifo; g.epi.rt_acc = acc; g.epi.rt_counter = counter;
@@ -497,6 +498,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       ProfScope ps(KC_FRAME, st);
       if (tc::launch_gcn_tc2(d.c_out, x, pp->wg16, g, 1, B, 1, st)) return 1;
       STGCN_LAUNCH_OK();
+      if (debug_dump("rt", d.c_out, st)) return 1;
     }
     ws.release(mark0);
     return 0;

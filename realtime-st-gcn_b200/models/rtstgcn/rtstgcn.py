@@ -41,7 +41,7 @@ class Model(nn.Module):
         A = torch.tensor(self.graph.A, dtype=torch.float32, device=rank, requires_grad=False)
         self.register_buffer('A', A)
         self.normalization = kwargs['normalization']
-        self.math = kwargs.get('math', 'fp32')
+        self.math = kwargs.get('math', 'bf16x3')
         self.num_classes = kwargs['num_classes']
         if self.normalization == 'LayerNorm':
             self.norm_in = LayerNorm([kwargs['in_feat'], 1, A.size(1)])

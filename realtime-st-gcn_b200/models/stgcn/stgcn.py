@@ -38,7 +38,7 @@ class Model(nn.Module):
 
         kernel_size = (conf['kernel'], kwargs['graph']['num_node'])
         self.normalization = kwargs['normalization']
-        self.math = kwargs.get('math', 'fp32')
+        self.math = kwargs.get('math', 'bf16x3')
         if self.normalization == 'LayerNorm':
             self.norm_in = LayerNorm([kwargs['in_feat'], 1, A.size(1)])
         else:
@@ -212,7 +212,7 @@ class StgcnLayer(nn.Module):
             d.nr_w, d.nr_b = self.residual[1].weight.data_ptr(), self.residual[1].bias.data_ptr()
 
     @torch.no_grad()
-    def forward(self, x, A, math='fp32'):
+    def forward(self, x, A, math='bf16x3'):
         n, c, t, v = x.shape
         x = x.contiguous()
         A = A.contiguous()
