@@ -79,7 +79,7 @@ typedef struct stgcn_model_desc {
   int32_t in_feat, num_joints, partitions, num_classes, num_layers;
   int32_t norm;          /* STGCN_NORM_* */
   int32_t math;          /* STGCN_MATH_* */
-  int32_t reserved;
+  int32_t reserved;      /* bit 0: do not use the few-streams cluster kernel in rtstgcn_step */
   const float *norm_in_w, *norm_in_b;
   const float *fcn_in_w, *fcn_in_b;
   const float *fcn_out_w, *fcn_out_b;

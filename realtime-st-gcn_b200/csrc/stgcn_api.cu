@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_rt_small.cuh"
 
 using namespace stgcn;
 
@@ -149,7 +150,7 @@ int check_layer(const stgcn_layer_desc &d) {
 // (stgcn_model_prepare) and every forward reuses them; the layer-level entry points build them
 // per call in the workspace.
 struct LayerPrep {
-  bool gcn = false, tcn = false, res = false;
+  bool gcn = false, tcn = false, res = false, csr = false;
   int *kw_ptr = nullptr;
   int2 *kw_va = nullptr;
   float *bzT = nullptr;
@@ -162,11 +163,14 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws) {
   LayerPrep P;
   const bool ln = d.norm == STGCN_NORM_LAYERNORM;
   P.gcn = ln && !d.a_per_sample && tc::gcn_tc_supported(d.c_in, d.c_out, V, K);
+  P.csr = !d.a_per_sample && K * V + 1 <= 1024;
   P.tcn = ln && !d.rt && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, 2);
   P.res = ln && d.residual == STGCN_RES_CONV && tc::gcn_tc_supported(d.c_in, d.c_out, V, 1);
-  if (P.gcn) {
+  if (P.csr) {
     P.kw_ptr = ws.take<int>((size_t)K * V + 1);
     P.kw_va = ws.take<int2>((size_t)K * V * V);
+  }
+  if (P.gcn) {
     P.bzT = ws.take<float>((size_t)d.c_out * V);
     P.wg16 = ws.take<__nv_bfloat16>((size_t)2 * K * d.c_out * d.c_in);
   }
@@ -183,10 +187,12 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws) {
 
 int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaStream_t st) {
   ProfScope ps(KC_MISC, st);
-  if (P.gcn) {
-    const long long nw = (long long)K * d.c_out * d.c_in;
+  if (P.csr) {
     tc::k_build_adj_csr_kw<<<1, 128, (K * V + 1) * sizeof(int), st>>>(d.a_eff, K, V, P.kw_ptr, P.kw_va);
     STGCN_LAUNCH_OK();
+  }
+  if (P.gcn) {
+    const long long nw = (long long)K * d.c_out * d.c_in;
     tc::k_bias_through_adj<<<cdiv((long long)d.c_out * V, 256), 256, 0, st>>>(d.a_eff, d.gcn_b, K, V, d.c_out,
                                                                               P.bzT);
     STGCN_LAUNCH_OK();
@@ -694,6 +700,25 @@ int rt_layout(const stgcn_model_desc &m, int B, RtLayout &L) {
   return 0;
 }
 
+// few streams: the whole step as one cluster kernel (kernels_rt_small.cuh)
+constexpr int kSmallBatchMax = 16;
+bool rt_small_supported(const stgcn_model_desc &m, int B) {
+  if (m.reserved & 1) return false;                      // caller opted out (tests of the batched path)
+  if (B > kSmallBatchMax || m.num_layers > rts::kMaxLayers || m.num_joints > 32) return false;
+  if (m.in_feat * m.num_joints > rts::kThreads || m.partitions * m.num_joints + 1 > 1024) return false;
+  int c_max = m.layers[0].c_in;
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    if (!d.rt || d.norm != STGCN_NORM_LAYERNORM || d.a_per_sample) return false;
+    if (d.c_out % rts::kNC || d.c_in % rts::kChunk) return false;
+    if (m.num_joints * (d.c_out / rts::kNC) > 4 * rts::kThreads) return false;
+    if ((m.partitions + 1) * (d.c_out / rts::kNC) > 128) return false;   // rows per CTA (register tile bound)
+    c_max = d.c_out > c_max ? d.c_out : c_max;
+    c_max = d.c_in > c_max ? d.c_in : c_max;
+  }
+  return rts::smem_floats(c_max, m.num_joints, m.partitions) * sizeof(float) <= 220 * 1024;
+}
+
 int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logits, int B, Bump &ws,
             cudaStream_t st) {
   const int V = m.num_joints, K = m.partitions;
@@ -701,6 +726,64 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
                 "continual inference needs LayerNorm (reference raises at models/utils/batchnorm.py:20)");
   RtLayout L;
   if (rt_layout(m, B, L)) return 1;
+  if (rt_small_supported(m, B)) {
+    const size_t mark = ws.mark();
+    rts::Params P{};
+    P.num_layers = m.num_layers; P.V = V; P.K = K; P.in_feat = m.in_feat; P.num_classes = m.num_classes; P.B = B;
+    P.eps = kEps;
+    P.x = x; P.logits = logits;
+    P.norm_in_w = m.norm_in_w; P.norm_in_b = m.norm_in_b;
+    P.fcn_in_w = m.fcn_in_w; P.fcn_in_b = m.fcn_in_b;
+    P.fcn_out_w = m.fcn_out_w; P.fcn_out_b = m.fcn_out_b;
+    char *sb = static_cast<char *>(state);
+    P.counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters);
+    Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
+    const bool have = use_prepared(m);
+    int c_max = m.layers[0].c_in;
+    for (int i = 0; i < m.num_layers; ++i) {
+      const stgcn_layer_desc &d = m.layers[i];
+      LayerPrep lp;
+      if (have) {
+        lp = prep_take(d, K, V, pb);
+      } else {
+        lp = prep_take(d, K, V, ws);
+        if (!ws.measuring()) {
+          STGCN_REQUIRE(!ws.overflow, "workspace too small (rt step operands)");
+          if (prep_run(d, K, V, lp, st)) return 1;
+        }
+      }
+      rts::Layer &R = P.layer[i];
+      R.c_in = d.c_in; R.c_out = d.c_out; R.F = d.stride * (d.kernel - 1) + 1; R.S = d.stride;
+      R.residual = d.residual;
+      R.gcn_w = d.gcn_w; R.gcn_b = d.gcn_b; R.n1_w = d.n1_w; R.n1_b = d.n1_b;
+      R.res_w = d.res_w; R.nr_w = d.nr_w; R.nr_b = d.nr_b;
+      R.kw_ptr = lp.kw_ptr; R.kw_va = lp.kw_va;
+      R.fifo = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.fifo[i]);
+      R.acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]);
+      c_max = d.c_out > c_max ? d.c_out : c_max;
+      c_max = d.c_in > c_max ? d.c_in : c_max;
+    }
+    P.c_max = c_max;
+    if (!ws.measuring()) {
+      const size_t smem = rts::smem_floats(c_max, V, K) * sizeof(float);
+      STGCN_CUDA_OK(cudaFuncSetAttribute(rts::k_rt_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ProfScope ps(KC_FRAME, st);
+      P.debug = debug_mode();
+      rts::k_rt_small<<<dim3(rts::kNC, B), rts::kThreads, smem, st>>>(P);
+      STGCN_LAUNCH_OK();
+      if (debug_mode() & 4) {
+        unsigned long long h[8];
+        STGCN_CUDA_OK(cudaStreamSynchronize(st));
+        STGCN_CUDA_OK(cudaMemcpyFromSymbol(h, rts::g_dbg, sizeof(h)));
+        fprintf(stderr, "[dbg] rt_small: input=%llu gemm(+preload)=%llu adj_state=%llu stats_barrier=%llu normalise=%llu tail=%llu issue=%llu wait=%llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        memset(h, 0, sizeof(h));
+        STGCN_CUDA_OK(cudaMemcpyToSymbol(rts::g_dbg, h, sizeof(h)));
+      }
+    }
+    ws.release(mark);
+    return 0;
+  }
   size_t max_act = (size_t)B * V * m.layers[0].c_in;
   for (int i = 0; i < m.num_layers; ++i) {
     size_t a = (size_t)B * V * m.layers[i].c_out;

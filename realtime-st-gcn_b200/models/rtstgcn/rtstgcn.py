@@ -61,6 +61,8 @@ class Model(nn.Module):
         self._state_streams = 0
         self._graph_on = False
         self._graph = None
+        # few streams (<= 16): run the whole step as ONE cluster kernel (csrc/kernels_rt_small.cuh)
+        self.small_batch_kernel = kwargs.get('small_batch_kernel', True)
 
     def _layer_kwargs(self, i, num_joints):
         c = self.conf
@@ -98,7 +100,7 @@ class Model(nn.Module):
     def _fingerprint(self):
         extra = tuple((l.aggregate.A.data_ptr(), l.aggregate.A._version) for l in self.st_gcn) \
             if self.is_online else ()
-        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + extra + (self.math,)
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + extra + (self.math, self.small_batch_kernel)
 
     def _descriptor(self):
         fp = self._fingerprint()
@@ -118,6 +120,7 @@ class Model(nn.Module):
         m.num_layers = len(self.st_gcn)
         m.norm = _lib.NORM_LAYERNORM if self.normalization == 'LayerNorm' else _lib.NORM_BATCHNORM
         m.math = _lib.MATH_NAMES[self.math]
+        m.reserved = 0 if self.small_batch_kernel else 1
         nin = self.norm_in if self.normalization == 'LayerNorm' else self.norm_in.norm
         m.norm_in_w, m.norm_in_b = nin.weight.data_ptr(), nin.bias.data_ptr()
         m.fcn_in_w, m.fcn_in_b = self.fcn_in.weight.data_ptr(), self.fcn_in.bias.data_ptr()

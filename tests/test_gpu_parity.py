@@ -348,12 +348,13 @@ def test_stgcn_model_c1_tensor_core(pkg, syn, cuda, math, tol):
 
 
 # ------------------------------------------------------------------ RT continual step on tensor cores
-def _rt_case(pkg, syn, cuda, tag, math):
+def _rt_case(pkg, syn, cuda, tag, math, small=False):
     a, _ = load_golden('rtstgcn_' + tag)
     kw = {} if tag == 'pku' else dict(graph='imu_fogit_ABCD', in_feat=6, num_classes=8)
     cfg = syn.arch_config('rt-st-gcn', **kw)
     sd = syn.synth_state_dict(pkg.RtStgcn(**cfg).state_dict(), int(a['seeds'][0]))
     cfg['math'] = math
+    cfg['small_batch_kernel'] = small
     m = pkg.RtStgcn(**cfg)
     m.load_state_dict(sd)
     m = m.to(cuda)
@@ -510,3 +511,45 @@ def test_tsplit_emulated_ranks(pkg, syn, cuda, world, total_frames, math, tol):
     ex = _LocalExchange(0, 1, pkg._lib.load().stgcn_model_halo_bytes(ctypes.byref(m._descriptor()[0]), 2), cuda, shared1)
     single = m.forward_tsplit(x.to(cuda), total_frames, ex)
     assert rel_err(single, m(x.to(cuda))) < 1e-6
+
+
+# ------------------------------------------------------------------ few-streams cluster kernel
+@pytest.mark.parametrize('tag', ['pku', 'imu'])
+def test_rt_small_batch_cluster_kernel(pkg, syn, cuda, tag):
+    """Latency path (<= 16 streams): the whole continual step in one thread-block-cluster kernel
+    (fp32 FMA, distributed-shared-memory exchange per layer) vs the reference's own loop."""
+    m, x, ref = _rt_case(pkg, syn, cuda, tag, 'bf16x3', small=True)
+    lib = pkg._lib.load()
+    m._descriptor()                                          # prepared operands are built once, up front
+    n0 = lib.stgcn_launch_count()
+    out = m(x)
+    assert lib.stgcn_launch_count() - n0 == 48               # ONE kernel per frame
+    assert rel_err(out, ref) < 1e-5, rel_err(out, ref)
+    # CUDA-graph replay, more streams than one, per-stream reset
+    m.enable_cuda_graph(True)
+    m.reset_streams()
+    assert torch.equal(m(x), out)
+    m.reset_streams(1, 1)
+    out2 = m(x[:, :, :7])
+    assert rel_err(out2[1], ref[1][:, :7]) < 1e-5
+    assert rel_err(out2[0], ref[0][:, :7]) > 1e-3            # stream 0 was not reset: it continues
+
+
+def test_rt_small_batch_matches_batched_path(pkg, syn, cuda):
+    """13 streams through the cluster kernel == the same streams through the tensor-core path."""
+    cfg = syn.arch_config('rt-st-gcn', num_classes=12, in_ch=[64, 64, 128], out_ch=[64, 128, 128], stride=[1, 2, 1],
+                          residual=[1, 1, 0])
+    sd = syn.synth_state_dict(pkg.RtStgcn(**cfg).state_dict(), 41)
+    x = syn.synth_input((13, 3, 20, 25), 42)
+    outs = []
+    for small in (True, False):
+        cfg['small_batch_kernel'] = small
+        m = pkg.RtStgcn(**cfg)
+        m.load_state_dict(sd)
+        m = m.to(cuda)
+        m.prepare_benchmark({})
+        outs.append(m(x.to(cuda)).cpu())
+    ref = O.rt_model_run(x, sd, dict(layers=3, stride=[1, 2, 1], residual=[1, 1, 0], importance=True, kernel=9,
+                                     out_ch=[64, 128, 128]))
+    assert rel_err(outs[0], ref) < 1e-5
+    assert rel_err(outs[1], ref) < TOL
