@@ -202,6 +202,17 @@ int rtstgcn_layer_step(const stgcn_layer_desc *d, int K, int V, int math, const 
                        float *y, void *layer_state, int32_t *frame_counter, int B,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- RT-ST-GCN training-time (whole-sequence) layer ------------------------------ */
+/* OfflineLayer.forward (rtstgcn.py:343-389, with the `self.toeplitz` -> `toeplitz` fix): graph
+ * convolution, causal sum of kernel/stride taps spaced `stride`, LayerNorm + ReLU, residual, ReLU.
+ * x (N,c_in,L,V) -> y (N,c_out,L,V); fp32 CUDA-core arithmetic.  d->rt must be 1 (bias-free,
+ * stride-free residual conv); d->a_eff = A * edge_importance. */
+size_t rtstgcn_offline_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int N, int L);
+int rtstgcn_offline_layer_forward(const stgcn_layer_desc *d, int K, int V, const float *x, float *y, int N,
+                                  int L, void *workspace, size_t workspace_bytes, void *stream);
+/* Mean over joints, x (N,C,L,V) -> y (N,C,L,1): nn.AvgPool2d((1,V)) of rtstgcn.py:127,149. */
+int stgcn_mean_joints_forward(const float *x, float *y, long long rows, int V, void *stream);
+
 /* ---- host-buffer entry points (processor.py:367,380 / :418 equivalents) ----- */
 /* x_host/logits_host are HOST buffers (pinned for async copies); device_io must
  * hold N*in_feat*T*V + N*num_classes floats.  H2D, forward, D2H on `stream`. */

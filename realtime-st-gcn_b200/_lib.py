@@ -76,6 +76,10 @@ SYMBOLS = {
     'rtstgcn_layer_workspace_bytes': (c_size_t, [_P_LAYER, c_int, c_int, c_int]),
     'rtstgcn_layer_step': (c_int, [_P_LAYER, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_void_p, c_size_t, c_void_p]),
+    'rtstgcn_offline_layer_workspace_bytes': (c_size_t, [_P_LAYER, c_int, c_int, c_int, c_int]),
+    'rtstgcn_offline_layer_forward': (c_int, [_P_LAYER, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                              c_void_p, c_size_t, c_void_p]),
+    'stgcn_mean_joints_forward': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     'stgcn_model_forward_host': (c_int, [_P_MODEL, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                          c_size_t, c_void_p]),
     'rtstgcn_step_host': (c_int, [_P_MODEL, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

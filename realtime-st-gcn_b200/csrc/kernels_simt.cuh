@@ -693,6 +693,35 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// RT-ST-GCN training-time temporal stage (rtstgcn.py:366-381): causal sum of `taps` frames spaced
+// `stride` apart, o[n,t,:] = sum_{j<taps} z[n, t - j*stride, :] (zero before the sequence start).
+// z, o are [N*T, VC] channels-last rows of one frame each.
+__global__ void k_causal_tap_sum(const float *__restrict__ z, float *__restrict__ o, long long N, int T, int VC,
+                                 int taps, int stride) {
+  const long long total = N * T * (long long)(VC / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % (VC / 4));
+    const long long f = i / (VC / 4);
+    const int t = (int)(f % T);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < taps && t - j * stride >= 0; ++j) {
+      const float4 v = *reinterpret_cast<const float4 *>(z + (f - (long long)j * stride) * VC + q * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4 *>(o + f * VC + q * 4) = s;
+  }
+}
+
+// mean over joints: x (N, C, L, V) -> y (N, C, L)   (nn.AvgPool2d((1, V)), rtstgcn.py:127,149)
+__global__ void k_mean_joints(const float *__restrict__ x, float *__restrict__ y, long long rows, int V) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  float s = 0.f;
+  for (int v = 0; v < V; ++v) s += x[i * V + v];
+  y[i] = s / (float)V;
+}
+
 __global__ void k_pool_sum(const float *__restrict__ part, int nchunk, int C, int N, float *__restrict__ sums) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * C) return;

@@ -366,12 +366,18 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
 #pragma unroll 1
   for (int sb = 0; sb < CH; sb += 32) {
     if (use_res) {
+      float4 tr[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
+        tr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((okmask >> rr) & 1)
-          *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + qq * 16) =
-              *reinterpret_cast<const float4 *>(e.res + (row0 + rr) * C + c0 + sb + qq * 4);
+          tr[i] = *reinterpret_cast<const float4 *>(e.res + (row0 + rr) * C + c0 + sb + qq * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
+        *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + qq * 16) = tr[i];
       }
       __syncwarp();
     }
@@ -524,17 +530,25 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
 #pragma unroll 1
   for (int cb = 0; cb < CH; cb += 16) {
     // cooperative load: 4 lanes per row (64 B of FIFO slot, 64 B of accumulator), 8 rows per instruction
+    // all eight 16-B loads are issued before the first one is consumed (one memory round trip)
+    float4 tf[4], ta[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
       const int fi = __shfl_sync(0xffffffffu, my_fi, rr), ai = __shfl_sync(0xffffffffu, my_ai, rr);
+      tf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ta[i] = tf[i];
       if ((okmask >> rr) & 1) {
         const long long off = (row0 + rr) * C + c0 + cb + qq * 4;
-        *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + qq * 16) =
-            *reinterpret_cast<const float4 *>(e.rt_fifo + (long long)fi * e.rt_slot + off);
-        *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + 64 + qq * 16) =
-            *reinterpret_cast<const float4 *>(e.rt_acc + (long long)ai * e.rt_slot + off);
+        tf[i] = *reinterpret_cast<const float4 *>(e.rt_fifo + (long long)fi * e.rt_slot + off);
+        ta[i] = *reinterpret_cast<const float4 *>(e.rt_acc + (long long)ai * e.rt_slot + off);
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
+      *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + qq * 16) = tf[i];
+      *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + 64 + qq * 16) = ta[i];
     }
     __syncwarp();
     tmem_ld16(taddr + c0 + cb, v);

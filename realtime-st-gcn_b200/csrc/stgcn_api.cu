@@ -1184,6 +1184,79 @@ int rtstgcn_layer_step(const stgcn_layer_desc *d, int K, int V, int math, const 
   return to_nctv(out, y, B, d->c_out, V, d->c_out, st);
 }
 
+// ---- RT-ST-GCN training-time layer (rtstgcn.py:343-389) ---------------------------------------
+namespace {
+int offline_layer(const stgcn_layer_desc &d, int K, int V, const float *x, float *y, int N, int L, Bump &ws,
+                  cudaStream_t st) {
+  if (check_layer(d)) return 1;
+  STGCN_REQUIRE(d.norm == STGCN_NORM_LAYERNORM, "offline layer: LayerNorm only on the B200 path");
+  const long long rows = (long long)N * L * V;
+  float *xin = ws.take<float>((size_t)rows * d.c_in);
+  float *yy = ws.take<float>((size_t)rows * K * d.c_out);
+  float *z = ws.take<float>((size_t)rows * d.c_out);
+  float *o = ws.take<float>((size_t)rows * d.c_out);
+  float *qr = d.residual == STGCN_RES_CONV ? yy : nullptr;          // reuses the 1x1 output buffer
+  float *out = ws.take<float>((size_t)rows * d.c_out);
+  AdjCsr csr;
+  if (build_csr(d.a_eff, 0, N, K, V, d.c_out, ws, csr, st)) return 1;
+  if (ws.measuring()) return 0;
+  STGCN_REQUIRE(!ws.overflow, "offline layer: workspace too small");
+  if (to_ntvc(x, xin, N, d.c_in, (long long)L * V, d.c_in, st)) return 1;
+  if (launch_gemm(xin, d.gcn_w, d.gcn_b, yy, N, L, V, d.c_in, K * d.c_out, 1, 1, st)) return 1;
+  FrameArgs a{};
+  a.producer = FRAME_ADJ;
+  a.frames = (long long)N * L;
+  a.frames_per_sample = L;
+  a.K = K; a.V = V; a.C = d.c_out;
+  a.y = yy;
+  a.adj_ptr = csr.ptr; a.adj_yoff = csr.yoff; a.adj_val = csr.val;
+  a.eps = kEps;
+  a.out = z;
+  if (launch_frame(a, st)) return 1;
+  const int taps = d.kernel / d.stride;                              // rtstgcn.py:369
+  k_causal_tap_sum<<<148 * 8, 256, 0, st>>>(z, o, N, L, V * d.c_out, taps, d.stride);
+  STGCN_LAUNCH_OK();
+  if (qr && launch_gemm(xin, d.res_w, nullptr, qr, N, L, V, d.c_in, d.c_out, 1, 1, st)) return 1;
+  FrameArgs f{};
+  f.producer = FRAME_LOAD;
+  f.frames = (long long)N * L;
+  f.frames_per_sample = L;
+  f.K = K; f.V = V; f.C = d.c_out;
+  f.a = o;
+  f.norm_a = 1; f.na_w = d.n1_w; f.na_b = d.n1_b;
+  f.relu_mid = 1;
+  if (d.residual == STGCN_RES_IDENTITY) { f.b_mode = B_RAW; f.b = xin; }
+  else if (d.residual == STGCN_RES_CONV) { f.b_mode = B_LN; f.b = qr; f.nb_w = d.nr_w; f.nb_b = d.nr_b; }
+  f.relu_out = 1;
+  f.eps = kEps;
+  f.out = out;
+  if (launch_frame(f, st)) return 1;
+  return to_nctv(out, y, N, d.c_out, (long long)L * V, d.c_out, st);
+}
+}  // namespace
+
+size_t rtstgcn_offline_layer_workspace_bytes(const stgcn_layer_desc *d, int K, int V, int N, int L) {
+  if (!d) return 0;
+  Bump ws(nullptr, 0);
+  offline_layer(*d, K, V, nullptr, nullptr, N, L, ws, nullptr);
+  return ws.peak;
+}
+
+int rtstgcn_offline_layer_forward(const stgcn_layer_desc *d, int K, int V, const float *x, float *y, int N, int L,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+  STGCN_REQUIRE(d && d->rt, "offline layer: descriptor must describe an RT-ST-GCN layer (rt == 1)");
+  STGCN_REQUIRE(workspace && x && y && N > 0 && L > 0, "offline layer: null argument or empty input");
+  Bump ws(workspace, workspace_bytes);
+  return offline_layer(*d, K, V, x, y, N, L, ws, as_stream(stream));
+}
+
+int stgcn_mean_joints_forward(const float *x, float *y, long long rows, int V, void *stream) {
+  STGCN_REQUIRE(x && y && rows > 0 && V > 0, "mean_joints: bad arguments");
+  k_mean_joints<<<cdiv(rows, 256), 256, 0, as_stream(stream)>>>(x, y, rows, V);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
 // ---- host-buffer entry points --------------------------------------------------------
 int stgcn_model_forward_host(const stgcn_model_desc *m, const float *x_host, float *logits_host, int N,
                              int T, void *device_io, void *workspace, size_t workspace_bytes,

@@ -210,10 +210,16 @@ class Model(nn.Module):
     @torch.no_grad()
     def forward(self, x):
         if not self.is_online:
-            raise NotImplementedError(
-                "the B200 path implements continual inference; call _swap_layers_for_inference() "
-                "(or prepare_benchmark) first -- the training-time OfflineLayer forward is provided "
-                "per layer (OfflineLayer.forward)")
+            # training-time definition on a whole sequence (rtstgcn.py:137-157 with OfflineLayers):
+            # (N, C, L, V) -> (N, classes, L); every stage is a C-ABI call
+            h = self.fcn_in(self.norm_in(x.contiguous()))
+            for layer in self.st_gcn:
+                h = layer(h, self.A)
+            n, c, l, v = h.shape
+            pooled = torch.empty((n, c, l, 1), device=h.device, dtype=torch.float32)
+            _lib.check(_lib.load().stgcn_mean_joints_forward(_lib.ptr(h), _lib.ptr(pooled), n * c * l, v,
+                                                             _lib.stream_ptr(h.device)))
+            return self.fcn_out(pooled).squeeze(-1)
         if x.shape[2] == 1:
             return self.step(x)
         # buffered realtime: feed the frames one by one (state carries across calls)
@@ -330,10 +336,23 @@ class OnlineLayer(_LayerBase):
 
 class OfflineLayer(_LayerBase):
     """[Training-time definition] whole-sequence layer (rtstgcn.py:220-389): causal sum of
-    ``kernel // stride`` taps spaced ``stride``.  Holds the trainable parameters; its
-    forward on the B200 path is not built yet."""
+    ``kernel // stride`` taps spaced ``stride`` (the reference builds an L x L band matrix per
+    call; here it is a windowed sum).  Holds the trainable parameters; ``forward`` is inference
+    of that definition (no autograd) through ``rtstgcn_offline_layer_forward``."""
     _importance_grad = True
 
+    @torch.no_grad()
     def forward(self, x, A):
-        raise NotImplementedError("OfflineLayer.forward (training-time band-matrix form) is not "
-                                  "part of the B200 inference path yet")
+        n, c, l, v = x.shape
+        x = x.contiguous()
+        a_eff = (A * self.edge_importance).contiguous()        # rtstgcn.py:364
+        dev = _lib.require_cuda(x, a_eff, self.conv.weight)
+        lib = _lib.load()
+        k = self.num_partitions
+        d = _lib.LayerDesc()
+        self._fill_desc(d, a_eff, rt=1)
+        ws = self._ws.get(lib.rtstgcn_offline_layer_workspace_bytes(ctypes.byref(d), k, v, n, l), dev)
+        y = torch.empty((n, self.out_channels, l, v), device=dev, dtype=torch.float32)
+        _lib.check(lib.rtstgcn_offline_layer_forward(ctypes.byref(d), k, v, _lib.ptr(x), _lib.ptr(y), n, l,
+                                                     _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        return y

@@ -553,3 +553,24 @@ def test_rt_small_batch_matches_batched_path(pkg, syn, cuda):
                                      out_ch=[64, 128, 128]))
     assert rel_err(outs[0], ref) < 1e-5
     assert rel_err(outs[1], ref) < TOL
+
+
+# ------------------------------------------------------------------ RT-ST-GCN training-time definition
+def test_rt_offline_model_and_layers(pkg, syn, cuda):
+    """rtstgcn.Model with OfflineLayers on a whole sequence (the definition trained weights refer
+    to; reference rtstgcn.py:137-157, 343-389) vs the reference's output."""
+    a, w = load_golden('rtstgcn_offline')
+    cfg = syn.arch_config('rt-st-gcn', num_classes=12, in_ch=[16, 16, 32], out_ch=[16, 32, 32], stride=[1, 2, 1],
+                          residual=[1, 1, 0])
+    m = pkg.RtStgcn(**cfg)
+    m.load_state_dict(w)
+    m = m.to(cuda).eval()
+    assert not m.is_online
+    x = a['x'].to(cuda)
+    logits = m(x)
+    assert logits.shape == (2, 12, 30)
+    assert rel_err(logits, a['logits']) < TOL
+    y1 = m.st_gcn[0](a['h'].to(cuda), m.A)
+    assert rel_err(y1, a['y1']) < 1e-5
+    y2 = m.st_gcn[1](a['y1'].to(cuda), m.A)
+    assert rel_err(y2, a['y2']) < 1e-5

@@ -211,9 +211,47 @@ def gen_rt_models():
              digest=np.array(syn.state_digest(sd)))
 
 
+def patched_offline_forward():
+    """The reference's OfflineLayer.forward references an undefined attribute (`self.toeplitz`,
+    rtstgcn.py:379; the local `toeplitz` is built at :368-374).  Harness-side one-token fix applied
+    to the source text at run time -- the reference file is not modified."""
+    import inspect
+    import textwrap
+    import models.rtstgcn.rtstgcn as R
+    src = textwrap.dedent(inspect.getsource(R.OfflineLayer.forward))
+    assert src.count('self.toeplitz') == 1
+    ns = {}
+    exec(compile(src.replace('self.toeplitz', 'toeplitz'), '<OfflineLayer.forward, fixed>', 'exec'), R.__dict__, ns)
+    return ns['forward']
+
+
+def gen_rt_offline():
+    """Training-time (whole-sequence) RT-ST-GCN: rtstgcn.Model with OfflineLayers (models/rtstgcn
+    rtstgcn.py:137-157, 343-389), stride-1 and stride-2 layers, conv residual and no residual."""
+    import models.rtstgcn.rtstgcn as R
+    R.OfflineLayer.forward = patched_offline_forward()
+    cfg = syn.arch_config('rt-st-gcn', num_classes=12, in_ch=[16, 16, 32], out_ch=[16, 32, 32], stride=[1, 2, 1],
+                          residual=[1, 1, 0])
+    m = RefRt(**cfg)
+    sd = syn.synth_state_dict(m.state_dict(), 71)
+    m.load_state_dict(sd)
+    m.eval()
+    x = syn.synth_input((2, 3, 30, 25), 72)
+    with torch.no_grad():
+        logits = m(x)
+        h = m.fcn_in(m.norm_in(x))
+        y1 = m.st_gcn[0](h, m.A)
+        y2 = m.st_gcn[1](y1, m.A)
+    save('rtstgcn_offline', x=x, logits=logits, h=h, y1=y1, y2=y2, **sd_arrays(sd))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'offline':
+        gen_rt_offline()
+        sys.exit(0)
     gen_graphs()
     gen_primitives()
     gen_layers()
     gen_stgcn_models()
     gen_rt_models()
+    gen_rt_offline()
