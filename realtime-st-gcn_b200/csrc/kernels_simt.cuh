@@ -674,6 +674,85 @@ __global__ void __launch_bounds__(256) k_embed(EmbedArgs p) {
   }
 }
 
+// Input stage, LayerNorm mode, one WARP per frame, reading the reference layout (N, C_in, T, V)
+// directly (no separate layout pass): V*C_in <= 128 values per frame live in registers, the
+// statistics are warp shuffles, and the C0 outputs of a joint are written as coalesced rows.
+struct EmbedWarpArgs {
+  const float *x;            // (N, C_in, T, V)
+  int N, T, V, C_in, C0;
+  const float *n_w, *n_b;    // (C_in, V)
+  float eps;
+  const float *W, *bias;     // (C0, C_in), (C0)
+  float *out;                // [N*T*V, C0]
+};
+
+__global__ void __launch_bounds__(256) k_embed_warp(EmbedWarpArgs p) {
+  extern __shared__ __align__(16) float s_buf[];
+  const int VCi = p.V * p.C_in;
+  float *sw = s_buf;                              // C0*C_in
+  float *sb = sw + p.C0 * p.C_in;                 // C0
+  float *sxn = sb + p.C0;                         // [8 warps][VCi]
+  for (int i = threadIdx.x; i < p.C0 * p.C_in; i += blockDim.x) sw[i] = p.W[i];
+  for (int i = threadIdx.x; i < p.C0; i += blockDim.x) sb[i] = p.bias[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *xn = sxn + warp * VCi;
+  const float inv_n = 1.f / (float)VCi, inv_nm1 = 1.f / (float)(VCi - 1);
+  const long long frames = (long long)p.N * p.T;
+  for (long long f = (long long)blockIdx.x * 8 + warp; f < frames; f += (long long)gridDim.x * 8) {
+    const long long n = f / p.T;
+    const int t = (int)(f - n * p.T);
+    float v[4];
+    int cidx[4], vidx[4];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = lane + 32 * q;                // i = c*V + vj (the reference layout of one frame)
+      v[q] = 0.f;
+      cidx[q] = i / p.V;
+      vidx[q] = i - cidx[q] * p.V;
+      if (i < VCi) {
+        v[q] = p.x[((n * p.C_in + cidx[q]) * p.T + t) * p.V + vidx[q]];
+        s += v[q];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_n;
+    float qd = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (lane + 32 * q < VCi) {
+        const float d = v[q] - mean;
+        qd = fmaf(d, d, qd);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qd += __shfl_xor_sync(0xffffffffu, qd, o);
+    const float rstd = 1.f / sqrtf(qd * inv_nm1 + p.eps);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = lane + 32 * q;
+      if (i < VCi) xn[vidx[q] * p.C_in + cidx[q]] = (v[q] - mean) * rstd * __ldg(p.n_w + i) + __ldg(p.n_b + i);
+    }
+    __syncwarp();
+    float *dst = p.out + f * (long long)p.V * p.C0;
+    const int C04 = p.C0 >> 2;                                 // C0 % 4 == 0 (checked by the caller)
+    for (int i = lane; i < p.V * C04; i += 32) {
+      const int vj = i / C04, co = (i - vj * C04) * 4;
+      float4 acc = make_float4(sb[co], sb[co + 1], sb[co + 2], sb[co + 3]);
+      for (int c = 0; c < p.C_in; ++c) {
+        const float xv = xn[vj * p.C_in + c];
+        acc.x = fmaf(sw[co * p.C_in + c], xv, acc.x);
+        acc.y = fmaf(sw[(co + 1) * p.C_in + c], xv, acc.y);
+        acc.z = fmaf(sw[(co + 2) * p.C_in + c], xv, acc.z);
+        acc.w = fmaf(sw[(co + 3) * p.C_in + c], xv, acc.w);
+      }
+      *reinterpret_cast<float4 *>(dst + vj * p.C0 + co) = acc;
+    }
+    __syncwarp();
+  }
+}
+
 // --------------------------------------------------------------------------- //
 // pooling + classifier (stgcn.py:92-95, rtstgcn.py:149-152)
 //   part[n][chunk][c] = sum over the chunk's rows;  logits = Wo * mean + bo

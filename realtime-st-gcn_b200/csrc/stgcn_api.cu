@@ -568,6 +568,22 @@ int pool_fc(const float *x, int N, long long R, int C, const float *W, const flo
 int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bump &ws, cudaStream_t st) {
   const int V = m.num_joints, Ci = m.in_feat, C0 = m.layers[0].c_in;
   const long long frames = (long long)N * T;
+  if (m.norm == STGCN_NORM_LAYERNORM && V * Ci <= 128 && C0 % 4 == 0) {
+    // one warp per frame, straight from the reference layout (no layout pass, no staging buffer)
+    if (ws.measuring()) return 0;
+    EmbedWarpArgs e{};
+    e.x = x; e.N = N; e.T = T; e.V = V; e.C_in = Ci; e.C0 = C0;
+    e.n_w = m.norm_in_w; e.n_b = m.norm_in_b; e.eps = kEps;
+    e.W = m.fcn_in_w; e.bias = m.fcn_in_b; e.out = h0;
+    const size_t smem = sizeof(float) * ((size_t)C0 * Ci + C0 + (size_t)8 * V * Ci);
+    STGCN_REQUIRE(smem <= 48 * 1024, "embed: input feature map too large");
+    long long blocks = (frames + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ProfScope ps(KC_EMBED, st);
+    k_embed_warp<<<(unsigned)blocks, 256, smem, st>>>(e);
+    STGCN_LAUNCH_OK();
+    return 0;
+  }
   const size_t mark = ws.mark();
   float *xin = ws.take<float>((size_t)frames * V * Ci);
   double *sums = m.norm == STGCN_NORM_BATCHNORM ? ws.take<double>((size_t)2 * V * Ci) : nullptr;

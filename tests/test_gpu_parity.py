@@ -574,3 +574,25 @@ def test_rt_offline_model_and_layers(pkg, syn, cuda):
     assert rel_err(y1, a['y1']) < 1e-5
     y2 = m.st_gcn[1](a['y1'].to(cuda), m.A)
     assert rel_err(y2, a['y2']) < 1e-5
+
+
+# ------------------------------------------------------------------ host harness (processor.py counterpart)
+def test_processor_benchmark_harness(pkg, syn, cuda, tmp_path):
+    """benchmark() = prepare_benchmark + frame loop + seconds-per-frame in the reference's
+    latency.csv schema (processor.py:395-427, 881-902, 977); predictions equal the plain loop and
+    the reference's continual output; top-1/top-5 follow utils/statistics.py."""
+    a, _ = load_golden('rtstgcn_pku')
+    cfg = syn.arch_config('rt-st-gcn')
+    sd = syn.synth_state_dict(pkg.RtStgcn(**cfg).state_dict(), int(a['seeds'][0]))
+    m = pkg.RtStgcn(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(cuda)
+    x = syn.synth_input((2, 3, 48, 25), int(a['seeds'][1])).to(cuda)
+    labels = a['logits'].argmax(1)                       # the reference's own top-1 as ground truth
+    res = pkg.processor.benchmark(m, x, labels, save_dir=str(tmp_path))
+    assert rel_err(res['predictions'], a['logits']) < TOL
+    assert res['tot'] == 96 and res['top1_cor'] >= 95 and res['top5_cor'] >= res['top1_cor']
+    assert 0 < res['latency'] < 0.01
+    rows = open(tmp_path / 'latency.csv').read().strip().split('\n')
+    assert rows[0] == ',latency_fp32,latency_int8' and rows[1].startswith('0,')
+    assert abs(float(rows[1].split(',')[1]) - res['latency']) < 1e-9
