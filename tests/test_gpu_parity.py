@@ -596,3 +596,28 @@ def test_processor_benchmark_harness(pkg, syn, cuda, tmp_path):
     rows = open(tmp_path / 'latency.csv').read().strip().split('\n')
     assert rows[0] == ',latency_fp32,latency_int8' and rows[1].startswith('0,')
     assert abs(float(rows[1].split(',')[1]) - res['latency']) < 1e-9
+
+
+# ------------------------------------------------------------------ other graphs / temporal kernels
+@pytest.mark.parametrize('graph,c,kernel,stride,t', [
+    ('openpose', 64, 9, 1, 23), ('coco', 128, 5, 2, 30), ('lara', 64, 3, 1, 11), ('hugadb', 128, 9, 1, 40),
+    ('ntu-edge', 64, 13, 1, 17), ('tp-vicon', 256, 9, 2, 21)])
+def test_stgcn_layer_tensor_core_other_graphs(pkg, cuda, graph, c, kernel, stride, t):
+    """Every skeleton under data/skeletons (6..24 joints: different frames-per-tile packing) and
+    temporal kernels other than 9, on the tensor-core path, vs the oracle."""
+    from importlib import import_module
+    from oracle import build_adjacency
+    Layer = import_module('realtime-st-gcn_b200.models.stgcn').StgcnLayer
+    g = pkg.skeletons.skeleton(graph)
+    v = g['num_node']
+    gen = torch.Generator().manual_seed(c + t + kernel)
+    A = torch.tensor(build_adjacency(**g), dtype=torch.float32) * (torch.rand(3, v, v, generator=gen) + 0.5)
+    layer = Layer(c, c, (kernel, v), 3, v, stride=stride, residual=True)
+    sd = pkg.synthetic.synth_state_dict(layer.state_dict(), 17)
+    layer.load_state_dict(sd)
+    x = torch.randn(2, c, t, v, generator=gen)
+    ref = O.stgcn_layer(x, A, sd, stride=stride, residual=True)
+    layer = layer.to(cuda).eval()
+    y3 = layer(x.to(cuda), A.to(cuda), math='bf16x3')
+    assert y3.shape == ref.shape
+    assert rel_err(y3, ref) < TOL, rel_err(y3, ref)
