@@ -302,7 +302,8 @@ constexpr int kEpiThreads = 128 * kEpiNH;
 constexpr int kPartBytes = 2 * 2 * kEpiNH * 128 * 4;
 constexpr int kPatchPitch = 144;                           // 128 B of data + 16 B: conflict-free own-row access
 constexpr int kPatchBytes = 32 * kPatchPitch;              // one epilogue warp's staging patch
-constexpr int kPatchTotal = 4 * kEpiNH * kPatchBytes;
+constexpr int kPatchTotal = 4 * kEpiNH * kPatchBytes;     // ST-GCN kernels: one patch per epilogue warp
+constexpr int kPatchTotalRt = 2 * kPatchTotal;            // RT kernel: two (cp.async double buffering)
 
 template <int C, int NH>
 __device__ __forceinline__ void frame_stats(const float *sp, int fr, int V, float eps, float &mean, float &rstd) {
@@ -526,31 +527,49 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
   const int my_fi = cnt % e.rt_F, my_ai = cnt % e.rt_S;
   const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
   const long long row0 = __shfl_sync(0xffffffffu, row, 0);
-  uint8_t *mine = patch + lane * kPatchPitch;
-#pragma unroll 1
-  for (int cb = 0; cb < CH; cb += 16) {
-    // cooperative load: 4 lanes per row (64 B of FIFO slot, 64 B of accumulator), 8 rows per instruction
-    // all eight 16-B loads are issued before the first one is consumed (one memory round trip)
-    float4 tf[4], ta[4];
+  // This lane's four cooperative pieces (row rr = pc >> 2, 16-B piece qq = pc & 3) of every chunk:
+  // slot indices of the piece's row (streams may sit at different ring positions) and addresses.
+  const float *gsrc_f[4], *gsrc_a[4];
+  uint32_t pdst[4];
+  bool pok[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
-      const int fi = __shfl_sync(0xffffffffu, my_fi, rr), ai = __shfl_sync(0xffffffffu, my_ai, rr);
-      tf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      ta[i] = tf[i];
-      if ((okmask >> rr) & 1) {
-        const long long off = (row0 + rr) * C + c0 + cb + qq * 4;
-        tf[i] = *reinterpret_cast<const float4 *>(e.rt_fifo + (long long)fi * e.rt_slot + off);
-        ta[i] = *reinterpret_cast<const float4 *>(e.rt_acc + (long long)ai * e.rt_slot + off);
+  for (int i = 0; i < 4; ++i) {
+    const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
+    const int fi = __shfl_sync(0xffffffffu, my_fi, rr), ai = __shfl_sync(0xffffffffu, my_ai, rr);
+    const long long off = (row0 + rr) * C + c0 + qq * 4;
+    gsrc_f[i] = e.rt_fifo + (long long)fi * e.rt_slot + off;
+    gsrc_a[i] = e.rt_acc + (long long)ai * e.rt_slot + off;
+    pdst[i] = (uint32_t)(rr * kPatchPitch + qq * 16);
+    pok[i] = (okmask >> rr) & 1;
+  }
+  // The FIFO slot / accumulator chunks stream global -> patch with cp.async, one chunk ahead
+  // (two patches per warp), so their latency overlaps the arithmetic and stores of the previous chunk.
+  auto issue = [&](int cb, int buf) {
+    const uint32_t pb = smem_u32(patch + buf * kPatchBytes);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (pok[i]) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pb + pdst[i]), "l"(gsrc_f[i] + cb) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pb + pdst[i] + 64), "l"(gsrc_a[i] + cb) : "memory");
       }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
-      *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + qq * 16) = tf[i];
-      *reinterpret_cast<float4 *>(patch + rr * kPatchPitch + 64 + qq * 16) = ta[i];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const bool tdbg = (e.debug & 4) && blockIdx.x == 0 && r == 0 && h == 0;
+  long long tA = 0, tB = 0, tC = 0, tl = tdbg ? clock64() : 0;
+  issue(0, 0);
+  int buf = 0;
+#pragma unroll 1
+  for (int cb = 0; cb < CH; cb += 16, buf ^= 1) {
+    if (cb + 16 < CH) {
+      issue(cb + 16, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncwarp();
+    if (tdbg) { const long long n_ = clock64(); tA += n_ - tl; tl = n_; }
+    uint8_t *pw = patch + buf * kPatchBytes;
+    uint8_t *mine = pw + lane * kPatchPitch;
     tmem_ld16(taddr + c0 + cb, v);
     if (row_ok) {
 #pragma unroll
@@ -580,22 +599,25 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
     }
     tmem_st16(taddr + c0 + cb, v);
     __syncwarp();
+    if (tdbg) { const long long n_ = clock64(); tB += n_ - tl; tl = n_; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
-      const int fi = __shfl_sync(0xffffffffu, my_fi, rr), ai = __shfl_sync(0xffffffffu, my_ai, rr);
-      if ((okmask >> rr) & 1) {
-        const long long off = (row0 + rr) * C + c0 + cb + qq * 4;
-        *reinterpret_cast<float4 *>(e.rt_fifo + (long long)fi * e.rt_slot + off) =
-            *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + qq * 16);
-        *reinterpret_cast<float4 *>(e.rt_acc + (long long)ai * e.rt_slot + off) =
-            *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + 64 + qq * 16);
+    for (int i = 0; i < 4; ++i)
+      if (pok[i]) {
+        *reinterpret_cast<float4 *>(const_cast<float *>(gsrc_f[i]) + cb) = *reinterpret_cast<const float4 *>(pw + pdst[i]);
+        *reinterpret_cast<float4 *>(const_cast<float *>(gsrc_a[i]) + cb) =
+            *reinterpret_cast<const float4 *>(pw + pdst[i] + 64);
       }
-    }
     __syncwarp();
+    if (tdbg) { const long long n_ = clock64(); tC += n_ - tl; tl = n_; }
+  }
+  if (tdbg) {
+    atomicAdd(&g_dbg[12], (unsigned long long)tA);
+    atomicAdd(&g_dbg[13], (unsigned long long)tB);
+    atomicAdd(&g_dbg[14], (unsigned long long)tC);
   }
   epi_finish<C, NH>(e, taddr, r, RT, V, fr, w, row_ok, row, row, s_part, tile_parity, h, patch, shift, s1, s2,
                     false, true);
+  if (tdbg) atomicAdd(&g_dbg[15], (unsigned long long)(clock64() - tl));
 }
 
 // --------------------------------------------------------------------------- //
@@ -935,7 +957,7 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
   const uint32_t sCsr = sB + S * kBBytes;
   const uint32_t sPart = sCsr + kGcn2Csr;
   const uint32_t sPatch = sPart + kPartBytes;
-  const uint32_t sBar = sPatch + kPatchTotal;
+  const uint32_t sBar = sPatch + (kRt ? kPatchTotalRt : kPatchTotal);
   const uint32_t bXsFull = sBar, bXsEmpty = sBar + 16, bTmemFull = sBar + 32, bTmemEmpty = sBar + 48;
   const uint32_t bAFull = sBar + 64, bAEmpty = sBar + 96;
   const uint32_t bFullB = sBar + 128, bEmptyB = bFullB + 8 * S;
@@ -1223,7 +1245,7 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
         if (kRt)
           rt_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, t, s_part, par, h,
-                                       s_patch + (warp - 10) * kPatchBytes);
+                                       s_patch + (warp - 10) * 2 * kPatchBytes);
         else
         {
           const long long row_o =
@@ -1333,14 +1355,16 @@ int launch_gcn_tc2_c(const float *x, const __nv_bfloat16 *wp, GcnTc2Params p, in
                      cudaStream_t st) {
   const int V = p.V, kMaxSmem = 232448;
   p.FT = 128 / V;
-  p.NT = CO >= 256 ? 1 : 2;                          // tiles per item; NT * CO * tb <= 512 TMEM columns
+  // tiles per item; NT * CO * tb <= 512 TMEM columns.  The RT step is HBM-bound, not weight-bound:
+  // single tiles leave shared memory for its double-buffered state patches.
+  p.NT = (CO >= 256 || p.epi.rt_fifo) ? 1 : 2;
   p.tb = 512 / (p.NT * CO) >= 2 ? 2 : 1;
   if (p.FT < 1) return fail("gcn tensor-core kernel: %d joints do not fit a 128-row tile", V);
   const int RT = p.FT * V;
   p.a_stage_bytes = ((p.NT * RT + 128 - RT) * 128 + 1023) & ~1023;
   p.xs_tx = p.NT * p.FT * V * 64 * 4;
   p.xs_alloc = 2 * ((p.NT * p.FT * V * 128 + 1023) & ~1023);   // two 32-channel swizzled sub-tiles
-  const int fixed = kGcn2Csr + kPartBytes + kPatchTotal + 512 + 1024;
+  const int fixed = kGcn2Csr + kPartBytes + (p.epi.rt_fifo ? kPatchTotalRt : kPatchTotal) + 512 + 1024;
   // prefer: double-buffered input tile, 3-deep A ring, >= 2 weight stages; back off as smem requires
   const int tries[4][2] = {{2, 3}, {2, 2}, {1, 3}, {1, 2}};
   int ok = 0;
