@@ -1418,6 +1418,19 @@ inline bool tcn_tc2_supported(int C, int V, int G, int stride, int T) {
 }
 
 // u planes: bf16 [planes][N][T][V][C] (T = input frames); wp: bf16 [2][G][C][C]; out/res rows over T_out
+// CTA-pair variant (kernels_tc_pair.cuh); STGCN_PAIR=0 selects the single-CTA kernel
+inline bool tcn_pair_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_PAIR");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
+template <int C>
+int launch_tcn_pair(const CUtensorMap &tm_u0, const CUtensorMap &tm_u1, const CUtensorMap &tm_wh,
+                    const TcnTc2Params &p, int grid, int smem, cudaStream_t st);
+
 // `halo`: the plane buffer holds `halo` extra frames before and after the T frames of every trial
 // (T-split: filled by the neighbouring ranks, or zeros at the sequence ends); output frame tau
 // still reads input frames stride*tau + j - pad of the T-frame sequence.
@@ -1502,6 +1515,23 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
   const uint64_t wst[3] = {(uint64_t)C * 2, (uint64_t)C * C * 2, (uint64_t)p.G * C * C * 2};
   const uint32_t wb[4] = {64, (uint32_t)C, 1, 1};
   if (make_tmap_bf16(&tm_w, wp, 4, wd, wst, wb)) return 1;
+  if (tcn_pair_enabled() && p.items >= 2) {
+    // CTA pairs (cta_group::2): every CTA stages only its half of each weight tile
+    const int kBHalf = (C / 2) * 128;
+    const int fixed_p = kPartBytes + kPatchTotal + 512 + 1024;
+    int S = (kMaxSmem - 2 * p.a_stage_bytes - fixed_p) / kBHalf;
+    if (S > 12) S = 12;
+    if (S >= 2) {
+      p.b_stages = S;
+      CUtensorMap tm_wh;
+      const uint32_t wbh[4] = {64, (uint32_t)(C / 2), 1, 1};
+      if (make_tmap_bf16(&tm_wh, wp, 4, wd, wst, wbh)) return 1;
+      const int smem_p = 2 * p.a_stage_bytes + S * kBHalf + fixed_p;
+      int pairs = (p.items + 1) / 2;
+      if (pairs > num_sms() / 2) pairs = num_sms() / 2;
+      return launch_tcn_pair<C>(tm_u0, tm_u1, tm_wh, p, 2 * pairs, smem_p, st);
+    }
+  }
   STGCN_CUDA_OK(cudaFuncSetAttribute(k_tcn_tc2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = p.items < num_sms() ? p.items : num_sms();
   k_tcn_tc2<C><<<grid, kTcn2Threads, smem, st>>>(tm_u0, tm_u1, tm_w, p);

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tc_pair.cuh"
 #include "kernels_rt_small.cuh"
 
 using namespace stgcn;
