@@ -353,9 +353,12 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)CH), 0.f);
   sp[h * 128 + r] = row_ok ? m_r : 0.f;
   sp[(NH + h) * 128 + r] = row_ok ? M2_r : 0.f;
+  const bool fdbg = add_bias && (e.debug & 4) && blockIdx.x == 0 && r == 0 && h == 0;
+  const long long tf0 = fdbg ? clock64() : 0;
   asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
   float mean = 0.f, rstd = 0.f;
   if (r < RT && !(e.debug & 64)) frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
+  const long long tf1 = fdbg ? clock64() : 0;
   const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT) + (c0 >> 2) * V + w;
   const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT) + (c0 >> 2) * V + w;
   const int lane = threadIdx.x & 31;
@@ -466,6 +469,10 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
     }
     __syncwarp();
   }
+  if (fdbg) {
+    atomicAdd(&g_dbg[13], (unsigned long long)(tf1 - tf0));
+    atomicAdd(&g_dbg[14], (unsigned long long)(clock64() - tf1));
+  }
 }
 
 // ST-GCN epilogue: y = LN_{C,V}(acc + bias) * g + b [+ res] [relu].
@@ -482,6 +489,8 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
   const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
   float v[16];
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
+  const bool pdbg = (e.debug & 4) && blockIdx.x == 0 && r == 0 && h == 0;
+  const long long tp0 = pdbg ? clock64() : 0;
 #pragma unroll 1
   for (int cb = 0; cb < CH; cb += 16) {
     tmem_ld16(taddr + c0 + cb, v);
@@ -498,6 +507,7 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
       s2 = fmaf(d, d, s2);
     }
   }
+  if (pdbg) atomicAdd(&g_dbg[12], (unsigned long long)(clock64() - tp0));
   epi_finish<C, NH>(e, taddr, r, RT, V, fr, w, row_ok, row, row_o, s_part, tile_parity, h, patch, shift, s1, s2,
                     true, false);
 }

@@ -37,7 +37,7 @@ int debug_dump(const char *what, int c, cudaStream_t st) {
                                   "xf_compute", "items"};
   fprintf(stderr, "[dbg] %s<%d>:", what, c);
   for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
-  fprintf(stderr, " rt_wait_state=%llu rt_update=%llu rt_store=%llu rt_finish=%llu", h[12], h[13], h[14], h[15]);
+  fprintf(stderr, " ph12(pass1|rt_wait)=%llu ph13(bar_stats|rt_update)=%llu ph14(pass2|rt_store)=%llu ph15(rt_finish)=%llu", h[12], h[13], h[14], h[15]);
   fprintf(stderr, "\n");
   memset(h, 0, sizeof(h));
   STGCN_CUDA_OK(cudaMemcpyToSymbol(tc::g_dbg, h, sizeof(h)));
