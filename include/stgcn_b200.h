@@ -154,6 +154,17 @@ int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits
                         float *features, int N, int T, void *workspace,
                         size_t workspace_bytes, void *stream);
 
+/* ---- sliding-window inference ------------------------------------------------------ */
+/* The reference's continual use of ST-GCN (WindowSegment, utils/segment_generator.py:109-154;
+ * processor.py:374-380): every frame is classified from the window of the W frames ending at it,
+ * windows are the batch.  captures (in_feat, L_pad, V) is ONE trial already padded with W-1 zero
+ * frames in front; window n covers frames [n, n+W).  The windows are read in place through
+ * overlapping strides -- the (n_windows, C, W, V) batch the reference materialises with
+ * unfold().contiguous() never exists.  logits (n_windows, num_classes).  LayerNorm only. */
+int stgcn_model_forward_windows(const stgcn_model_desc *m, const float *captures, float *logits,
+                                int n_windows, int W, int L_pad, void *workspace,
+                                size_t workspace_bytes, void *stream);
+
 /* ---- T-split: one long trial partitioned along time across ranks ----------------- */
 /* Every rank holds a contiguous chunk of T_local frames (a multiple of the trunk's total temporal
  * stride on every rank but the last).  All stages of a layer are frame-local except the Gamma x 1

@@ -64,6 +64,8 @@ SYMBOLS = {
     'stgcn_model_workspace_bytes': (c_size_t, [_P_MODEL, c_int, c_int]),
     'stgcn_model_forward': (c_int, [_P_MODEL, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                     c_size_t, c_void_p]),
+    'stgcn_model_forward_windows': (c_int, [_P_MODEL, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                            c_size_t, c_void_p]),
     'stgcn_model_halo_bytes': (c_size_t, [_P_MODEL, c_int]),
     'stgcn_model_tsplit_workspace_bytes': (c_size_t, [_P_MODEL, c_int, c_int]),
     'stgcn_model_forward_tsplit': (c_int, [_P_MODEL, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,

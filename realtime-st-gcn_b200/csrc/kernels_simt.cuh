@@ -678,7 +678,8 @@ __global__ void __launch_bounds__(256) k_embed(EmbedArgs p) {
 // directly (no separate layout pass): V*C_in <= 128 values per frame live in registers, the
 // statistics are warp shuffles, and the C0 outputs of a joint are written as coalesced rows.
 struct EmbedWarpArgs {
-  const float *x;            // (N, C_in, T, V)
+  const float *x;            // (N, C_in, T, V), or any view with element strides (sn, sc, st, 1)
+  long long sn, sc, st;      // strides of trial / channel / frame (sliding windows: sn = st = V)
   int N, T, V, C_in, C0;
   const float *n_w, *n_b;    // (C_in, V)
   float eps;
@@ -712,7 +713,7 @@ __global__ void __launch_bounds__(256) k_embed_warp(EmbedWarpArgs p) {
       cidx[q] = i / p.V;
       vidx[q] = i - cidx[q] * p.V;
       if (i < VCi) {
-        v[q] = p.x[((n * p.C_in + cidx[q]) * p.T + t) * p.V + vidx[q]];
+        v[q] = p.x[n * p.sn + cidx[q] * p.sc + t * p.st + vidx[q]];
         s += v[q];
       }
     }

@@ -567,7 +567,9 @@ int pool_fc(const float *x, int N, long long R, int C, const float *W, const flo
 }
 
 // input stage: x (N,C_in,T,V) -> h0 [N*T*V, C0]
-int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bump &ws, cudaStream_t st) {
+// xs: optional element strides (trial, channel, frame) of `x`; null = contiguous (N, C_in, T, V)
+int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bump &ws, cudaStream_t st,
+          const long long *xs = nullptr) {
   const int V = m.num_joints, Ci = m.in_feat, C0 = m.layers[0].c_in;
   const long long frames = (long long)N * T;
   if (m.norm == STGCN_NORM_LAYERNORM && V * Ci <= 128 && C0 % 4 == 0) {
@@ -575,6 +577,9 @@ int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bu
     if (ws.measuring()) return 0;
     EmbedWarpArgs e{};
     e.x = x; e.N = N; e.T = T; e.V = V; e.C_in = Ci; e.C0 = C0;
+    e.sn = xs ? xs[0] : (long long)Ci * T * V;
+    e.sc = xs ? xs[1] : (long long)T * V;
+    e.st = xs ? xs[2] : (long long)V;
     e.n_w = m.norm_in_w; e.n_b = m.norm_in_b; e.eps = kEps;
     e.W = m.fcn_in_w; e.bias = m.fcn_in_b; e.out = h0;
     const size_t smem = sizeof(float) * ((size_t)C0 * Ci + C0 + (size_t)8 * V * Ci);
@@ -586,6 +591,7 @@ int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bu
     STGCN_LAUNCH_OK();
     return 0;
   }
+  STGCN_REQUIRE(!xs, "strided (sliding-window) input needs the LayerNorm input stage");
   const size_t mark = ws.mark();
   float *xin = ws.take<float>((size_t)frames * V * Ci);
   double *sums = m.norm == STGCN_NORM_BATCHNORM ? ws.take<double>((size_t)2 * V * Ci) : nullptr;
@@ -639,7 +645,8 @@ size_t model_prepare_layout(const stgcn_model_desc &m, void *base, size_t cap, L
 
 // ST-GCN model on `n` trials (one chunk).  logits [n, classes]; features optional (NCTV).
 int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float *features, int n, int T,
-                Bump &ws, cudaStream_t st, const stgcn_halo_desc *halo = nullptr, float *pooled_sums = nullptr) {
+                Bump &ws, cudaStream_t st, const stgcn_halo_desc *halo = nullptr, float *pooled_sums = nullptr,
+                const long long *xs = nullptr) {
   const int V = m.num_joints, K = m.partitions;
   // ping-pong activation buffers sized for the largest layer interface
   size_t max_act = (size_t)n * T * V * m.layers[0].c_in;
@@ -650,7 +657,7 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     if (a > max_act) max_act = a;
   }
   float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
-  if (embed(m, x, buf[0], n, T, ws, st)) return 1;
+  if (embed(m, x, buf[0], n, T, ws, st, xs)) return 1;
   int cur = 0;
   t = T;
   Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
@@ -1081,6 +1088,30 @@ int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits
     Bump ws(workspace, workspace_bytes);
     if (model_chunk(*m, x + (size_t)n0 * m->in_feat * T * V, logits + (size_t)n0 * m->num_classes,
                     features ? features + (size_t)n0 * c_last * t_final * V : nullptr, n, T, ws, st))
+      return 1;
+  }
+  return 0;
+}
+
+// ---- sliding-window inference (utils/segment_generator.py:109-154, processor.py:374-380) ------------
+int stgcn_model_forward_windows(const stgcn_model_desc *m, const float *captures, float *logits, int n_windows,
+                                int W, int L_pad, void *workspace, size_t workspace_bytes, void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(captures && logits && workspace && n_windows > 0 && W > 0 && L_pad >= n_windows + W - 1,
+                "forward_windows: bad arguments (need L_pad >= n_windows + W - 1)");
+  STGCN_REQUIRE(m->norm == STGCN_NORM_LAYERNORM, "forward_windows: LayerNorm only (windows are independent trials)");
+  cudaStream_t st = as_stream(stream);
+  const int V = m->num_joints;
+  // window n = frames [n, n + W) of the padded capture: a (n_windows, C, W, V) VIEW, never materialised
+  const long long xs[3] = {(long long)V, (long long)L_pad * V, (long long)V};
+  int nc = default_chunk(*m, n_windows, W);
+  while (nc > 1 && model_chunk_bytes(*m, nc, W) > workspace_bytes) nc = (nc + 1) / 2;
+  STGCN_REQUIRE(model_chunk_bytes(*m, nc, W) <= workspace_bytes, "forward_windows: workspace too small");
+  for (int n0 = 0; n0 < n_windows; n0 += nc) {
+    const int n = n_windows - n0 < nc ? n_windows - n0 : nc;
+    Bump ws(workspace, workspace_bytes);
+    if (model_chunk(*m, captures + (size_t)n0 * V, logits + (size_t)n0 * m->num_classes, nullptr, n, W, ws, st,
+                    nullptr, nullptr, xs))
       return 1;
   }
   return 0;

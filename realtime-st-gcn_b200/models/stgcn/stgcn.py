@@ -123,6 +123,30 @@ class Model(nn.Module):
 
     # ------------------------------------------------------------------ #
     @torch.no_grad()
+    def forward_windows(self, captures, receptive_field):
+        """Sliding-window inference of one trial, the reference's continual use of ST-GCN
+        (``WindowSegment``, utils/segment_generator.py:109-154 + processor.py:374-384): frame i is
+        classified from the ``receptive_field`` frames ending at i (zeros before the start).
+        ``captures (1, in_feat, L, V)`` -> ``(1, num_classes, L)``.  The window batch is read in
+        place through overlapping strides instead of being materialised."""
+        n, c, length, v = captures.shape
+        if n != 1:
+            raise RuntimeError("forward_windows takes one trial at a time (like the reference's 'dir' datasets)")
+        if self.normalization != 'LayerNorm':
+            raise RuntimeError("forward_windows needs LayerNorm (windows must be independent trials)")
+        w = int(receptive_field)
+        padded = torch.nn.functional.pad(captures, (0, 0, w - 1, 0)).contiguous()   # pad_sequence: W-1 in front
+        dev = _lib.require_cuda(padded, self.A, self.fcn_in.weight)
+        lib = _lib.load()
+        m, _ = self._descriptor()
+        ws = self._ws.get(lib.stgcn_model_workspace_bytes(ctypes.byref(m), length, w), dev)
+        logits = torch.empty((length, self.num_classes), device=dev, dtype=torch.float32)
+        _lib.check(lib.stgcn_model_forward_windows(ctypes.byref(m), _lib.ptr(padded), _lib.ptr(logits), length, w,
+                                                   length + w - 1, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        return logits.t().unsqueeze(0)                     # mask_segment: (N', C', 1) -> (1, C', L)
+
+    # ------------------------------------------------------------------ #
+    @torch.no_grad()
     def forward_tsplit(self, x_local, total_frames, exchange):
         """T-split forward (BASELINE config 4): ``x_local (N, in_feat, T_local, V)`` is this rank's
         contiguous chunk of a ``total_frames``-frame trial (chunking: ``tsplit.chunk_bounds``);

@@ -621,3 +621,27 @@ def test_stgcn_layer_tensor_core_other_graphs(pkg, cuda, graph, c, kernel, strid
     y3 = layer(x.to(cuda), A.to(cuda), math='bf16x3')
     assert y3.shape == ref.shape
     assert rel_err(y3, ref) < TOL, rel_err(y3, ref)
+
+
+# ------------------------------------------------------------------ sliding-window inference
+def test_stgcn_sliding_windows(pkg, syn, cuda):
+    """WindowSegment semantics (utils/segment_generator.py:109-154): frame i classified from the W
+    frames ending at i, zeros before the start.  The in-place strided read equals the materialised
+    unfold() batch bit for bit, and matches the oracle on sampled windows."""
+    cfg = syn.arch_config('st-gcn', num_classes=12, in_ch=[64, 64, 128], out_ch=[64, 128, 128], stride=[1, 2, 1])
+    sd = syn.synth_state_dict(pkg.Stgcn(**cfg).state_dict(), 81)
+    m = pkg.Stgcn(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    L, W = 45, 16
+    cap = syn.synth_input((1, 3, L, 25), 82)
+    out = m.forward_windows(cap.to(cuda), W)
+    assert out.shape == (1, 12, L)
+    padded = torch.nn.functional.pad(cap, (0, 0, W - 1, 0))
+    windows = padded.unfold(2, W, 1).permute(0, 2, 1, 4, 3).contiguous().view(L, 3, W, 25)   # the reference's batch
+    ref_gpu = m(windows.to(cuda))                                     # (L, classes, 1)
+    assert torch.equal(out, ref_gpu.permute(2, 1, 0))
+    pick = [0, 1, 15, 16, 44]
+    ref = O.stgcn_model(windows[pick], sd, dict(layers=3, stride=[1, 2, 1], residual=[1, 1, 1],
+                                                normalization='LayerNorm'))
+    assert rel_err(out[0, :, pick].t().unsqueeze(-1), ref) < TOL
