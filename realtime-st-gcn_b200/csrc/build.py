@@ -32,7 +32,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+    extra = os.environ.get('STGCN_NVCC_EXTRA', '').split()     # e.g. -DSTGCN_G3_DEBUG (role cycle counters)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
           ['-o', LIB] + [os.path.join(HERE, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:

@@ -684,7 +684,8 @@ struct EmbedWarpArgs {
   const float *n_w, *n_b;    // (C_in, V)
   float eps;
   const float *W, *bias;     // (C0, C_in), (C0)
-  float *out;                // [N*T*V, C0]
+  float *out;                // [N*T*V, C0], or (out == null) bf16 hi/lo planes of the same rows
+  __nv_bfloat16 *out_hi, *out_lo;
 };
 
 __global__ void __launch_bounds__(256) k_embed_warp(EmbedWarpArgs p) {
@@ -736,7 +737,8 @@ __global__ void __launch_bounds__(256) k_embed_warp(EmbedWarpArgs p) {
       if (i < VCi) xn[vidx[q] * p.C_in + cidx[q]] = (v[q] - mean) * rstd * __ldg(p.n_w + i) + __ldg(p.n_b + i);
     }
     __syncwarp();
-    float *dst = p.out + f * (long long)p.V * p.C0;
+    const long long dst_o = f * (long long)p.V * p.C0;
+    float *dst = p.out + dst_o;
     const int C04 = p.C0 >> 2;                                 // C0 % 4 == 0 (checked by the caller)
     for (int i = lane; i < p.V * C04; i += 32) {
       const int vj = i / C04, co = (i - vj * C04) * 4;
@@ -748,7 +750,21 @@ __global__ void __launch_bounds__(256) k_embed_warp(EmbedWarpArgs p) {
         acc.z = fmaf(sw[(co + 2) * p.C_in + c], xv, acc.z);
         acc.w = fmaf(sw[(co + 3) * p.C_in + c], xv, acc.w);
       }
-      *reinterpret_cast<float4 *>(dst + vj * p.C0 + co) = acc;
+      if (p.out) {
+        *reinterpret_cast<float4 *>(dst + vj * p.C0 + co) = acc;
+      } else {
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(acc.x, acc.y), h23 = __floats2bfloat162_rn(acc.z, acc.w);
+        const long long o = dst_o + vj * p.C0 + co;
+        *reinterpret_cast<uint2 *>(p.out_hi + o) =
+            make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+        if (p.out_lo) {
+          const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+          const __nv_bfloat162 l01 = __floats2bfloat162_rn(acc.x - f01.x, acc.y - f01.y);
+          const __nv_bfloat162 l23 = __floats2bfloat162_rn(acc.z - f23.x, acc.w - f23.y);
+          *reinterpret_cast<uint2 *>(p.out_lo + o) =
+              make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+        }
+      }
     }
     __syncwarp();
   }

@@ -278,6 +278,7 @@ struct EpiParams {
   int bias_sw;
   const float *n_wT, *n_bT;      // LayerNorm affine in [C/4][V][4] (k_transpose_affine)
   const float *res;              // fp32 [rows][C] added after the norm, or null
+  const __nv_bfloat16 *res_hi, *res_lo;   // the same residual as bf16 hi/lo planes [rows][C] (res == null)
   float *out_f32;                // fp32 [rows][C] or null
   __nv_bfloat16 *out_hi, *out_lo;  // split-bf16 planes [rows][C] or null
   int out_T, out_t0;             // frames per trial of the plane buffer and frame offset of t = 0
@@ -369,10 +370,52 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   const long long row0 = __shfl_sync(0xffffffffu, row, 0);        // rows of a warp are contiguous
   const long long rowo0 = __shfl_sync(0xffffffffu, row_o, 0);
   uint8_t *mine = patch + lane * kPatchPitch;
-  const bool use_res = e.res != nullptr && !(e.debug & 8);
+  const bool use_res = (e.res != nullptr || e.res_hi != nullptr) && !(e.debug & 8);
+  const bool res_planes = e.res == nullptr;
 #pragma unroll 1
   for (int sb = 0; sb < CH; sb += 32) {
-    if (use_res) {
+    if (use_res && res_planes) {
+      // patch row, per 16-column half h: [hi: 32 B][lo: 32 B] at h * 64 (a half's output never
+      // overwrites the other half's unread residual, whatever the residual / output formats)
+      uint4 tr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
+        tr[i] = make_uint4(0u, 0u, 0u, 0u);
+        const __nv_bfloat16 *src = (qq < 4) ? e.res_hi : e.res_lo;
+        if (((okmask >> rr) & 1) && src)
+          tr[i] = *reinterpret_cast<const uint4 *>(src + (row0 + rr) * C + c0 + sb + (qq & 3) * 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7, q3 = qq & 3;
+        *reinterpret_cast<uint4 *>(patch + rr * kPatchPitch + (q3 >> 1) * 64 + (q3 & 1) * 16 + (qq < 4 ? 0 : 32)) = tr[i];
+      }
+      __syncwarp();
+      if (e.out_f32) {
+        // fp32 output reuses the patch row as 32 floats: turn this lane's own row into hi + lo first
+        uint4 h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          h[i] = *reinterpret_cast<const uint4 *>(mine + (i >> 1) * 64 + (i & 1) * 16);
+          l[i] = *reinterpret_cast<const uint4 *>(mine + (i >> 1) * 64 + 32 + (i & 1) * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t hw[4] = {h[i].x, h[i].y, h[i].z, h[i].w}, lw[4] = {l[i].x, l[i].y, l[i].z, l[i].w};
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&hw[j]));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&lw[j]));
+            o[2 * j] = a.x + b.x;
+            o[2 * j + 1] = a.y + b.y;
+          }
+          *reinterpret_cast<float4 *>(mine + i * 32) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4 *>(mine + i * 32 + 16) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    } else if (use_res) {
       float4 tr[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -409,7 +452,21 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (use_res) {
+        if (use_res && res_planes && !e.out_f32) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint4 h4 = *reinterpret_cast<const uint4 *>(mine + half * 64 + i * 16);
+            const uint4 l4 = *reinterpret_cast<const uint4 *>(mine + half * 64 + 32 + i * 16);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&hw[j]));
+              const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&lw[j]));
+              v[8 * i + 2 * j] += a.x + b.x;
+              v[8 * i + 2 * j + 1] += a.y + b.y;
+            }
+          }
+        } else if (use_res) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 r4 = *reinterpret_cast<const float4 *>(mine + half * 64 + i * 16);
@@ -436,11 +493,10 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
             hi[i] = *reinterpret_cast<uint32_t *>(&hh);
             lo[i] = *reinterpret_cast<uint32_t *>(&ll);
           }
-          // patch row: [hi of 32 columns: 64 B][lo of 32 columns: 64 B]
-          uint4 *ph = reinterpret_cast<uint4 *>(mine + half * 32);
+          uint4 *ph = reinterpret_cast<uint4 *>(mine + half * 64);
           ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          uint4 *pl = reinterpret_cast<uint4 *>(mine + 64 + half * 32);
+          uint4 *pl = reinterpret_cast<uint4 *>(mine + half * 64 + 32);
           pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
@@ -461,11 +517,12 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
         for (int i = 0; i < 4; ++i) {
           const int pc = i * 32 + lane, rr = pc >> 2, qq = pc & 3;
           if ((okmask >> rr) & 1) {
+            const uint8_t *src = patch + rr * kPatchPitch + (qq >> 1) * 64 + (qq & 1) * 16;
             *reinterpret_cast<uint4 *>(e.out_hi + (rowo0 + rr) * C + c0 + sb + qq * 8) =
-                *reinterpret_cast<const uint4 *>(patch + rr * kPatchPitch + qq * 16);
+                *reinterpret_cast<const uint4 *>(src);
             if (e.out_lo)
               *reinterpret_cast<uint4 *>(e.out_lo + (rowo0 + rr) * C + c0 + sb + qq * 8) =
-                  *reinterpret_cast<const uint4 *>(patch + rr * kPatchPitch + 64 + qq * 16);
+                  *reinterpret_cast<const uint4 *>(src + 32);
           }
         }
       }

@@ -62,10 +62,15 @@ __device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// NOTE: default (.acquire.cta) semantics on purpose.  With .acquire.cluster every successful wait
+// is followed by CCTL.IVALL -- an invalidation of the whole L1 -- issued from the MMA warp's wait
+// loop; ncu showed it wiping the epilogue's parameter tables (L1 hit rate 45-60 %).  The waiter
+// (MMA issuer) consumes only async-proxy data (TMA -> shared memory, tcgen05 -> TMEM), ordered by
+// the barrier completion itself and tcgen05.fence, as in CUTLASS's ClusterBarrier::wait.
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -284,6 +289,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
                                                             h * (C / kEpiNH));
 #pragma unroll
             for (int o = 0; o < (C / kEpiNH) * 4; o += 128) prefetch_l2(rp + o);
+          }
+        }
+      } else if (valid && p.epi.res_hi && r < RT) {
+        for (int m = 0; m < p.NT; ++m) {
+          const int t = f0 + m * p.FT + fr;
+          if (t < p.T_out) {
+            const long long ro = (((long long)n * p.T_out + t) * p.V + w) * C + h * (C / kEpiNH);
+            const char *rh = reinterpret_cast<const char *>(p.epi.res_hi + ro);
+            const char *rl = reinterpret_cast<const char *>(p.epi.res_lo ? p.epi.res_lo + ro : p.epi.res_hi + ro);
+#pragma unroll
+            for (int o = 0; o < (C / kEpiNH) * 2; o += 128) {
+              prefetch_l2(rh + o);
+              prefetch_l2(rl + o);
+            }
           }
         }
       }

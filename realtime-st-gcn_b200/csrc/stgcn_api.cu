@@ -7,6 +7,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc_pair.cuh"
+#include "kernels_gcn3.cuh"
 #include "kernels_rt_small.cuh"
 
 using namespace stgcn;
@@ -37,6 +38,8 @@ int debug_dump(const char *what, int c, cudaStream_t st) {
                                   "xf_compute", "items"};
   fprintf(stderr, "[dbg] %s<%d>:", what, c);
   for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
+  if (!strcmp(what, "gcn3"))
+    fprintf(stderr, " [gcn3: 6 epi_wait_tmem 7 barA 8 phase1 9 barB 10 gather 12 stats 13 normalise+store]");
   fprintf(stderr, " ph12(pass1|rt_wait)=%llu ph13(bar_stats|rt_update)=%llu ph14(pass2|rt_store)=%llu ph15(rt_finish)=%llu", h[12], h[13], h[14], h[15]);
   fprintf(stderr, "\n");
   memset(h, 0, sizeof(h));
@@ -159,6 +162,11 @@ struct LayerPrep {
   __nv_bfloat16 *wg16 = nullptr, *wp16 = nullptr, *wr16 = nullptr;
   float *zero = nullptr;  // c_out zeros: bias of the bias-free RT residual conv (rtstgcn.py:503)
   float *n1T = nullptr, *n2T = nullptr, *nrT = nullptr;  // LayerNorm affine (V, C): weight then bias
+  // graph-conv v3 (kernels_gcn3.cuh): gather tables, weight tiles, [V][C] parameter tables
+  bool g3 = false, g3r = false;
+  tc::Gcn3Tables *tab = nullptr, *tabr = nullptr;
+  __nv_bfloat16 *wg3 = nullptr, *wr3 = nullptr;
+  float *bzR = nullptr, *n1R = nullptr, *nrR = nullptr;
 };
 
 LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws) {
@@ -184,6 +192,20 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws) {
   }
   if (P.gcn) P.n1T = ws.take<float>((size_t)2 * d.c_out * V);
   if (P.tcn) P.n2T = ws.take<float>((size_t)2 * d.c_out * V);
+  P.g3 = P.gcn && tc::gcn3_enabled() && tc::gcn3_supported(d.c_in, d.c_out, V, K) &&
+         (d.residual != STGCN_RES_CONV || (P.res && tc::gcn3_supported(d.c_in, d.c_out, V, 1)));
+  P.g3r = P.g3 && d.residual == STGCN_RES_CONV;
+  if (P.g3) {
+    P.tab = ws.take<tc::Gcn3Tables>(1);
+    P.wg3 = ws.take<__nv_bfloat16>((size_t)2 * K * d.c_out * d.c_in);
+    P.bzR = ws.take<float>((size_t)d.c_out * V);
+    P.n1R = ws.take<float>((size_t)2 * d.c_out * V);
+  }
+  if (P.g3r) {
+    P.tabr = ws.take<tc::Gcn3Tables>(1);
+    P.wr3 = ws.take<__nv_bfloat16>((size_t)2 * d.c_out * d.c_in);
+    P.nrR = ws.take<float>((size_t)2 * d.c_out * V);
+  }
   return P;
 }
 
@@ -212,6 +234,31 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
     STGCN_LAUNCH_OK();
     STGCN_CUDA_OK(cudaMemsetAsync(P.zero, 0, sizeof(float) * d.c_out, st));
   }
+  if (P.g3) {
+    const long long nw = (long long)K * d.c_out * d.c_in;
+    const int cvn = d.c_out * V;
+    tc::k_gcn3_tables<<<1, 32, 0, st>>>(d.a_eff, K, V, 0, P.tab);
+    STGCN_LAUNCH_OK();
+    tc::k_pack_gcn3_w<<<cdiv(nw, 256), 256, 0, st>>>(d.gcn_w, P.wg3, d.c_out, d.c_in, K);
+    STGCN_LAUNCH_OK();
+    tc::k_bias_through_adj_vc<<<cdiv(cvn, 256), 256, 0, st>>>(d.a_eff, d.gcn_b, K, V, d.c_out, P.bzR);
+    STGCN_LAUNCH_OK();
+    tc::k_transpose_cv<<<cdiv(cvn, 256), 256, 0, st>>>(d.n1_w, P.n1R, d.c_out, V);
+    STGCN_LAUNCH_OK();
+    tc::k_transpose_cv<<<cdiv(cvn, 256), 256, 0, st>>>(d.n1_b, P.n1R + cvn, d.c_out, V);
+    STGCN_LAUNCH_OK();
+    if (P.g3r) {
+      const long long nwr = (long long)d.c_out * d.c_in;
+      tc::k_gcn3_tables<<<1, 32, 0, st>>>(nullptr, 1, V, 1, P.tabr);
+      STGCN_LAUNCH_OK();
+      tc::k_pack_gcn3_w<<<cdiv(nwr, 256), 256, 0, st>>>(d.res_w, P.wr3, d.c_out, d.c_in, 1);
+      STGCN_LAUNCH_OK();
+      tc::k_transpose_cv<<<cdiv(cvn, 256), 256, 0, st>>>(d.nr_w, P.nrR, d.c_out, V);
+      STGCN_LAUNCH_OK();
+      tc::k_transpose_cv<<<cdiv(cvn, 256), 256, 0, st>>>(d.nr_b, P.nrR + cvn, d.c_out, V);
+      STGCN_LAUNCH_OK();
+    }
+  }
   const int cv = d.c_out * V;
   const float *src[3][2] = {{d.n1_w, d.n1_b}, {d.n2_w, d.n2_b}, {d.nr_w, d.nr_b}};
   float *dst[3] = {P.n1T, P.n2T, P.nrT};
@@ -229,9 +276,12 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
 // `pp`: prepared operands (model path) or null (built here, per call).
 constexpr int kHalo = 4;   // halo frames carried on each side of the temporal-conv input in T-split mode
 
+// x_planes / out_planes: the buffer holds bf16 hi/lo planes [plane][rows][C] (one plane in bf16
+// mode) instead of fp32 rows -- the inter-layer format of the graph-conv v3 path.
 int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        int N, int T, Bump &ws, cudaStream_t st, const LayerPrep *pp = nullptr,
-                       const stgcn_halo_desc *halo = nullptr, int layer_index = 0) {
+                       const stgcn_halo_desc *halo = nullptr, int layer_index = 0, bool x_planes = false,
+                       bool out_planes = false) {
   if (check_layer(d)) return 1;
   const size_t mark = ws.mark();
   const int T_out = (T - 1) / d.stride + 1;
@@ -252,6 +302,26 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
   // tensor-core graph-convolution stage: LayerNorm, shared adjacency, C_in % 64 == 0
   const bool tc_gcn = math != STGCN_MATH_FP32 && pp && pp->gcn;
+  // graph-conv v3: reference operation order on CTA pairs, input as bf16 planes
+  const bool use_g3 = tc_gcn && tc_tcn && pp->g3;
+  STGCN_REQUIRE(use_g3 || (!x_planes && !out_planes), "bf16-plane activations need the graph-conv v3 path");
+  const __nv_bfloat16 *xh = nullptr, *xl = nullptr;
+  if (use_g3) {
+    if (x_planes) {
+      xh = reinterpret_cast<const __nv_bfloat16 *>(x);
+    } else {
+      __nv_bfloat16 *sc = ws.take<__nv_bfloat16>((size_t)planes * rows * d.c_in);
+      if (!ws.measuring()) {
+        STGCN_REQUIRE(!ws.overflow, "workspace too small (layer input planes)");
+        const long long tot = rows * d.c_in;
+        ProfScope ps(KC_LAYOUT, st);
+        tc::k_rows_to_planes<<<cdiv(tot, 256), 256, 0, st>>>(x, sc, planes == 2 ? sc + tot : nullptr, tot);
+        STGCN_LAUNCH_OK();
+      }
+      xh = sc;
+    }
+    xl = (planes == 2 && xh) ? xh + (size_t)rows * d.c_in : nullptr;
+  }
 
   const int hf = halo ? kHalo : 0;                          // halo frames per side
   if (halo) {
@@ -264,7 +334,25 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   __nv_bfloat16 *u16 = tc_tcn ? ws.take<__nv_bfloat16>((size_t)planes * rows_u * d.c_out) : nullptr;
   __nv_bfloat16 *u16_lo = (tc_tcn && planes == 2 && u16) ? u16 + (size_t)rows_u * d.c_out : nullptr;
   double *sums = bn ? ws.take<double>((size_t)4 * d.c_out) : nullptr;
-  if (tc_gcn) {
+  if (use_g3) {
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
+      tc::Gcn3Params g{};
+      g.T = T; g.V = V; g.Cin = d.c_in; g.planes = planes;
+      g.tab = pp->tab;
+      g.bias = pp->bzR; g.bias_v = 1;
+      g.n_w = pp->n1R; g.n_b = pp->n1R + (size_t)d.c_out * V;
+      g.out_hi = u16; g.out_lo = u16_lo;
+      if (hf) { g.out_T = T + 2 * hf; g.out_t0 = hf; }
+      g.relu = 1;
+      g.eps = kEps;
+      g.debug = debug_mode();
+      ProfScope ps(KC_GEMM_1X1, st);
+      if (tc::launch_gcn3(d.c_out, K, xh, pp->wg3, g, N, T, 1, st)) return 1;
+      STGCN_LAUNCH_OK();
+      if (debug_dump("gcn3", d.c_out, st)) return 1;
+    }
+  } else if (tc_gcn) {
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
       tc::GcnTc2Params g{};
@@ -328,7 +416,20 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     float *qr = (res_conv && !res_tc) ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
-      if (res_tc) {
+      if (res_tc && use_g3) {
+        tc::Gcn3Params g{};
+        g.T = T_out; g.V = V; g.Cin = d.c_in; g.planes = planes;
+        g.tab = pp->tabr;
+        g.bias = d.res_b; g.bias_v = 0;
+        g.n_w = pp->nrR; g.n_b = pp->nrR + (size_t)d.c_out * V;
+        g.out_f32 = resb;
+        g.relu = 0;
+        g.eps = kEps;
+        g.debug = debug_mode();
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcn3(d.c_out, 1, xh, pp->wr3, g, N, T, d.stride, st)) return 1;
+        STGCN_LAUNCH_OK();
+      } else if (res_tc) {
         tc::GcnTc2Params g{};
         g.T_out = T_out; g.V = V; g.K = 1; g.Cin = d.c_in; g.planes = planes;
         g.identity = 1;
@@ -387,8 +488,17 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       p.planes = planes;
       p.epi.bias = d.tcn_b; p.epi.bias_sw = 0;
       p.epi.n_wT = pp->n2T; p.epi.n_bT = pp->n2T + (size_t)d.c_out * V;
-      p.epi.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
-      p.epi.out_f32 = out;
+      if (d.residual == STGCN_RES_IDENTITY && use_g3) {
+        p.epi.res_hi = xh; p.epi.res_lo = xl;            // the layer input as planes (hi + lo = x to 2^-17)
+      } else {
+        p.epi.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
+      }
+      if (out_planes) {
+        p.epi.out_hi = reinterpret_cast<__nv_bfloat16 *>(out);
+        p.epi.out_lo = planes == 2 ? p.epi.out_hi + (size_t)rows_out * d.c_out : nullptr;
+      } else {
+        p.epi.out_f32 = out;
+      }
       p.epi.relu = 1;
       p.epi.eps = kEps;
       p.epi.debug = debug_mode();
@@ -452,7 +562,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
 // x [B*V, c_in] -> out [B*V, c_out]; fifo [F][B][V][C], acc [S][B][V][C]; counter[B].
 int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st,
-                       const LayerPrep *pp = nullptr) {
+                       const LayerPrep *pp = nullptr, bool x_planes = false, bool out_planes = false) {
   if (check_layer(d)) return 1;
   STGCN_REQUIRE(d.norm == STGCN_NORM_LAYERNORM,
                 "continual inference needs LayerNorm: batch statistics of a single frame are undefined "
@@ -466,6 +576,72 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       if (prep_run(d, K, V, local, st)) return 1;
     }
     pp = &local;
+  }
+  const bool use_g3 = math != STGCN_MATH_FP32 && pp && pp->g3;
+  STGCN_REQUIRE(use_g3 || (!x_planes && !out_planes), "bf16-plane activations need the graph-conv v3 path");
+  if (use_g3) {
+    // ---- graph-conv v3 step (kernels_gcn3.cuh): streams are the frames of one trial ----
+    const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
+    const long long rows = (long long)B * V;
+    float *resb = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows * d.c_out) : nullptr;
+    const __nv_bfloat16 *xh = reinterpret_cast<const __nv_bfloat16 *>(x);
+    if (!x_planes) {
+      __nv_bfloat16 *sc = ws.take<__nv_bfloat16>((size_t)planes * rows * d.c_in);
+      if (!ws.measuring()) {
+        STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer input planes)");
+        const long long tot = rows * d.c_in;
+        ProfScope ps(KC_LAYOUT, st);
+        tc::k_rows_to_planes<<<cdiv(tot, 256), 256, 0, st>>>(x, sc, planes == 2 ? sc + tot : nullptr, tot);
+        STGCN_LAUNCH_OK();
+      }
+      xh = sc;
+    }
+    const __nv_bfloat16 *xl = (planes == 2 && xh) ? xh + (size_t)rows * d.c_in : nullptr;
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer)");
+      if (resb) {
+        // residual branch LN_R(conv1x1(x)): no bias, no stride (rtstgcn.py:503)
+        tc::Gcn3Params g{};
+        g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes;
+        g.tab = pp->tabr;
+        g.n_w = pp->nrR; g.n_b = pp->nrR + (size_t)d.c_out * V;
+        g.out_f32 = resb;
+        g.eps = kEps;
+        g.debug = debug_mode();
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcn3(d.c_out, 1, xh, pp->wr3, g, 1, B, 1, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      tc::Gcn3Params g{};
+      g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes;
+      g.tab = pp->tab;
+      g.bias = pp->bzR; g.bias_v = 1;
+      g.n_w = pp->n1R; g.n_b = pp->n1R + (size_t)d.c_out * V;
+      if (d.residual == STGCN_RES_IDENTITY) {
+        if (x_planes) { g.res_hi = xh; g.res_lo = xl; }
+        else g.res_f32 = x;
+      } else {
+        g.res_f32 = resb;
+      }
+      if (out_planes) {
+        g.out_hi = reinterpret_cast<__nv_bfloat16 *>(out);
+        g.out_lo = planes == 2 ? g.out_hi + (size_t)rows * d.c_out : nullptr;
+      } else {
+        g.out_f32 = out;
+      }
+      g.relu = 1;                             // relu(relu(LN(o)) + res); idempotent without a residual
+      g.eps = kEps;
+      g.debug = debug_mode();
+      g.rt_fifo = fifo; g.rt_acc = acc; g.rt_counter = counter;
+      g.rt_F = d.stride * (d.kernel - 1) + 1;
+      g.rt_S = d.stride;
+      g.rt_slot = rows * d.c_out;
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_gcn3(d.c_out, K, xh, pp->wg3, g, 1, B, 1, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    ws.release(mark0);
+    return 0;
   }
   if (math != STGCN_MATH_FP32 && pp && pp->gcn && (d.residual != STGCN_RES_CONV || pp->res)) {
     // ---- tensor-core step: the B streams form one "trial" of B frames (rows (b, w)) ----
@@ -568,11 +744,16 @@ int pool_fc(const float *x, int N, long long R, int C, const float *W, const flo
 
 // input stage: x (N,C_in,T,V) -> h0 [N*T*V, C0]
 // xs: optional element strides (trial, channel, frame) of `x`; null = contiguous (N, C_in, T, V)
+inline bool embed_warp_path(const stgcn_model_desc &m) {
+  return m.norm == STGCN_NORM_LAYERNORM && m.num_joints * m.in_feat <= 128 && m.layers[0].c_in % 4 == 0;
+}
+// out_planes: 0 = fp32 rows, 1 / 2 = bf16 hi (/ lo) planes in the same buffer (warp path only)
 int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bump &ws, cudaStream_t st,
-          const long long *xs = nullptr) {
+          const long long *xs = nullptr, int out_planes = 0) {
   const int V = m.num_joints, Ci = m.in_feat, C0 = m.layers[0].c_in;
   const long long frames = (long long)N * T;
-  if (m.norm == STGCN_NORM_LAYERNORM && V * Ci <= 128 && C0 % 4 == 0) {
+  STGCN_REQUIRE(!out_planes || embed_warp_path(m), "embed: bf16-plane output needs the LayerNorm input stage");
+  if (embed_warp_path(m)) {
     // one warp per frame, straight from the reference layout (no layout pass, no staging buffer)
     if (ws.measuring()) return 0;
     EmbedWarpArgs e{};
@@ -582,6 +763,11 @@ int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bu
     e.st = xs ? xs[2] : (long long)V;
     e.n_w = m.norm_in_w; e.n_b = m.norm_in_b; e.eps = kEps;
     e.W = m.fcn_in_w; e.bias = m.fcn_in_b; e.out = h0;
+    if (out_planes) {
+      e.out = nullptr;
+      e.out_hi = reinterpret_cast<__nv_bfloat16 *>(h0);
+      e.out_lo = out_planes == 2 ? e.out_hi + (size_t)frames * V * C0 : nullptr;
+    }
     const size_t smem = sizeof(float) * ((size_t)C0 * Ci + C0 + (size_t)8 * V * Ci);
     STGCN_REQUIRE(smem <= 48 * 1024, "embed: input feature map too large");
     long long blocks = (frames + 7) / 8;
@@ -657,19 +843,39 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     if (a > max_act) max_act = a;
   }
   float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
-  if (embed(m, x, buf[0], n, T, ws, st, xs)) return 1;
+  // which layers run the graph-conv v3 path (bf16-plane input); a producer writes planes when its
+  // consumer wants them and it can (warp input stage / tensor-core temporal epilogue)
+  const bool have = use_prepared(m);
+  const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
+  bool g3[65] = {false};
+  STGCN_REQUIRE(m.num_layers <= 64, "too many layers");
+  {
+    Bump pm(nullptr, 0);
+    int tt = T;
+    for (int i = 0; i < m.num_layers; ++i) {
+      const stgcn_layer_desc &d = m.layers[i];
+      const LayerPrep P = prep_take(d, K, V, pm);
+      g3[i] = m.math != STGCN_MATH_FP32 && P.g3 && P.tcn && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, tt);
+      tt = (tt - 1) / d.stride + 1;
+    }
+  }
+  const bool in0_planes = g3[0] && embed_warp_path(m);
+  if (embed(m, x, buf[0], n, T, ws, st, xs, in0_planes ? planes : 0)) return 1;
   int cur = 0;
   t = T;
   Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
+  bool x_planes = in0_planes;
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
     STGCN_REQUIRE(!d.rt, "stgcn_model_forward needs ST-GCN layers (rt == 0)");
     STGCN_REQUIRE(!d.a_per_sample, "per-sample adjacency is only supported by the layer-level API");
     LayerPrep P;
-    const bool have = use_prepared(m);
     if (have) P = prep_take(d, K, V, pb);
-    if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st, have ? &P : nullptr, halo, i))
+    const bool out_planes = g3[i] && g3[i + 1];
+    if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st, have ? &P : nullptr, halo, i,
+                           x_planes, out_planes))
       return 1;
+    x_planes = out_planes;
     t = (t - 1) / d.stride + 1;
     cur ^= 1;
   }
@@ -815,22 +1021,32 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     if (a > max_act) max_act = a;
   }
   float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
-  if (embed(m, x, buf[0], B, 1, ws, st)) return 1;
+  const bool have = use_prepared(m);
+  const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
+  bool g3[65] = {false};
+  {
+    Bump pm(nullptr, 0);
+    for (int i = 0; i < m.num_layers; ++i) g3[i] = m.math != STGCN_MATH_FP32 && prep_take(m.layers[i], K, V, pm).g3;
+  }
+  const bool in0_planes = g3[0] && embed_warp_path(m);
+  if (embed(m, x, buf[0], B, 1, ws, st, nullptr, in0_planes ? planes : 0)) return 1;
   char *sb = static_cast<char *>(state);
   int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters);
   int cur = 0;
   Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
+  bool x_planes = in0_planes;
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
     STGCN_REQUIRE(d.rt, "rtstgcn_step needs online layers (rt == 1)");
     float *fifo = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.fifo[i]);
     float *acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]);
     LayerPrep P;
-    const bool have = use_prepared(m);
     if (have) P = prep_take(d, K, V, pb);
+    const bool out_planes = g3[i] && g3[i + 1];
     if (rt_layer_step_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], fifo, acc, counter, B, ws, st,
-                           have ? &P : nullptr))
+                           have ? &P : nullptr, x_planes, out_planes))
       return 1;
+    x_planes = out_planes;
     cur ^= 1;
   }
   const int c_last = m.layers[m.num_layers - 1].c_out;
