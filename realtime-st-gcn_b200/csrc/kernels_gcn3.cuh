@@ -14,19 +14,22 @@
 //   warp 0   lane 0: TMA producer of the activation chunks ([128 rows][64 ch] bf16 per plane, ring of 8)
 //            lane 1: TMA producer of this CTA's half of every weight tile
 //   warp 1   MMA issuer (leader CTA only); accumulators double buffered in TMEM (2 x K*64 columns)
-//   warps 2..11 epilogue.  Per 32-channel pass: (1) warps 2..9 copy the pass's K*32 accumulator
-//            columns TMEM -> shared memory (thread = row); (2) all ten warps contract over the
-//            adjacency: a warp pair owns one frame, a quarter-warp one output row (8 lanes x float4
-//            = 32 channels, conflict-free 128-B reads), results stay in registers for all passes.
-//            After the last pass the frame statistics are merged by shuffles (+ one 64-thread named
-//            barrier), and the normalised rows are written as 64/128-B row segments.
+//   warps 2..21 epilogue (20 warps: the CUDA-core work is latency-bound, so it is spread over as
+//            many warps as the register file allows).  Per 32-channel pass: (1) warps 2..17 copy the
+//            pass's K*32 accumulator columns TMEM -> shared memory (thread = row); (2) all twenty
+//            warps contract over the adjacency: four warps own one frame, a quarter-warp one output
+//            row (8 lanes x float4 = 32 channels, conflict-free 128-B reads), results stay in
+//            registers for all passes.  After the last pass the frame statistics are merged by
+//            shuffles (+ one 128-thread named barrier), and the normalised rows are written as
+//            64/128-B row segments.
 #pragma once
 #include "kernels_tc_pair.cuh"
 
 namespace stgcn {
 namespace tc {
 
-constexpr int kG3EpiWarps = 10;
+constexpr int kG3EpiWarps = 20;
+constexpr int kG3LdWarps = 16;          // epilogue warps that read TMEM (four per lane quarter)
 constexpr int kG3EpiThreads = 32 * kG3EpiWarps;
 constexpr int kG3Threads = 32 * (2 + kG3EpiWarps);
 constexpr int kG3R = 8;                 // activation chunk ring slots
@@ -38,11 +41,11 @@ constexpr int kG3EntCap = 3 * kG3MaxV * kG3MaxV;
 
 // Per-layer gather tables, built on the device from A_eff (K, V, V):
 //   entries of output joint w: ent[row_ptr[w] .. row_ptr[w+1]) = (v | k << 8, A[k,v,w])
-//   rowmap[(warp-in-pair*4 + slot)*4 + quarter-warp] = output joint handled there (or -1); joints
+//   rowmap[(warp-in-frame*2 + slot)*4 + quarter-warp] = output joint handled there (or -1); joints
 //   are dealt in order of decreasing entry count so the four rows of one warp instruction have
-//   similar trip counts.
-//   ent2[((warp-in-pair*4 + slot)*kG3Steps + step)*4 + quarter-warp]: the step-th entry of the row at
-//   that position, padded with (0, 0.f); cm[warp-in-pair*4 + slot] = steps needed there (<= kG3Steps).
+//   similar trip counts, heavy and light groups paired per warp.
+//   ent2[((warp-in-frame*2 + slot)*kG3Steps + step)*4 + quarter-warp]: the step-th entry of the row at
+//   that position, padded with (0, 0.f); cm[warp-in-frame*2 + slot] = steps needed there (<= kG3Steps).
 struct Gcn3Tables {
   int row_ptr[kG3MaxV + 1];
   int rowmap[32];
@@ -85,8 +88,9 @@ __global__ void k_gcn3_tables(const float *__restrict__ A, int K, int V, int ide
     }
     for (int i = 0; i < 32; ++i) tab->rowmap[i] = -1;
     for (int i = 0; i < V; ++i) {
-      const int g = i >> 2, qw = i & 3;       // group g = 2*slot + warp-in-pair
-      tab->rowmap[((g & 1) * 4 + (g >> 1)) * 4 + qw] = order[i];
+      const int g = i >> 2, qw = i & 3;       // group g (four joints) -> warp g / 7-g of the frame, slot 0 / 1
+      const int pos = g < 4 ? g * 2 : (7 - g) * 2 + 1;
+      tab->rowmap[pos * 4 + qw] = order[i];
     }
   }
   __syncthreads();
@@ -102,7 +106,7 @@ __global__ void k_gcn3_tables(const float *__restrict__ A, int K, int V, int ide
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kG3MaxEnt; i += blockDim.x) {
-    const int qw = i & 3, step = (i >> 2) % kG3Steps, pos = (i >> 2) / kG3Steps;   // pos = warp-in-pair*4 + slot
+    const int qw = i & 3, step = (i >> 2) % kG3Steps, pos = (i >> 2) / kG3Steps;   // pos = warp-in-frame*2 + slot
     const int j = tab->rowmap[pos * 4 + qw];
     int2 en = make_int2(0, 0);
     if (j >= 0 && step < tab->row_ptr[j + 1] - tab->row_ptr[j]) en = tab->ent[tab->row_ptr[j] + step];
@@ -204,6 +208,11 @@ __device__ __forceinline__ void st_stream(float4 *p, const float4 &v) {
 __device__ __forceinline__ void st_stream(uint2 *p, const uint2 &v) {
   asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t *r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -223,14 +232,6 @@ struct Gcn3Params {
   int relu;
   float eps;
   int debug;
-  // residual added after the norm (RT step): fp32 rows or bf16 planes, same row indexing as out_f32
-  const float *res_f32;
-  const __nv_bfloat16 *res_hi, *res_lo;
-  // RT-ST-GCN continual step (rtstgcn.py:611-625): fifo [F][rows][CO], acc [S][rows][CO], counter[stream]
-  float *rt_fifo, *rt_acc;
-  const int *rt_counter;
-  int rt_F, rt_S;
-  long long rt_slot;
 };
 
 // exact merge of two (count, mean, M2) partial statistics (Chan et al.)
@@ -243,7 +244,7 @@ __device__ __forceinline__ void stat_merge(float &n, float &m, float &M2, float 
   n = nn;
 }
 
-template <int CO, int K, bool kRt>
+template <int CO, int K>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
     k_gcn3(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Gcn3Params p) {
   constexpr int NB = CO / 64;               // 64-channel blocks
@@ -262,7 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
   const uint32_t sY = sW + S * kWHalf;
   const uint32_t sEnt = sY + kYBytes;
   const uint32_t sMisc = sEnt + kG3MaxEnt * 8;
-  const uint32_t sBar = sMisc + 512;
+  const uint32_t sBar = sMisc + 768;
   const uint32_t bXFull = sBar, bXEmpty = sBar + 8 * R, bTFull = sBar + 16 * R, bTEmpty = bTFull + 16;
   const uint32_t bWFull = bTEmpty + 16, bWEmpty = bWFull + 8 * S;
   const uint32_t sTmemPtr = bWEmpty + 8 * S;
@@ -271,7 +272,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
   int2 *s_ent = reinterpret_cast<int2 *>(gen_base + (sEnt - smem_base));
   int *s_rowptr = reinterpret_cast<int *>(gen_base + (sMisc - smem_base));          // [33]
   int *s_rowmap = s_rowptr + 36;                                                     // [32]
-  float *s_stat = reinterpret_cast<float *>(s_rowmap + 32);                          // [5 frames][2 warps][4]
+  float *s_stat = reinterpret_cast<float *>(s_rowmap + 32);                          // [5 frames][4 warps][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -295,7 +296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bTFull + 8 * i, 1);
-      mbar_init(bTEmpty + 8 * i, 2 * 8);              // the eight TMEM-reading warps of BOTH CTAs
+      mbar_init(bTEmpty + 8 * i, 2 * kG3LdWarps);     // the TMEM-reading warps of BOTH CTAs
     }
     for (int i = 0; i < S; ++i) {
       mbar_init(bWFull + 8 * i, 2);
@@ -428,34 +429,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
     }
   } else {
     // ---- epilogue ----
-    const int e = warp - 2;                          // 0..9
-    const int f = e >> 1, wp = e & 1;                // frame of the tile / warp within the frame's pair
+    const int e = warp - 2;                          // 0..19
+    const int f = e >> 2, wq = e & 3;                // frame of the tile / warp within the frame's four
     const int qw = lane >> 3, l8 = lane & 7;
-    const int q = warp & 3, hh = e >> 2;             // TMEM lane quarter / column half (warps 2..9)
-    int jw[4], cm[4];
-    int nvalid = 0, cmax = 0;
+    const int q = warp & 3, hh = e >> 2;             // TMEM lane quarter / column share (warps 2..17)
+    int jw[2], cm[2];
+    int nvalid = 0;
     bool overflow = false;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      jw[i] = s_rowmap[(wp * 4 + i) * 4 + qw];
-      cm[i] = __ldg(&p.tab->cm[wp * 4 + i]);         // warp-uniform step count of this slot
-      cmax = max(cmax, cm[i]);
+    for (int i = 0; i < 2; ++i) {
+      jw[i] = s_rowmap[(wq * 2 + i) * 4 + qw];
+      cm[i] = __ldg(&p.tab->cm[wq * 2 + i]);         // warp-uniform step count of this slot
       if (jw[i] >= 0) {
         ++nvalid;
         overflow |= s_rowptr[jw[i] + 1] - s_rowptr[jw[i]] > kG3Steps;
       }
     }
+    const int cmax = max(cm[0], cm[1]);
     overflow = __any_sync(0xffffffffu, overflow);    // rows with more entries than the table holds (dense A)
     // elements of the frame this warp accumulates (for the statistics merge)
     float cnt_w = (float)(nvalid * 4 * NP);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) cnt_w += __shfl_xor_sync(0xffffffffu, cnt_w, o);
-    const float inv_cnt_w = 1.f / cnt_w;
+    const float inv_cnt_w = cnt_w > 0.f ? 1.f / cnt_w : 0.f;
     const bool f_in_tile = f < p.FT;
     const char *yf = reinterpret_cast<const char *>(s_y) + (size_t)f * p.V * (YP * 4) + l8 * 16;
-    const int2 *ep0 = s_ent + (wp * 4) * kG3Steps * 4 + qw;
+    const int2 *ep0 = s_ent + (wq * 2) * kG3Steps * 4 + qw;
     const float *bias_l = p.bias ? p.bias + l8 * 4 : nullptr;
     const float *nw_l = p.n_w + l8 * 4, *nb_l = p.n_b + l8 * 4;
+    const int jo0 = max(jw[0], 0) * CO, jo1 = max(jw[1], 0) * CO;
     int buf = 0, t_ph = 0;
     for (int it = 0; it < iters; ++it) {
       const int item = 2 * (pair + it * npairs) + (int)rank;
@@ -463,27 +465,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
       const int n = valid ? item / p.tiles_per_trial : 0;
       const int t = (valid ? (item - n * p.tiles_per_trial) * p.FT : 0) + f;
       const bool frame_ok = valid && f_in_tile && t < p.T;
-      float4 z[NP][4];
+      float4 z[NP][2];
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
-      // RT step: this frame is stream t; its ring positions come from the stream's own counter
-      float *rt_fw = nullptr, *rt_a = nullptr;
-      if (kRt && frame_ok) {
-        const int cnt = __ldg(p.rt_counter + t);
-        const long long ro = (long long)t * p.V * CO + l8 * 4;
-        rt_fw = p.rt_fifo + (long long)(cnt % p.rt_F) * p.rt_slot + ro;
-        rt_a = p.rt_acc + (long long)(cnt % p.rt_S) * p.rt_slot + ro;
-        // pull the tile's FIFO slot / accumulator lines towards L2 while the MMAs run
-#pragma unroll
-        for (int ps = 0; ps < NP; ++ps)
-          if (l8 == (ps & 7)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (jw[i] >= 0) {
-                prefetch_l2(rt_fw + jw[i] * CO + ps * 32 - l8 * 4);
-                prefetch_l2(rt_a + jw[i] * CO + ps * 32 - l8 * 4);
-              }
-          }
-      }
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         { DbgTimer tm(dbg); mbar_wait(bTFull + 8 * buf, t_ph); tm.stop(d0); }
@@ -491,28 +474,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
 #pragma unroll
         for (int hp = 0; hp < 2; ++hp) {
           const int ps = b * 2 + hp;
-          float4 pf[4], pa[4];
-          // operands of this pass that come from global memory: issued here, in flight across the staging
+          // the bias rows of this pass: issued here, in flight across the staging below
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             z[ps][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (frame_ok && jw[i] >= 0) {
-              if (bias_l) z[ps][i] = __ldg(reinterpret_cast<const float4 *>(bias_l + (p.bias_v ? jw[i] * CO : 0) + ps * 32));
-              if (kRt) {
-                pf[i] = ld_stream(reinterpret_cast<const float4 *>(rt_fw + jw[i] * CO + ps * 32));
-                pa[i] = ld_stream(reinterpret_cast<const float4 *>(rt_a + jw[i] * CO + ps * 32));
-              }
-            }
+            if (frame_ok && bias_l && jw[i] >= 0)
+              z[ps][i] = __ldg(reinterpret_cast<const float4 *>(bias_l + (p.bias_v ? (i ? jo1 : jo0) : 0) + ps * 32));
           }
           { DbgTimer tm(dbg); named_bar_sync(1, kG3EpiThreads); tm.stop(d1); }   // staged rows of the previous pass are consumed
           DbgTimer tp1(dbg);
-          if (e < 8) {
-            uint32_t rr[K][16];
+          if (e < kG3LdWarps) {
+            // this warp's share of the pass: K segments of 8 accumulator columns of its 32 rows
+            uint32_t rr[K][8];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + 32 * hp);
 #pragma unroll
             for (int s = 0; s < K; ++s) {
-              const int seg = hh * K + s;
-              tmem_ld16_issue(taddr + (uint32_t)((seg >> 1) * 64 + (seg & 1) * 16), rr[s]);
+              const int seg = hh * K + s;               // 0 .. 4K-1: partition seg / 4, columns (seg % 4) * 8 ..
+              tmem_ld8_issue(taddr + (uint32_t)((seg >> 2) * 64 + (seg & 3) * 8), rr[s]);
             }
             tmem_ld_wait();
             if (hp == 1) {
@@ -527,8 +505,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
             for (int s = 0; s < K; ++s) {
               const int seg = hh * K + s;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4 *>(yrow + seg * 16 + j * 4) =
+              for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<uint4 *>(yrow + seg * 8 + j * 4) =
                     make_uint4(rr[s][4 * j], rr[s][4 * j + 1], rr[s][4 * j + 2], rr[s][4 * j + 3]);
             }
           }
@@ -542,7 +520,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
             const int2 *ep = ep0;
             for (int s = 0; s < cmax; ++s, ep += 4) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
+              for (int i = 0; i < 2; ++i)
                 if (s < cm[i]) {
                   const int2 en = ep[i * kG3Steps * 4];
                   const float a = __int_as_float(en.y);
@@ -555,7 +533,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
             }
             if (overflow) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < 2; ++i) {
                 if (jw[i] < 0) continue;
                 const int e0 = s_rowptr[jw[i]], cn = s_rowptr[jw[i] + 1] - e0;
                 for (int s = kG3Steps; s < cn; ++s) {
@@ -570,27 +548,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
                 }
               }
             }
-            if (kRt) {
-              // acc <- (acc + z_t) + (-fifo[slot]); fifo[slot] <- z_t; o = acc   (rtstgcn.py:611-625)
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (jw[i] >= 0) {
-                  const float4 zt = z[ps][i];
-                  float4 a = pa[i];
-                  a.x = (a.x + zt.x) + (-pf[i].x);
-                  a.y = (a.y + zt.y) + (-pf[i].y);
-                  a.z = (a.z + zt.z) + (-pf[i].z);
-                  a.w = (a.w + zt.w) + (-pf[i].w);
-                  st_stream(reinterpret_cast<float4 *>(rt_fw + jw[i] * CO + ps * 32), zt);
-                  st_stream(reinterpret_cast<float4 *>(rt_a + jw[i] * CO + ps * 32), a);
-                  z[ps][i] = a;
-                }
-            }
             // statistics about a warp-common shift (lane 0's first element), so that the warp merge
             // is a plain sum and the squares do not cancel
             if (ps == 0) shift = __shfl_sync(0xffffffffu, z[0][0].x, 0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
               if (jw[i] >= 0) {
                 const float d0 = z[ps][i].x - shift, d1 = z[ps][i].y - shift, d2 = z[ps][i].z - shift,
                             d3 = z[ps][i].w - shift;
@@ -608,100 +570,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
       }
       if (!frame_ok) continue;
       DbgTimer tfs(dbg);
-      // ---- frame statistics: warp (shuffled sums) -> warp pair (shared memory, exact merge) ----
-      // the first pass of the normalisation needs the LayerNorm affine of 4 rows: load it now
-      float4 g4[4], o4[4];
+      // ---- frame statistics: warp (shuffled sums) -> the frame's four warps (shared memory, exact merge) ----
+      // the first pass of the normalisation needs the LayerNorm affine of this thread's rows: load it now
+      float4 g4[2], o4[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
         if (jw[i] >= 0) {
-          g4[i] = __ldg(reinterpret_cast<const float4 *>(nw_l + jw[i] * CO));
-          o4[i] = __ldg(reinterpret_cast<const float4 *>(nb_l + jw[i] * CO));
+          g4[i] = __ldg(reinterpret_cast<const float4 *>(nw_l + (i ? jo1 : jo0)));
+          o4[i] = __ldg(reinterpret_cast<const float4 *>(nb_l + (i ? jo1 : jo0)));
         }
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
       }
-      float cnt_t = cnt_w;
-      float mean = fmaf(s1, inv_cnt_w, shift);
-      float M2 = fmaxf(s2 - s1 * s1 * inv_cnt_w, 0.f);
-      float *st = s_stat + (f * 2) * 4;
+      float *st = s_stat + (f * 4) * 4;
       if (lane == 0) {
-        st[wp * 4] = cnt_t;
-        st[wp * 4 + 1] = mean;
-        st[wp * 4 + 2] = M2;
+        st[wq * 4] = cnt_w;
+        st[wq * 4 + 1] = fmaf(s1, inv_cnt_w, shift);
+        st[wq * 4 + 2] = fmaxf(s2 - s1 * s1 * inv_cnt_w, 0.f);
       }
-      named_bar_sync(2 + f, 64);
-      {
-        const float nb = st[(wp ^ 1) * 4], mb = st[(wp ^ 1) * 4 + 1], Mb = st[(wp ^ 1) * 4 + 2];
-        // merge in a fixed order (warp 0's partial first) so both warps get bit-identical statistics
-        if (wp == 0) stat_merge(cnt_t, mean, M2, nb, mb, Mb);
-        else {
-          float n0 = nb, m0 = mb, M0 = Mb;
-          stat_merge(n0, m0, M0, cnt_t, mean, M2);
-          cnt_t = n0; mean = m0; M2 = M0;
-        }
-      }
+      named_bar_sync(2 + f, 128);
+      // merge the four partials in a fixed order so that all four warps get bit-identical statistics
+      float cnt_t = st[0], mean = st[1], M2 = st[2];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) stat_merge(cnt_t, mean, M2, st[j * 4], st[j * 4 + 1], st[j * 4 + 2]);
       const float rstd = 1.f / sqrtf(M2 * (1.f / (float)(p.V * CO - 1)) + p.eps);
       const float nmr = -mean * rstd;
       tfs.stop(d5);
       DbgTimer tfn(dbg);
       const long long frow = (long long)n * p.T + t;
       const long long frow_o = p.out_T ? (long long)n * p.out_T + t + p.out_t0 : frow;
+      // row bases of this thread's two rows (element offsets of channel l8*4)
+      const long long ob0 = ((p.out_f32 ? frow : frow_o) * p.V) * CO + jo0 + l8 * 4;
+      const long long ob1 = ((p.out_f32 ? frow : frow_o) * p.V) * CO + jo1 + l8 * 4;
 #pragma unroll
       for (int ps = 0; ps < NP; ++ps) {
-        const int c = ps * 32 + l8 * 4;
         if (ps > 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 2; ++i)
             if (jw[i] >= 0) {
-              g4[i] = __ldg(reinterpret_cast<const float4 *>(nw_l + jw[i] * CO + ps * 32));
-              o4[i] = __ldg(reinterpret_cast<const float4 *>(nb_l + jw[i] * CO + ps * 32));
+              g4[i] = __ldg(reinterpret_cast<const float4 *>(nw_l + (i ? jo1 : jo0) + ps * 32));
+              o4[i] = __ldg(reinterpret_cast<const float4 *>(nb_l + (i ? jo1 : jo0) + ps * 32));
             }
         }
-        float4 r4[4];
-        if (kRt) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jw[i] < 0) continue;
-            const long long ro = (frow * p.V + jw[i]) * CO + c;
-            if (p.res_f32) {
-              r4[i] = ld_stream(reinterpret_cast<const float4 *>(p.res_f32 + ro));
-            } else if (p.res_hi) {
-              const uint2 rh = *reinterpret_cast<const uint2 *>(p.res_hi + ro);
-              const float2 a01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rh.x));
-              const float2 a23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rh.y));
-              r4[i] = make_float4(a01.x, a01.y, a23.x, a23.y);
-              if (p.res_lo) {
-                const uint2 rl = *reinterpret_cast<const uint2 *>(p.res_lo + ro);
-                const float2 b01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rl.x));
-                const float2 b23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rl.y));
-                r4[i].x += b01.x; r4[i].y += b01.y; r4[i].z += b23.x; r4[i].w += b23.y;
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           if (jw[i] < 0) continue;
           float4 v = z[ps][i];
           v.x = fmaf(fmaf(v.x, rstd, nmr), g4[i].x, o4[i].x);
           v.y = fmaf(fmaf(v.y, rstd, nmr), g4[i].y, o4[i].y);
           v.z = fmaf(fmaf(v.z, rstd, nmr), g4[i].z, o4[i].z);
           v.w = fmaf(fmaf(v.w, rstd, nmr), g4[i].w, o4[i].w);
-          if (kRt) {   // out = relu(relu(LN(o)) + res)   (rtstgcn.py:548-553)
-            v.x = fmaxf(v.x, 0.f) + r4[i].x; v.y = fmaxf(v.y, 0.f) + r4[i].y;
-            v.z = fmaxf(v.z, 0.f) + r4[i].z; v.w = fmaxf(v.w, 0.f) + r4[i].w;
-          }
           if (p.relu) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
           }
+          const long long o = (i ? ob1 : ob0) + ps * 32;
           if (p.out_f32) {
-            st_stream(reinterpret_cast<float4 *>(p.out_f32 + (frow * p.V + jw[i]) * CO + c), v);
+            st_stream(reinterpret_cast<float4 *>(p.out_f32 + o), v);
           } else {
             const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
-            const long long o = (frow_o * p.V + jw[i]) * CO + c;
             st_stream(reinterpret_cast<uint2 *>(p.out_hi + o),
                       make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23)));
             if (p.out_lo) {
@@ -734,11 +662,15 @@ inline bool gcn3_supported(int c_in, int c_out, int V, int K) {
   return (c_out == 64 || c_out == 128 || c_out == 256) && c_in % 64 == 0 && c_in >= 64 && c_in <= 256 &&
          V >= 22 && V <= kG3MaxV && (K == 1 || K == 3);
 }
+// Opt-in (STGCN_GCN3=1).  Measured on B200 (profiles/r01_gcn3_*): 851 us vs 1090 us (v2) per 3.2 M
+// rows at C = 64 but no gain at C = 128 and a loss at C = 256 (register spills), and the temporal
+// kernel pays ~13 % for writing / reading bf16 planes instead of fp32 rows -- a net loss over the
+// whole trunk, so v2 stays the default.  DESIGN.md section 4 has the analysis.
 inline bool gcn3_enabled() {
   static int on = -1;
   if (on < 0) {
     const char *e = getenv("STGCN_GCN3");
-    on = e ? atoi(e) != 0 : 1;
+    on = e ? atoi(e) != 0 : 0;
   }
   return on != 0;
 }
@@ -754,7 +686,7 @@ int launch_gcn3_ck(const __nv_bfloat16 *x, const __nv_bfloat16 *wb, Gcn3Params p
   if (p.FT > 5) p.FT = 5;
   p.tiles_per_trial = (p.T + p.FT - 1) / p.FT;
   p.items = N * p.tiles_per_trial;
-  const int fixed = kG3R * kG3Chunk + 128 * YP * 4 + kG3MaxEnt * 8 + 512 + 16 * kG3R + 32 + 64 + 1024;
+  const int fixed = kG3R * kG3Chunk + 128 * YP * 4 + kG3MaxEnt * 8 + 768 + 16 * kG3R + 32 + 64 + 1024;
   int S = (kMaxSmem - fixed) / (kWHalf + 16);
   if (S > 8) S = 8;
   if (S < 2) return fail("gcn3: shared memory does not fit");
@@ -773,13 +705,8 @@ int launch_gcn3_ck(const __nv_bfloat16 *x, const __nv_bfloat16 *wb, Gcn3Params p
   if (make_tmap_bf16(&tm_w, wb, 3, wd, wst, wbx)) return 1;
   int pairs = (p.items + 1) / 2;
   if (pairs > num_sms() / 2) pairs = num_sms() / 2;
-  if (p.rt_fifo) {
-    STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn3<CO, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gcn3<CO, K, true><<<2 * pairs, kG3Threads, smem, st>>>(tm_x, tm_w, p);
-  } else {
-    STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn3<CO, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_gcn3<CO, K, false><<<2 * pairs, kG3Threads, smem, st>>>(tm_x, tm_w, p);
-  }
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcn3<CO, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_gcn3<CO, K><<<2 * pairs, kG3Threads, smem, st>>>(tm_x, tm_w, p);
   return 0;
 }
 

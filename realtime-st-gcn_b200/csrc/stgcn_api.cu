@@ -192,7 +192,7 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws) {
   }
   if (P.gcn) P.n1T = ws.take<float>((size_t)2 * d.c_out * V);
   if (P.tcn) P.n2T = ws.take<float>((size_t)2 * d.c_out * V);
-  P.g3 = P.gcn && tc::gcn3_enabled() && tc::gcn3_supported(d.c_in, d.c_out, V, K) &&
+  P.g3 = P.gcn && !d.rt && tc::gcn3_enabled() && tc::gcn3_supported(d.c_in, d.c_out, V, K) &&
          (d.residual != STGCN_RES_CONV || (P.res && tc::gcn3_supported(d.c_in, d.c_out, V, 1)));
   P.g3r = P.g3 && d.residual == STGCN_RES_CONV;
   if (P.g3) {
@@ -562,7 +562,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
 // x [B*V, c_in] -> out [B*V, c_out]; fifo [F][B][V][C], acc [S][B][V][C]; counter[B].
 int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st,
-                       const LayerPrep *pp = nullptr, bool x_planes = false, bool out_planes = false) {
+                       const LayerPrep *pp = nullptr) {
   if (check_layer(d)) return 1;
   STGCN_REQUIRE(d.norm == STGCN_NORM_LAYERNORM,
                 "continual inference needs LayerNorm: batch statistics of a single frame are undefined "
@@ -576,72 +576,6 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       if (prep_run(d, K, V, local, st)) return 1;
     }
     pp = &local;
-  }
-  const bool use_g3 = math != STGCN_MATH_FP32 && pp && pp->g3;
-  STGCN_REQUIRE(use_g3 || (!x_planes && !out_planes), "bf16-plane activations need the graph-conv v3 path");
-  if (use_g3) {
-    // ---- graph-conv v3 step (kernels_gcn3.cuh): streams are the frames of one trial ----
-    const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
-    const long long rows = (long long)B * V;
-    float *resb = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows * d.c_out) : nullptr;
-    const __nv_bfloat16 *xh = reinterpret_cast<const __nv_bfloat16 *>(x);
-    if (!x_planes) {
-      __nv_bfloat16 *sc = ws.take<__nv_bfloat16>((size_t)planes * rows * d.c_in);
-      if (!ws.measuring()) {
-        STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer input planes)");
-        const long long tot = rows * d.c_in;
-        ProfScope ps(KC_LAYOUT, st);
-        tc::k_rows_to_planes<<<cdiv(tot, 256), 256, 0, st>>>(x, sc, planes == 2 ? sc + tot : nullptr, tot);
-        STGCN_LAUNCH_OK();
-      }
-      xh = sc;
-    }
-    const __nv_bfloat16 *xl = (planes == 2 && xh) ? xh + (size_t)rows * d.c_in : nullptr;
-    if (!ws.measuring()) {
-      STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer)");
-      if (resb) {
-        // residual branch LN_R(conv1x1(x)): no bias, no stride (rtstgcn.py:503)
-        tc::Gcn3Params g{};
-        g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes;
-        g.tab = pp->tabr;
-        g.n_w = pp->nrR; g.n_b = pp->nrR + (size_t)d.c_out * V;
-        g.out_f32 = resb;
-        g.eps = kEps;
-        g.debug = debug_mode();
-        ProfScope ps(KC_GEMM_1X1, st);
-        if (tc::launch_gcn3(d.c_out, 1, xh, pp->wr3, g, 1, B, 1, st)) return 1;
-        STGCN_LAUNCH_OK();
-      }
-      tc::Gcn3Params g{};
-      g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes;
-      g.tab = pp->tab;
-      g.bias = pp->bzR; g.bias_v = 1;
-      g.n_w = pp->n1R; g.n_b = pp->n1R + (size_t)d.c_out * V;
-      if (d.residual == STGCN_RES_IDENTITY) {
-        if (x_planes) { g.res_hi = xh; g.res_lo = xl; }
-        else g.res_f32 = x;
-      } else {
-        g.res_f32 = resb;
-      }
-      if (out_planes) {
-        g.out_hi = reinterpret_cast<__nv_bfloat16 *>(out);
-        g.out_lo = planes == 2 ? g.out_hi + (size_t)rows * d.c_out : nullptr;
-      } else {
-        g.out_f32 = out;
-      }
-      g.relu = 1;                             // relu(relu(LN(o)) + res); idempotent without a residual
-      g.eps = kEps;
-      g.debug = debug_mode();
-      g.rt_fifo = fifo; g.rt_acc = acc; g.rt_counter = counter;
-      g.rt_F = d.stride * (d.kernel - 1) + 1;
-      g.rt_S = d.stride;
-      g.rt_slot = rows * d.c_out;
-      ProfScope ps(KC_FRAME, st);
-      if (tc::launch_gcn3(d.c_out, K, xh, pp->wg3, g, 1, B, 1, st)) return 1;
-      STGCN_LAUNCH_OK();
-    }
-    ws.release(mark0);
-    return 0;
   }
   if (math != STGCN_MATH_FP32 && pp && pp->gcn && (d.residual != STGCN_RES_CONV || pp->res)) {
     // ---- tensor-core step: the B streams form one "trial" of B frames (rows (b, w)) ----
@@ -1022,19 +956,11 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
   }
   float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
   const bool have = use_prepared(m);
-  const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
-  bool g3[65] = {false};
-  {
-    Bump pm(nullptr, 0);
-    for (int i = 0; i < m.num_layers; ++i) g3[i] = m.math != STGCN_MATH_FP32 && prep_take(m.layers[i], K, V, pm).g3;
-  }
-  const bool in0_planes = g3[0] && embed_warp_path(m);
-  if (embed(m, x, buf[0], B, 1, ws, st, nullptr, in0_planes ? planes : 0)) return 1;
+  if (embed(m, x, buf[0], B, 1, ws, st)) return 1;
   char *sb = static_cast<char *>(state);
   int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters);
   int cur = 0;
   Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
-  bool x_planes = in0_planes;
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
     STGCN_REQUIRE(d.rt, "rtstgcn_step needs online layers (rt == 1)");
@@ -1042,11 +968,9 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     float *acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]);
     LayerPrep P;
     if (have) P = prep_take(d, K, V, pb);
-    const bool out_planes = g3[i] && g3[i + 1];
     if (rt_layer_step_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], fifo, acc, counter, B, ws, st,
-                           have ? &P : nullptr, x_planes, out_planes))
+                           have ? &P : nullptr))
       return 1;
-    x_planes = out_planes;
     cur ^= 1;
   }
   const int c_last = m.layers[m.num_layers - 1].c_out;

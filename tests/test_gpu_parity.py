@@ -645,3 +645,26 @@ def test_stgcn_sliding_windows(pkg, syn, cuda):
     ref = O.stgcn_model(windows[pick], sd, dict(layers=3, stride=[1, 2, 1], residual=[1, 1, 1],
                                                 normalization='LayerNorm'))
     assert rel_err(out[0, :, pick].t().unsqueeze(-1), ref) < TOL
+
+
+# ------------------------------------------------------------------ opt-in graph-conv v3 path
+def test_stgcn_model_gcn3_path_subprocess(cuda):
+    """The opt-in graph-conv v3 kernels (STGCN_GCN3=1: reference operation order on CTA pairs, bf16-plane
+    activations between layers) against the oracle: models of growing depth incl. strided /
+    channel-changing layers, both arithmetic modes.  The switch is read once per process, so the
+    check runs tools/debug_g3.py in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, STGCN_GCN3='1')
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'debug_g3.py')], env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith(('bf16x3', 'bf16 '))]
+    assert len(lines) == 20, out.stdout[-2000:]
+    for l in lines:
+        feats = float(l.split('feats ')[1].split()[0])
+        logits = float(l.split('logits ')[1].split()[0])
+        tol = TOL if l.startswith('bf16x3') else BF16_TOL
+        assert feats < tol and logits < tol, l
