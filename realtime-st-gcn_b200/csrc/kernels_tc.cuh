@@ -342,7 +342,9 @@ __device__ __forceinline__ void frame_stats(const float *sp, int fr, int V, floa
 // the residual block is loaded and the output block stored COOPERATIVELY (8 lanes per row, whole
 // 128-B lines, 4 rows per instruction) instead of 32 different rows per instruction; in between
 // every lane touches only its own patch row.
-template <int C, int NH>
+// kPR: compile the bf16-plane residual path (temporal kernels of the opt-in graph-conv v3 path only:
+// in the graph-conv / RT kernels it only costs registers)
+template <int C, int NH, bool kPR>
 __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr, int w,
                                            bool row_ok, long long row, long long row_o, float *s_part,
                                            int tile_parity, int h, uint8_t *patch, float shift, float s1, float s2,
@@ -371,8 +373,8 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   const long long row0 = __shfl_sync(0xffffffffu, row, 0);        // rows of a warp are contiguous
   const long long rowo0 = __shfl_sync(0xffffffffu, row_o, 0);
   uint8_t *mine = patch + lane * kPatchPitch;
-  const bool use_res = (e.res != nullptr || e.res_hi != nullptr) && !(e.debug & 8);
-  const bool res_planes = e.res == nullptr;
+  const bool use_res = (e.res != nullptr || (kPR && e.res_hi != nullptr)) && !(e.debug & 8);
+  const bool res_planes = kPR && e.res == nullptr;
 #pragma unroll 1
   for (int sb = 0; sb < CH; sb += 32) {
     if (use_res && res_planes) {
@@ -537,7 +539,7 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
 }
 
 // ST-GCN epilogue: y = LN_{C,V}(acc + bias) * g + b [+ res] [relu].
-template <int C, int NH>
+template <int C, int NH, bool kPR = false>
 __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
                                                  int w, bool row_ok, long long row, long long row_o,
                                                  float *s_part, int tile_parity, int h, uint8_t *patch) {
@@ -570,8 +572,8 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
     }
   }
   if (pdbg) atomicAdd(&g_dbg[12], (unsigned long long)(clock64() - tp0));
-  epi_finish<C, NH>(e, taddr, r, RT, V, fr, w, row_ok, row, row_o, s_part, tile_parity, h, patch, shift, s1, s2,
-                    true, false);
+  epi_finish<C, NH, kPR>(e, taddr, r, RT, V, fr, w, row_ok, row, row_o, s_part, tile_parity, h, patch, shift, s1, s2,
+                         true, false);
 }
 
 // RT-ST-GCN epilogue: the accumulator row holds z_t (graph-convolved frame, before bias).  Per
@@ -687,8 +689,8 @@ __device__ __forceinline__ void rt_epilogue_tile(const EpiParams &e, uint32_t ta
     atomicAdd(&g_dbg[13], (unsigned long long)tB);
     atomicAdd(&g_dbg[14], (unsigned long long)tC);
   }
-  epi_finish<C, NH>(e, taddr, r, RT, V, fr, w, row_ok, row, row, s_part, tile_parity, h, patch, shift, s1, s2,
-                    false, true);
+  epi_finish<C, NH, false>(e, taddr, r, RT, V, fr, w, row_ok, row, row, s_part, tile_parity, h, patch, shift, s1, s2,
+                           false, true);
   if (tdbg) atomicAdd(&g_dbg[15], (unsigned long long)(clock64() - tl));
 }
 
@@ -900,8 +902,8 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
         const bool row_ok = (r < RT) && (t < p.T_out);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<C, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h,
-                                    s_patch + (warp - 3) * kPatchBytes);
+        ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h,
+                                          s_patch + (warp - 3) * kPatchBytes);
       }
       // accumulator buffer drained: hand it back to the MMA issuer
       tc_fence_before();

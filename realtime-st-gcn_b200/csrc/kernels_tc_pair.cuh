@@ -314,7 +314,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
         const bool row_ok = valid && (r < RT) && (t < p.T_out);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<C, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h,
+        ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h,
                                     s_patch + (warp - 3) * kPatchBytes);
       }
       tc_fence_before();
