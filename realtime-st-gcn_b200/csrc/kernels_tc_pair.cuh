@@ -77,21 +77,9 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  long long t0 = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if ((++spins & 1023u) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 4000000000ll) {
-        printf("stgcn_b200: cluster mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-               threadIdx.x, bar, parity);
-        __trap();
-      }
-    }
-  }
-}
+// the MMA issuer's waits: same bounded, hardware-suspended wait as everywhere else (a pure spin of
+// the 32 lanes took issue slots from the epilogue warps sharing the scheduler, and power)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols));
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
