@@ -515,6 +515,133 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// --------------------------------------------------------------------------- //
+// RT-ST-GCN continual step, state half (rtstgcn.py:611-625, 548-553), as a streaming kernel:
+// one block per stream; z is the graph-convolved frame (bias included) written by the tensor-core
+// GEMM kernel and still L2-resident.  Per element, in the reference's order:
+//   acc <- (acc + z) + (-fifo[slot]);  fifo[slot] <- z;  o = acc
+//   out = relu( relu(LN_{C,V}(o)) + res ),  res = x | LN_R(q) | nothing
+// Everything is float4 and row-contiguous, every thread issues all its loads before the first use,
+// and the 6.9 GB of state move at HBM speed instead of through a latency-bound GEMM epilogue.
+// --------------------------------------------------------------------------- //
+struct RtUpdateArgs {
+  int B, V, C;
+  const float *z;                 // [B*V, C]
+  float *fifo, *acc;              // [F][B*V, C], [S][B*V, C]
+  const int *counter;             // [B]
+  int F, S;
+  long long slot;                 // B*V*C
+  const float *n_wT, *n_bT;       // LayerNorm affine as [C/4][V][4]
+  int res_mode;                   // 0 none, 1 raw rows, 2 LayerNorm_R(rows)
+  const float *res;               // [B*V, C]
+  const float *r_wT, *r_bT;       // affine of the residual norm, [C/4][V][4]
+  float eps;
+  float *out;                     // [B*V, C]
+};
+
+__device__ __forceinline__ float4 ld_nc_stream4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256, 2) k_rt_update(RtUpdateArgs p) {
+  __shared__ float s_red[32];
+  const int b = blockIdx.x;
+  const int VC4 = (p.V * p.C) >> 2, C4 = p.C >> 2;
+  const int cnt = __ldg(p.counter + b);
+  const long long base = (long long)b * p.V * p.C;
+  float *fp = p.fifo + (long long)(cnt % p.F) * p.slot + base;
+  float *ap = p.acc + (long long)(cnt % p.S) * p.slot + base;
+  const float *zp = p.z + base;
+  const float *rp = p.res ? p.res + base : nullptr;
+  float4 a[NV], r[NV], zz[NV], ff[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    a[j] = zz[j] = ff[j] = r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < VC4) {
+      zz[j] = ld_nc_stream4(zp + 4 * i);
+      ff[j] = ld_nc_stream4(fp + 4 * i);
+      a[j] = ld_nc_stream4(ap + 4 * i);
+      if (p.res_mode) r[j] = ld_nc_stream4(rp + 4 * i);
+    }
+  }
+  float s = 0.f, sr = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < VC4) {
+      a[j].x = (a[j].x + zz[j].x) + (-ff[j].x);
+      a[j].y = (a[j].y + zz[j].y) + (-ff[j].y);
+      a[j].z = (a[j].z + zz[j].z) + (-ff[j].z);
+      a[j].w = (a[j].w + zz[j].w) + (-ff[j].w);
+      *reinterpret_cast<float4 *>(fp + 4 * i) = zz[j];
+      *reinterpret_cast<float4 *>(ap + 4 * i) = a[j];
+      s += (a[j].x + a[j].y) + (a[j].z + a[j].w);
+      sr += (r[j].x + r[j].y) + (r[j].z + r[j].w);
+    }
+  }
+  const float inv_n = 1.f / (float)(p.V * p.C), inv_nm1 = 1.f / (float)(p.V * p.C - 1);
+  const float mean = block_sum(s, s_red) * inv_n;
+  float mean_r = 0.f, rstd_r = 1.f;
+  if (p.res_mode == 2) mean_r = block_sum(sr, s_red) * inv_n;
+  float q = 0.f, qr = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < VC4) {
+      const float d0 = a[j].x - mean, d1 = a[j].y - mean, d2 = a[j].z - mean, d3 = a[j].w - mean;
+      q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+      const float e0 = r[j].x - mean_r, e1 = r[j].y - mean_r, e2 = r[j].z - mean_r, e3 = r[j].w - mean_r;
+      qr = fmaf(e0, e0, qr); qr = fmaf(e1, e1, qr); qr = fmaf(e2, e2, qr); qr = fmaf(e3, e3, qr);
+    }
+  }
+  const float rstd = 1.f / sqrtf(block_sum(q, s_red) * inv_nm1 + p.eps);
+  if (p.res_mode == 2) rstd_r = 1.f / sqrtf(block_sum(qr, s_red) * inv_nm1 + p.eps);
+  float *op = p.out + base;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < VC4) {
+      const int w = i / C4, g = i - w * C4;                 // joint, channel group
+      const int ti = (g * p.V + w) * 4;                     // [C/4][V][4]
+      const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.n_wT + ti));
+      const float4 o4 = __ldg(reinterpret_cast<const float4 *>(p.n_bT + ti));
+      float4 v;
+      v.x = fmaxf((a[j].x - mean) * rstd * g4.x + o4.x, 0.f);
+      v.y = fmaxf((a[j].y - mean) * rstd * g4.y + o4.y, 0.f);
+      v.z = fmaxf((a[j].z - mean) * rstd * g4.z + o4.z, 0.f);
+      v.w = fmaxf((a[j].w - mean) * rstd * g4.w + o4.w, 0.f);
+      if (p.res_mode == 1) {
+        v.x += r[j].x; v.y += r[j].y; v.z += r[j].z; v.w += r[j].w;
+      } else if (p.res_mode == 2) {
+        const float4 rg = __ldg(reinterpret_cast<const float4 *>(p.r_wT + ti));
+        const float4 ro = __ldg(reinterpret_cast<const float4 *>(p.r_bT + ti));
+        v.x += (r[j].x - mean_r) * rstd_r * rg.x + ro.x;
+        v.y += (r[j].y - mean_r) * rstd_r * rg.y + ro.y;
+        v.z += (r[j].z - mean_r) * rstd_r * rg.z + ro.z;
+        v.w += (r[j].w - mean_r) * rstd_r * rg.w + ro.w;
+      }
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      *reinterpret_cast<float4 *>(op + 4 * i) = v;
+    }
+  }
+}
+
+inline int launch_rt_update(const RtUpdateArgs &a, cudaStream_t st) {
+  const int nv = (a.V * a.C / 4 + 255) / 256;
+  if (nv <= 2) k_rt_update<2><<<a.B, 256, 0, st>>>(a);
+  else if (nv <= 4) k_rt_update<4><<<a.B, 256, 0, st>>>(a);
+  else if (nv <= 7) k_rt_update<7><<<a.B, 256, 0, st>>>(a);
+  else return fail("rt update: V*C = %d too large", a.V * a.C);
+  return 0;
+}
+inline bool rt_update_supported(int V, int C) { return C % 4 == 0 && (V * C / 4 + 255) / 256 <= 7; }
+
 __global__ void k_advance_counters(int *counter, int first, int count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) counter[first + i] += 1;

@@ -284,6 +284,8 @@ struct EpiParams {
   int out_T, out_t0;             // frames per trial of the plane buffer and frame offset of t = 0
                                  // (T-split: the planes carry halo frames on both sides); 0,0 = same as rows
   int relu;
+  int raw;                       // 1: no norm at all -- out_f32 = acc + bias (RT step: the state update and the
+                                 // LayerNorm run in the streaming kernel k_rt_update)
   float eps;
   int debug;                     // measurement aid: 1 = skip the epilogue body, 2 = skip transform math
   // RT-ST-GCN continual step (rtstgcn.py:611-625): per-stream ring FIFO and running accumulators.
@@ -535,6 +537,44 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   if (fdbg) {
     atomicAdd(&g_dbg[13], (unsigned long long)(tf1 - tf0));
     atomicAdd(&g_dbg[14], (unsigned long long)(clock64() - tf1));
+  }
+}
+
+// Raw epilogue: out_f32 = acc + bias, through the warp's patch so that rows leave as whole 128-B lines.
+template <int C, int NH>
+__device__ __forceinline__ void raw_epilogue_tile(const EpiParams &e, uint32_t taddr, int V, int w, bool row_ok,
+                                                  long long row, int h, uint8_t *patch) {
+  constexpr int CH = C / NH;
+  const int c0 = h * CH;
+  const int pstep = e.bias_sw ? V : 1;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+  const long long row0 = __shfl_sync(0xffffffffu, row, 0);
+  uint8_t *mine = patch + lane * kPatchPitch;
+  float v[16];
+#pragma unroll 1
+  for (int sb = 0; sb < CH; sb += 32) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int cb = sb + half * 16;
+      tmem_ld16(taddr + c0 + cb, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
+        *reinterpret_cast<float4 *>(mine + half * 64 + i * 16) =
+            make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
+      if ((okmask >> rr) & 1)
+        *reinterpret_cast<float4 *>(e.out_f32 + (row0 + rr) * C + c0 + sb + qq * 4) =
+            *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + qq * 16);
+    }
+    __syncwarp();
   }
 }
 
@@ -1320,6 +1360,8 @@ __global__ void __launch_bounds__(kGcn2Threads, 1)
         if (kRt)
           rt_epilogue_tile<CO, kEpiNH>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, t, s_part, par, h,
                                        s_patch + (warp - 10) * 2 * kPatchBytes);
+        else if (p.epi.raw)
+          raw_epilogue_tile<CO, kEpiNH>(p.epi, taddr, p.V, w, row_ok, row, h, s_patch + (warp - 10) * kPatchBytes);
         else
         {
           const long long row_o =

@@ -558,6 +558,16 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   return 0;
 }
 
+// STGCN_RT_SPLIT=0 selects the fused step (state update inside the GEMM kernel's epilogue)
+inline bool rt_split_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_RT_SPLIT");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
+
 // ---- RT online layer on channels-last frames -----------------------------------
 // x [B*V, c_in] -> out [B*V, c_out]; fifo [F][B][V][C], acc [S][B][V][C]; counter[B].
 int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
@@ -576,6 +586,63 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       if (prep_run(d, K, V, local, st)) return 1;
     }
     pp = &local;
+  }
+  if (math != STGCN_MATH_FP32 && pp && pp->gcn && (d.residual != STGCN_RES_CONV || pp->res) && rt_split_enabled() &&
+      rt_update_supported(V, d.c_out)) {
+    // ---- split step: tensor-core GEMM (+ adjacency) writes z = gcn(x) raw (it stays in L2), then the
+    // streaming kernel k_rt_update does the FIFO / accumulator update, LayerNorm and residual ----
+    const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
+    const long long rows = (long long)B * V;
+    float *zb = ws.take<float>((size_t)rows * d.c_out);
+    float *qr = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows * d.c_out) : nullptr;
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer)");
+      if (qr) {
+        // residual branch conv1x1(x): no bias, no stride (rtstgcn.py:503); its LayerNorm runs in k_rt_update
+        tc::GcnTc2Params g{};
+        g.T_out = B; g.V = V; g.K = 1; g.Cin = d.c_in; g.planes = planes;
+        g.identity = 1;
+        g.epi.bias = pp->zero; g.epi.bias_sw = 0;
+        g.epi.out_f32 = qr;
+        g.epi.raw = 1;
+        g.epi.debug = debug_mode();
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcn_tc2(d.c_out, x, pp->wr16, g, 1, B, 1, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      {
+        tc::GcnTc2Params g{};
+        g.T_out = B; g.V = V; g.K = K; g.Cin = d.c_in; g.planes = planes;
+        g.csr_ptr = pp->kw_ptr; g.csr_va = pp->kw_va;
+        g.epi.bias = pp->bzT; g.epi.bias_sw = 1;
+        g.epi.out_f32 = zb;
+        g.epi.raw = 1;
+        g.epi.debug = debug_mode();
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcn_tc2(d.c_out, x, pp->wg16, g, 1, B, 1, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      RtUpdateArgs u{};
+      u.B = B; u.V = V; u.C = d.c_out;
+      u.z = zb;
+      u.fifo = fifo; u.acc = acc; u.counter = counter;
+      u.F = d.stride * (d.kernel - 1) + 1;
+      u.S = d.stride;
+      u.slot = rows * d.c_out;
+      u.n_wT = pp->n1T; u.n_bT = pp->n1T + (size_t)d.c_out * V;
+      if (d.residual == STGCN_RES_IDENTITY) { u.res_mode = 1; u.res = x; }
+      else if (d.residual == STGCN_RES_CONV) {
+        u.res_mode = 2; u.res = qr;
+        u.r_wT = pp->nrT; u.r_bT = pp->nrT + (size_t)d.c_out * V;
+      }
+      u.eps = kEps;
+      u.out = out;
+      ProfScope ps(KC_FRAME, st);
+      if (launch_rt_update(u, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    ws.release(mark0);
+    return 0;
   }
   if (math != STGCN_MATH_FP32 && pp && pp->gcn && (d.residual != STGCN_RES_CONV || pp->res)) {
     // ---- tensor-core step: the B streams form one "trial" of B frames (rows (b, w)) ----
