@@ -668,3 +668,20 @@ def test_stgcn_model_gcn3_path_subprocess(cuda):
         logits = float(l.split('logits ')[1].split()[0])
         tol = TOL if l.startswith('bf16x3') else BF16_TOL
         assert feats < tol and logits < tol, l
+
+
+def test_rt_fused_step_subprocess(cuda):
+    """The continual step defaults to the split form (tensor-core GEMM + streaming state kernel); the fused
+    form (state update inside the GEMM kernel's epilogue, STGCN_RT_SPLIT=0) stays covered: the RT
+    tensor-core tests again in a child process with the switch off."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, STGCN_RT_SPLIT='0')
+    out = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_parity.py'), '-m', 'gpu',
+                          '-q', '-x', '-k', 'rt_full_tensor_core or rt_cuda_graph or rt_online_layer_module or '
+                          'rt_small_batch_matches_batched_path'],
+                         env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert ' passed' in out.stdout and 'failed' not in out.stdout, out.stdout[-1000:]
