@@ -336,6 +336,53 @@ __device__ __forceinline__ void frame_stats(const float *sp, int fr, int V, floa
   rstd = 1.f / sqrtf(tq * (1.f / (float)(V * C - 1)) + eps);
 }
 
+// The same statistics computed by the warp as a whole (16 <= V <= 32, so the warp's 32 rows span at
+// most three frames): lane j reads the partials of row j of a frame, three shuffle reductions merge
+// them.  Every warp that touches a frame runs the identical reduction, so all rows of a frame get
+// bit-identical statistics.  ~1/3 of the dependent-chain length of the per-thread loop above.
+template <int C, int NH>
+__device__ __forceinline__ void frame_stats_warp(const float *sp, int r0, int fr, int V, int RT, float eps,
+                                                 float &mean, float &rstd) {
+  constexpr int CH = C / NH;
+  const int lane = threadIdx.x & 31;
+  const int f_first = r0 / V;
+  const float inv_n = 1.f / (float)(NH * V);
+  const float inv_cv = 1.f / (float)(V * C - 1);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int f = f_first + k;
+    if (f * V >= RT || f * V > r0 + 31) break;          // warp-uniform
+    float d[NH], sm2 = 0.f;
+    const bool on = lane < V;
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      d[hh] = on ? sp[hh * 128 + f * V + lane] : 0.f;
+      sm2 += on ? sp[(NH + hh) * 128 + f * V + lane] : 0.f;
+    }
+    const float ref = __shfl_sync(0xffffffffu, d[0], 0);
+    float sd = 0.f, sdd = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      const float x = on ? d[hh] - ref : 0.f;
+      sd += x;
+      sdd = fmaf(x, x, sdd);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      sdd += __shfl_xor_sync(0xffffffffu, sdd, o);
+      sm2 += __shfl_xor_sync(0xffffffffu, sm2, o);
+    }
+    const float m = ref + sd * inv_n;
+    const float tq = sm2 + (float)CH * fmaxf(sdd - sd * sd * inv_n, 0.f);
+    const float rs = 1.f / sqrtf(tq * inv_cv + eps);
+    if (fr == f) {
+      mean = m;
+      rstd = rs;
+    }
+  }
+}
+
 // Second half of both epilogues: publish this thread's partial statistics, merge the frame's
 // partials, then normalise / add the residual / activate the accumulator rows (re-read from TMEM)
 // and write them out.  `add_bias`: the accumulator still lacks the bias (ST-GCN); the RT path has
@@ -354,8 +401,7 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   constexpr int CH = C / NH;
   const int c0 = h * CH;
   const int pstep = e.bias_sw ? V : 1;
-  const int tab_on = (e.debug & 128) ? 0 : 1;   // measurement aid: all table reads hit one cache line
-  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + ((c0 >> 2) * pstep + (e.bias_sw ? w : 0)) * tab_on;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
   float *sp = s_part + tile_parity * (2 * NH * 128);
   float v[16];
   const float m_r = shift + s1 * (1.f / (float)CH);
@@ -366,10 +412,15 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   const long long tf0 = fdbg ? clock64() : 0;
   asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
   float mean = 0.f, rstd = 0.f;
-  if (r < RT && !(e.debug & 64)) frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
+  if (V >= 16 && V <= 32) {
+    if (!(e.debug & 64)) frame_stats_warp<C, NH>(sp, r - (threadIdx.x & 31), fr, V, RT, e.eps, mean, rstd);
+  } else if (r < RT && !(e.debug & 64)) {
+    frame_stats<C, NH>(sp, fr, V, e.eps, mean, rstd);
+  }
+  const float nmr = -mean * rstd;
   const long long tf1 = fdbg ? clock64() : 0;
-  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT) + ((c0 >> 2) * V + w) * tab_on;
-  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT) + ((c0 >> 2) * V + w) * tab_on;
+  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT) + (c0 >> 2) * V + w;
+  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT) + (c0 >> 2) * V + w;
   const int lane = threadIdx.x & 31;
   const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
   const long long row0 = __shfl_sync(0xffffffffu, row, 0);        // rows of a warp are contiguous
@@ -377,6 +428,12 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   uint8_t *mine = patch + lane * kPatchPitch;
   const bool use_res = (e.res != nullptr || (kPR && e.res_hi != nullptr)) && !(e.debug & 8);
   const bool res_planes = kPR && e.res == nullptr;
+#ifdef STGCN_EPI_DEBUG   // fine-grained pass-2 phase timers (cost registers: off by default)
+  long long tq = fdbg ? clock64() : 0, q_res = 0, q_tm = 0, q_math = 0, q_st = 0;
+#define EPI_STAMP(acc) if (fdbg) { const long long n_ = clock64(); acc += n_ - tq; tq = n_; }
+#else
+#define EPI_STAMP(acc)
+#endif
 #pragma unroll 1
   for (int sb = 0; sb < CH; sb += 32) {
     if (use_res && res_planes) {
@@ -436,22 +493,26 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
       }
       __syncwarp();
     }
+    EPI_STAMP(q_res)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int cb = sb + half * 16;
+      if (half == 1) { EPI_STAMP(q_math) }
       tmem_ld16(taddr + c0 + cb, v);
+      EPI_STAMP(q_tm)
       if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int pi = (cb >> 2) + i;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (add_bias) b4 = __ldg(bias4 + pi * pstep * tab_on);
-          const float4 g4 = __ldg(nw4 + pi * V * tab_on);
-          const float4 o4 = __ldg(nb4 + pi * V * tab_on);
-          v[4 * i] = (v[4 * i] + b4.x - mean) * rstd * g4.x + o4.x;
-          v[4 * i + 1] = (v[4 * i + 1] + b4.y - mean) * rstd * g4.y + o4.y;
-          v[4 * i + 2] = (v[4 * i + 2] + b4.z - mean) * rstd * g4.z + o4.z;
-          v[4 * i + 3] = (v[4 * i + 3] + b4.w - mean) * rstd * g4.w + o4.w;
+          if (add_bias) b4 = __ldg(bias4 + pi * pstep);
+          const float4 g4 = __ldg(nw4 + pi * V);
+          const float4 o4 = __ldg(nb4 + pi * V);
+          // ((v + b) - mean) * rstd * g + o as two FMAs on (v + b): x * rstd + (-mean * rstd), then * g + o
+          v[4 * i] = fmaf(fmaf(v[4 * i] + b4.x, rstd, nmr), g4.x, o4.x);
+          v[4 * i + 1] = fmaf(fmaf(v[4 * i + 1] + b4.y, rstd, nmr), g4.y, o4.y);
+          v[4 * i + 2] = fmaf(fmaf(v[4 * i + 2] + b4.z, rstd, nmr), g4.z, o4.z);
+          v[4 * i + 3] = fmaf(fmaf(v[4 * i + 3] + b4.w, rstd, nmr), g4.w, o4.w);
         }
         if (relu_mid) {
 #pragma unroll
@@ -491,12 +552,12 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[2 * i], h0, l0);
-            split_bf16(v[2 * i + 1], h1, l1);
-            __nv_bfloat162 hh(h0, h1), ll(l0, l1);
-            hi[i] = *reinterpret_cast<uint32_t *>(&hh);
-            lo[i] = *reinterpret_cast<uint32_t *>(&ll);
+            // packed conversions (one F2FP per pair; the scalar form compiles to two slow-pipe F2F + PRMT)
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            const float2 hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+            hi[i] = *reinterpret_cast<const uint32_t *>(&hh);
+            lo[i] = *reinterpret_cast<const uint32_t *>(&ll);
           }
           uint4 *ph = reinterpret_cast<uint4 *>(mine + half * 64);
           ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -508,6 +569,7 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
       }
     }
     __syncwarp();
+    EPI_STAMP(q_math)
     if (!(e.debug & 32)) {
       if (e.out_f32) {
 #pragma unroll
@@ -535,6 +597,13 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
     __syncwarp();
   }
   if (fdbg) {
+#ifdef STGCN_EPI_DEBUG
+    q_st = (clock64() - tf1) - q_res - q_tm - q_math;
+    atomicAdd(&g_dbg[8], (unsigned long long)q_res);
+    atomicAdd(&g_dbg[9], (unsigned long long)q_tm);
+    atomicAdd(&g_dbg[10], (unsigned long long)q_math);
+    atomicAdd(&g_dbg[15], (unsigned long long)q_st);
+#endif
     atomicAdd(&g_dbg[13], (unsigned long long)(tf1 - tf0));
     atomicAdd(&g_dbg[14], (unsigned long long)(clock64() - tf1));
   }
@@ -589,8 +658,7 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
   const int c0 = h * CH;
   // float4 index of channel group g: table -> g*V + w, plain vector -> g
   const int pstep = e.bias_sw ? V : 1;
-  const int tab_on = (e.debug & 128) ? 0 : 1;
-  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + ((c0 >> 2) * pstep + (e.bias_sw ? w : 0)) * tab_on;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(e.bias) + (c0 >> 2) * pstep + (e.bias_sw ? w : 0);
   float v[16];
   float shift = 0.f, s1 = 0.f, s2 = 0.f;
   const bool pdbg = (e.debug & 4) && blockIdx.x == 0 && r == 0 && h == 0;
@@ -600,7 +668,7 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
     tmem_ld16(taddr + c0 + cb, v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep * tab_on);
+      const float4 b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
       v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
     }
     if (cb == 0) shift = v[0];

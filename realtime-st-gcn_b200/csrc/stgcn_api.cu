@@ -38,6 +38,8 @@ int debug_dump(const char *what, int c, cudaStream_t st) {
                                   "xf_compute", "items"};
   fprintf(stderr, "[dbg] %s<%d>:", what, c);
   for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
+  if (!strcmp(what, "tcn"))
+    fprintf(stderr, " [tcn pass 2 of CTA 0 / row 0: 8 residual load 9 tmem loads 10 tables+math+patch 15 cooperative store]");
   if (!strcmp(what, "gcn3"))
     fprintf(stderr, " [gcn3: 6 epi_wait_tmem 7 barA 8 phase1 9 barB 10 gather 12 stats 13 normalise+store]");
   fprintf(stderr, " ph12(pass1|rt_wait)=%llu ph13(bar_stats|rt_update)=%llu ph14(pass2|rt_store)=%llu ph15(rt_finish)=%llu", h[12], h[13], h[14], h[15]);
