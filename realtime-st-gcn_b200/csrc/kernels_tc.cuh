@@ -397,7 +397,7 @@ template <int C, int NH, bool kPR>
 __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr, int w,
                                            bool row_ok, long long row, long long row_o, float *s_part,
                                            int tile_parity, int h, uint8_t *patch, float shift, float s1, float s2,
-                                           bool add_bias, bool relu_mid) {
+                                           bool add_bias, bool relu_mid, int bar_id = 1) {
   constexpr int CH = C / NH;
   const int c0 = h * CH;
   const int pstep = e.bias_sw ? V : 1;
@@ -410,7 +410,7 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   sp[(NH + h) * 128 + r] = row_ok ? M2_r : 0.f;
   const bool fdbg = add_bias && (e.debug & 4) && blockIdx.x == 0 && r == 0 && h == 0;
   const long long tf0 = fdbg ? clock64() : 0;
-  asm volatile("bar.sync 1, %0;" ::"n"(128 * NH) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(128 * NH) : "memory");   // the 4*NH warps working on this tile
   float mean = 0.f, rstd = 0.f;
   if (V >= 16 && V <= 32) {
     if (!(e.debug & 64)) frame_stats_warp<C, NH>(sp, r - (threadIdx.x & 31), fr, V, RT, e.eps, mean, rstd);
@@ -651,7 +651,8 @@ __device__ __forceinline__ void raw_epilogue_tile(const EpiParams &e, uint32_t t
 template <int C, int NH, bool kPR = false>
 __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
                                                  int w, bool row_ok, long long row, long long row_o,
-                                                 float *s_part, int tile_parity, int h, uint8_t *patch) {
+                                                 float *s_part, int tile_parity, int h, uint8_t *patch,
+                                                 int bar_id = 1) {
   if (e.debug & 1) return;
   constexpr int CH = C / NH;
   static_assert(CH % 32 == 0, "epilogue works in 32-column super-chunks");
@@ -681,7 +682,7 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
   }
   if (pdbg) atomicAdd(&g_dbg[12], (unsigned long long)(clock64() - tp0));
   epi_finish<C, NH, kPR>(e, taddr, r, RT, V, fr, w, row_ok, row, row_o, s_part, tile_parity, h, patch, shift, s1, s2,
-                         true, false);
+                         true, false, bar_id);
 }
 
 // RT-ST-GCN epilogue: the accumulator row holds z_t (graph-convolved frame, before bias).  Per
@@ -1613,7 +1614,16 @@ inline bool tcn_pair_enabled() {
 }
 template <int C>
 int launch_tcn_pair(const CUtensorMap &tm_u0, const CUtensorMap &tm_u1, const CUtensorMap &tm_wh,
-                    const TcnTc2Params &p, int grid, int smem, cudaStream_t st);
+                    const TcnTc2Params &p, int grid, int smem, int sets, cudaStream_t st);
+// STGCN_TCN_SETS=1 / 2 forces one / two sets of eight epilogue warps in the pair kernel (0 = by mode)
+inline int tcn_sets_wanted() {
+  static int n = -1;
+  if (n < 0) {
+    const char *e = getenv("STGCN_TCN_SETS");
+    n = e ? atoi(e) : 0;
+  }
+  return n;
+}
 
 // `halo`: the plane buffer holds `halo` extra frames before and after the T frames of every trial
 // (T-split: filled by the neighbouring ranks, or zeros at the sequence ends); output frame tau
@@ -1702,7 +1712,15 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
   if (tcn_pair_enabled() && p.items >= 2) {
     // CTA pairs (cta_group::2): every CTA stages only its half of each weight tile
     const int kBHalf = (C / 2) * 128;
-    const int fixed_p = kPartBytes + kPatchTotal + 512 + 1024;
+    // two sets of eight epilogue warps (one per tile of the item) when the item has two tiles and the
+    // extra statistics / patch buffers still leave three weight stages.  Measured: -7.5 % on the
+    // temporal class in bf16 mode (one MMA per product: the kernel is epilogue-bound), +1 % in
+    // bf16x3 mode (MMA / operand-bound; fewer weight stages and 96 registers per thread cost more
+    // than the second set gains) -- so only bf16 mode uses it unless STGCN_TCN_SETS forces it.
+    const int want = tcn_sets_wanted() ? tcn_sets_wanted() : (p.planes == 1 ? 2 : 1);
+    int sets = (p.NT == 2 && want >= 2 &&
+                (kMaxSmem - 2 * p.a_stage_bytes - 2 * (kPartBytes + kPatchTotal) - 1536) / kBHalf >= 3) ? 2 : 1;
+    const int fixed_p = sets * (kPartBytes + kPatchTotal) + 512 + 1024;
     int S = (kMaxSmem - 2 * p.a_stage_bytes - fixed_p) / kBHalf;
     if (S > 12) S = 12;
     if (S >= 2) {
@@ -1713,7 +1731,7 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
       const int smem_p = 2 * p.a_stage_bytes + S * kBHalf + fixed_p;
       int pairs = (p.items + 1) / 2;
       if (pairs > num_sms() / 2) pairs = num_sms() / 2;
-      return launch_tcn_pair<C>(tm_u0, tm_u1, tm_wh, p, 2 * pairs, smem_p, st);
+      return launch_tcn_pair<C>(tm_u0, tm_u1, tm_wh, p, 2 * pairs, smem_p, sets, st);
     }
   }
   STGCN_CUDA_OK(cudaFuncSetAttribute(k_tcn_tc2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

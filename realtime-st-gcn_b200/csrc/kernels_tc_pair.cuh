@@ -103,8 +103,10 @@ __device__ __forceinline__ void umma_commit_2(uint32_t bar) {
       : "memory");
 }
 
-template <int C>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
+// SETS: sets of eight epilogue warps.  With two sets (items of two tiles) each set normalises one
+// tile, so the item's epilogue takes half as long -- the epilogue is latency-bound, not issue-bound.
+template <int C, int SETS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * kEpiNH * SETS), 1)
     k_tcn_tc2p(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__ CUtensorMap tm_u1,
                const __grid_constant__ CUtensorMap tm_w, const TcnTc2Params p) {
   constexpr int kBHalf = (C / 2) * 128;           // this CTA's half of a weight tile: [C/2 rows][64 ch] bf16
@@ -118,8 +120,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + 2 * p.a_stage_bytes;
   const uint32_t sPart = sB + S * kBHalf;
-  const uint32_t sPatch = sPart + kPartBytes;
-  const uint32_t sBar = sPatch + kPatchTotal;
+  const uint32_t sPatch = sPart + SETS * kPartBytes;
+  const uint32_t sBar = sPatch + SETS * kPatchTotal;
   const uint32_t bFullA = sBar, bEmptyA = sBar + 16, bPeerA = sBar + 32, bTmemFull = sBar + 48, bTmemEmpty = sBar + 64;
   const uint32_t bFullB = sBar + 80, bEmptyB = bFullB + 8 * S, bPeerB = bEmptyB + 8 * S;
   const uint32_t sTmemPtr = bPeerB + 8 * S;
@@ -145,7 +147,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
       mbar_init(bEmptyA + 8 * i, 1);
       mbar_init(bPeerA + 8 * i, 1);
       mbar_init(bTmemFull + 8 * i, 1);
-      mbar_init(bTmemEmpty + 8 * i, 2 * 4 * kEpiNH);   // the epilogue warps of BOTH CTAs
+      mbar_init(bTmemEmpty + 8 * i, 2 * 4 * kEpiNH * SETS);   // the epilogue warps of BOTH CTAs
     }
     for (int i = 0; i < S; ++i) {
       mbar_init(bFullB + 8 * i, 2);
@@ -259,10 +261,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
     }
   } else {
     // ---- epilogue (both CTAs, own TMEM, own item) ----
+    const int ew = warp - 3;                       // 0 .. 8*SETS-1
+    const int set = ew >> 3;                       // SETS == 2: tile of the item this set normalises
     const int q = warp & 3;
-    const int h = (warp - 3) >> 2;
+    const int h = (ew & 7) >> 2;
     const int r = q * 32 + lane;
     const int fr = r / p.V, w = r - fr * p.V;
+    float *s_part_set = s_part + set * (kPartBytes / 4);
+    uint8_t *patch = s_patch + ew * kPatchBytes;
+    const int m_first = SETS == 2 ? set : 0, m_last = SETS == 2 ? set + 1 : p.NT;
     int buf = 0, t_ph = 0, par = 0;
     for (int it = 0; it < iters; ++it) {
       const int item = 2 * (pair + it * npairs) + (int)rank;
@@ -270,7 +277,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
       const int n = valid ? item / p.groups_per_trial : 0;
       const int f0 = valid ? (item - n * p.groups_per_trial) * p.NT * p.FT : 0;
       if (valid && p.epi.res && r < RT) {
-        for (int m = 0; m < p.NT; ++m) {
+        for (int m = m_first; m < m_last; ++m) {
           const int t = f0 + m * p.FT + fr;
           if (t < p.T_out) {
             const char *rp = reinterpret_cast<const char *>(p.epi.res + (((long long)n * p.T_out + t) * p.V + w) * C +
@@ -280,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
           }
         }
       } else if (valid && p.epi.res_hi && r < RT) {
-        for (int m = 0; m < p.NT; ++m) {
+        for (int m = m_first; m < m_last; ++m) {
           const int t = f0 + m * p.FT + fr;
           if (t < p.T_out) {
             const long long ro = (((long long)n * p.T_out + t) * p.V + w) * C + h * (C / kEpiNH);
@@ -297,13 +304,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
       mbar_wait(bTmemFull + 8 * buf, t_ph);
       tc_fence_after();
 #pragma unroll 1
-      for (int m = 0; m < p.NT; ++m, par ^= 1) {
+      for (int m = m_first; m < m_last; ++m, par ^= 1) {
         const int t = f0 + m * p.FT + fr;
         const bool row_ok = valid && (r < RT) && (t < p.T_out);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h,
-                                    s_patch + (warp - 3) * kPatchBytes);
+        ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part_set, par, h, patch,
+                                          1 + set);
       }
       tc_fence_before();
       __syncwarp();
@@ -322,9 +329,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcn2Threads, 1)
 
 template <int C>
 int launch_tcn_pair(const CUtensorMap &tm_u0, const CUtensorMap &tm_u1, const CUtensorMap &tm_wh,
-                    const TcnTc2Params &p, int grid, int smem, cudaStream_t st) {
-  STGCN_CUDA_OK(cudaFuncSetAttribute(k_tcn_tc2p<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_tcn_tc2p<C><<<grid, kTcn2Threads, smem, st>>>(tm_u0, tm_u1, tm_wh, p);
+                    const TcnTc2Params &p, int grid, int smem, int sets, cudaStream_t st) {
+  if constexpr (C <= 128) {
+    if (sets == 2) {
+      STGCN_CUDA_OK(cudaFuncSetAttribute(k_tcn_tc2p<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_tcn_tc2p<C, 2><<<grid, 32 * (3 + 8 * kEpiNH), smem, st>>>(tm_u0, tm_u1, tm_wh, p);
+      return 0;
+    }
+  }
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_tcn_tc2p<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_tcn_tc2p<C, 1><<<grid, kTcn2Threads, smem, st>>>(tm_u0, tm_u1, tm_wh, p);
   return 0;
 }
 
