@@ -825,6 +825,17 @@ __global__ void __launch_bounds__(256) k_embed_warp(EmbedWarpArgs p) {
   for (int i = threadIdx.x; i < p.C0; i += blockDim.x) sb[i] = p.bias[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // C_in == 3 and 32 % (C0/4) == 0 (the shipped trunks: 3 -> 64): a lane always produces the same four
+  // output channels, so its weights live in registers and the inner product needs no shared-memory reads
+  const bool reg_w = p.C_in == 3 && (p.C0 >> 2) <= 32 && 32 % (p.C0 >> 2) == 0;
+  const int co_l = (lane % (p.C0 >> 2)) * 4;
+  float wr[12];
+  float4 br = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (reg_w) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) wr[k] = sw[(co_l + k / 3) * 3 + (k % 3)];
+    br = make_float4(sb[co_l], sb[co_l + 1], sb[co_l + 2], sb[co_l + 3]);
+  }
   float *xn = sxn + warp * VCi;
   const float inv_n = 1.f / (float)VCi, inv_nm1 = 1.f / (float)(VCi - 1);
   const long long frames = (long long)p.N * p.T;
@@ -867,6 +878,35 @@ __global__ void __launch_bounds__(256) k_embed_warp(EmbedWarpArgs p) {
     const long long dst_o = f * (long long)p.V * p.C0;
     float *dst = p.out + dst_o;
     const int C04 = p.C0 >> 2;                                 // C0 % 4 == 0 (checked by the caller)
+    if (reg_w) {
+      // lane -> fixed channel group co (32 % (C0/4) == 0): its 4 x C_in weights and biases sit in registers
+      for (int i = lane; i < p.V * C04; i += 32) {
+        const int vj = i / C04;
+        const float x0 = xn[vj * 3], x1 = xn[vj * 3 + 1], x2 = xn[vj * 3 + 2];
+        float4 acc;
+        acc.x = fmaf(wr[2], x2, fmaf(wr[1], x1, fmaf(wr[0], x0, br.x)));
+        acc.y = fmaf(wr[5], x2, fmaf(wr[4], x1, fmaf(wr[3], x0, br.y)));
+        acc.z = fmaf(wr[8], x2, fmaf(wr[7], x1, fmaf(wr[6], x0, br.z)));
+        acc.w = fmaf(wr[11], x2, fmaf(wr[10], x1, fmaf(wr[9], x0, br.w)));
+        if (p.out) {
+          *reinterpret_cast<float4 *>(dst + vj * p.C0 + co_l) = acc;
+        } else {
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(acc.x, acc.y), h23 = __floats2bfloat162_rn(acc.z, acc.w);
+          const long long o = dst_o + vj * p.C0 + co_l;
+          *reinterpret_cast<uint2 *>(p.out_hi + o) =
+              make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+          if (p.out_lo) {
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(acc.x - f01.x, acc.y - f01.y);
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(acc.z - f23.x, acc.w - f23.y);
+            *reinterpret_cast<uint2 *>(p.out_lo + o) =
+                make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+          }
+        }
+      }
+      __syncwarp();
+      continue;
+    }
     for (int i = lane; i < p.V * C04; i += 32) {
       const int vj = i / C04, co = (i - vj * C04) * 4;
       float4 acc = make_float4(sb[co], sb[co + 1], sb[co + 2], sb[co + 3]);
@@ -909,6 +949,43 @@ __global__ void __launch_bounds__(256)
   long long r0 = (long long)ch * rows_per_chunk, r1 = r0 + rows_per_chunk;
   if (r1 > R) r1 = R;
   const float *xs = x + n * R * C;
+  const int C4 = C >> 2;
+  if ((C & 3) == 0 && C4 <= 256 && 256 % C4 == 0) {
+    // float4 lanes over the channels, 256 / (C/4) row groups in parallel, four independent
+    // accumulators per thread; the row groups are merged in a fixed order (deterministic)
+    __shared__ float4 s_acc[256];
+    const int c4 = threadIdx.x % C4, rg = threadIdx.x / C4, RG = 256 / C4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    const float4 *xp = reinterpret_cast<const float4 *>(xs) + c4;
+    long long r = r0 + rg;
+    for (; r + 3 * RG < r1; r += 4 * RG) {
+      const float4 v0 = __ldg(xp + r * C4), v1 = __ldg(xp + (r + RG) * C4), v2 = __ldg(xp + (r + 2 * RG) * C4),
+                   v3 = __ldg(xp + (r + 3 * RG) * C4);
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+      a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; r < r1; r += RG) {
+      const float4 v0 = __ldg(xp + r * C4);
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    a0.x = (a0.x + a1.x) + (a2.x + a3.x);
+    a0.y = (a0.y + a1.y) + (a2.y + a3.y);
+    a0.z = (a0.z + a1.z) + (a2.z + a3.z);
+    a0.w = (a0.w + a1.w) + (a2.w + a3.w);
+    s_acc[threadIdx.x] = a0;
+    __syncthreads();
+    if (rg == 0) {
+      float4 t = s_acc[c4];
+      for (int g = 1; g < RG; ++g) {
+        const float4 u = s_acc[g * C4 + c4];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      reinterpret_cast<float4 *>(part + (n * nchunk + ch) * C)[c4] = t;
+    }
+    return;
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (long long r = r0; r < r1; ++r) s += xs[r * C + c];
