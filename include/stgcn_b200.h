@@ -79,7 +79,9 @@ typedef struct stgcn_model_desc {
   int32_t in_feat, num_joints, partitions, num_classes, num_layers;
   int32_t norm;          /* STGCN_NORM_* */
   int32_t math;          /* STGCN_MATH_* */
-  int32_t reserved;      /* bit 0: do not use the few-streams cluster kernel in rtstgcn_step */
+  int32_t reserved;      /* bit 0: do not use the few-streams cluster kernel in rtstgcn_step;
+                          * bit 1: the adjacency has at most 6*V non-zeros (tree skeletons): the graph-conv
+                          *        stage may use one pre-scaled weight copy per edge (kernels_gcnw.cuh) */
   const float *norm_in_w, *norm_in_b;
   const float *fcn_in_w, *fcn_in_b;
   const float *fcn_out_w, *fcn_out_b;

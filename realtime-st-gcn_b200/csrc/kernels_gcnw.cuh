@@ -1,0 +1,495 @@
+// Graph convolution as a GEMM with per-joint, pre-scaled weights (default for model-level forwards whose
+// adjacency is known to be sparse, stgcn_model_desc.reserved bit 1; STGCN_GCNW=0 disables it).
+//
+//   z[(n,t,w), c] = bz[w,c] + sum_{edges e = (k,v) into w} x[(n,t,v), :] . (A[k,v,w] * W_k[c, :])
+//
+// The adjacency weight of an edge is folded into the WEIGHTS (one pre-scaled, bf16-split copy of W_k
+// per edge, built once per parameter set), and a tile is 128 consecutive frames of ONE output joint
+// w: its A operands are plain strided TMA boxes of the bf16-plane input (joint v_e, 128 frames), its
+// B operands the edge's weight tiles.  No CUDA-core arithmetic before the MMA, no gather after it; the
+// epilogue only adds the bias and stores z (fp32, rows strided by V).  LayerNorm(C,V) + ReLU + the
+// bf16 split for the temporal kernel run in the streaming kernel k_ln_stream (one block per frame),
+// i.e. the stage trades one extra HBM round trip of z for kernels that are bandwidth- / MMA-bound
+// instead of latency-bound.  Tree-structured adjacency only: the weight buffer
+// holds 6*V edges.
+#pragma once
+#include "kernels_tc.cuh"
+
+namespace stgcn {
+namespace tc {
+
+constexpr int kGwMaxV = 32;
+constexpr int kGwEdgeCap = 6 * kGwMaxV;
+inline int gcnw_edge_cap(int V) { return 6 * V; }
+
+struct GcnwTables {
+  int ptr[kGwMaxV + 1];       // edges into joint w: [ptr[w], ptr[w+1])
+  int nedge;                  // -1: the adjacency has more edges than the weight buffer holds
+  int pad[2];
+  int src[kGwEdgeCap];        // source joint v
+  int kk[kGwEdgeCap];         // partition k
+  float val[kGwEdgeCap];      // A[k,v,w]
+};
+
+__global__ void k_gcnw_tables(const float *__restrict__ A, int K, int V, int identity, int cap, GcnwTables *tab) {
+  __shared__ int cnt[kGwMaxV + 1];
+  const int w = threadIdx.x;
+  if (w < V) {
+    int c = 0;
+    if (identity) c = 1;
+    else
+      for (int k = 0; k < K; ++k)
+        for (int v = 0; v < V; ++v) c += (A[((long long)k * V + v) * V + w] != 0.f);
+    cnt[w] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < V; ++i) {
+      tab->ptr[i] = run;
+      run += cnt[i];
+    }
+    tab->ptr[V] = run;
+    tab->nedge = run <= cap ? run : -1;
+  }
+  __syncthreads();
+  if (w < V && tab->nedge >= 0) {
+    int at = tab->ptr[w];
+    if (identity) {
+      tab->src[at] = w; tab->kk[at] = 0; tab->val[at] = 1.f;
+    } else {
+      for (int k = 0; k < K; ++k)
+        for (int v = 0; v < V; ++v) {
+          const float a = A[((long long)k * V + v) * V + w];
+          if (a != 0.f) {
+            tab->src[at] = v; tab->kk[at] = k; tab->val[at] = a;
+            ++at;
+          }
+        }
+    }
+  }
+}
+
+// wsc[plane][edge][c_out][c_in] = split_bf16(A_e * W[k_e*CO + c][ci]); plane stride = cap*CO*Cin
+__global__ void k_gcnw_pack(const float *__restrict__ w, const GcnwTables *__restrict__ tab, int CO, int Cin, int cap,
+                            __nv_bfloat16 *__restrict__ wsc) {
+  const long long per = (long long)CO * Cin;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ne = tab->nedge;
+  if (ne < 0 || i >= per * ne) return;
+  const int e = (int)(i / per);
+  const long long r = i - (long long)e * per;
+  __nv_bfloat16 hi, lo;
+  split_bf16(tab->val[e] * w[(long long)tab->kk[e] * per + r], hi, lo);
+  wsc[i] = hi;
+  wsc[(long long)cap * per + i] = lo;
+}
+
+struct GcnwParams {
+  int T, V, Cin, planes, N;     // frames per trial of this view, joints, input channels, bf16 planes, trials
+  int tblocks, items;           // 128-frame blocks per trial; items = N * tblocks * V (w fastest)
+  int a_stages, b_stages;
+  const GcnwTables *tab;
+  const float *bias;            // bias_sw = 1: [C/4][V][4] table, 0: [C] vector, null: none
+  int bias_sw;
+  float *out;                   // z fp32 rows [(n*T + t)*V + w][CO]
+  int debug;
+};
+
+constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B producer, 3.. epilogue
+
+// MERGE (C_out <= 128): one activation stage holds both bf16 planes of an (edge, 64-channel chunk)
+// and one weight stage both weight planes, so the MMA issuer waits on two barriers per twelve MMAs
+// instead of five per twelve, and the weight hi plane is loaded once instead of twice.
+template <int CO, bool MERGE>
+__global__ void __launch_bounds__(kGwThreads, 1)
+    k_gcnw(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GcnwParams p) {
+  constexpr int kAPlane = 128 * 128;            // [128 frames][64 ch] bf16
+  constexpr int kBPlane = CO * 128;             // [CO][64 ch] bf16
+  constexpr int kABytes = MERGE ? 2 * kAPlane : kAPlane;
+  constexpr int kBBytes = MERGE ? 2 * kBPlane : kBPlane;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int SA = p.a_stages, SB = p.b_stages;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + SA * kABytes;
+  const uint32_t sPatch = sB + SB * kBBytes;
+  const uint32_t sTab = sPatch + kPatchTotal;                    // ptr[33] + src[192]
+  const uint32_t sBar = sTab + 1024;
+  const uint32_t bTmemFull = sBar, bTmemEmpty = sBar + 16;
+  const uint32_t bFullA = sBar + 32, bEmptyA = bFullA + 8 * SA;
+  const uint32_t bFullB = bEmptyA + 8 * SA, bEmptyB = bFullB + 8 * SB;
+  const uint32_t sTmemPtr = bEmptyB + 8 * SB;
+  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(gen_base + (sTmemPtr - smem_base));
+  uint8_t *s_patch = gen_base + (sPatch - smem_base);
+  int *s_ptr = reinterpret_cast<int *>(gen_base + (sTab - smem_base));
+  int *s_src = s_ptr + 40;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = p.Cin / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bTmemFull + 8 * i, 1);
+      mbar_init(bTmemEmpty + 8 * i, 4 * kEpiNH);
+    }
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(bFullA + 8 * i, 1);
+      mbar_init(bEmptyA + 8 * i, 1);
+    }
+    for (int i = 0; i < SB; ++i) {
+      mbar_init(bFullB + 8 * i, 1);
+      mbar_init(bEmptyB + 8 * i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(sTmemPtr, 512);
+  for (int i = threadIdx.x; i <= p.V; i += blockDim.x) s_ptr[i] = __ldg(&p.tab->ptr[i]);
+  for (int i = threadIdx.x; i < kGwEdgeCap; i += blockDim.x) s_src[i] = __ldg(&p.tab->src[i]);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ---- A producer: for every edge of the item's joint, the source joint's 128 frames, per 64-channel
+    // chunk and plane ----
+    if (lane == 0) {
+      int as = 0, a_ph = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int w = item % p.V;
+        const int tb = (item / p.V) % p.tblocks, n = item / (p.V * p.tblocks);
+        for (int e = s_ptr[w]; e < s_ptr[w + 1]; ++e)
+          for (int kc = 0; kc < KC; ++kc) {
+            if (MERGE) {
+              mbar_wait(bEmptyA + 8 * as, a_ph ^ 1);
+              mbar_expect_tx(bFullA + 8 * as, (uint32_t)(p.planes * kAPlane));
+              for (int ap = 0; ap < p.planes; ++ap)
+                tma_load_5d(sA + as * kABytes + ap * kAPlane, &tm_x, bFullA + 8 * as, kc * 64, s_src[e], tb * 128, n, ap);
+              if (++as == SA) { as = 0; a_ph ^= 1; }
+            } else {
+              for (int ap = 0; ap < p.planes; ++ap) {
+                mbar_wait(bEmptyA + 8 * as, a_ph ^ 1);
+                mbar_expect_tx(bFullA + 8 * as, kAPlane);
+                tma_load_5d(sA + as * kABytes, &tm_x, bFullA + 8 * as, kc * 64, s_src[e], tb * 128, n, ap);
+                if (++as == SA) { as = 0; a_ph ^= 1; }
+              }
+            }
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ---- B producer: the edge's pre-scaled weight tiles (hi, lo for an A hi stage; hi for an A lo stage) ----
+    if (lane == 0) {
+      int bs = 0, b_ph = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int w = item % p.V;
+        for (int e = s_ptr[w]; e < s_ptr[w + 1]; ++e)
+          for (int kc = 0; kc < KC; ++kc) {
+            if (MERGE) {
+              mbar_wait(bEmptyB + 8 * bs, b_ph ^ 1);
+              mbar_expect_tx(bFullB + 8 * bs, (uint32_t)(p.planes * kBPlane));
+              for (int bp = 0; bp < p.planes; ++bp)
+                tma_load_4d(sB + bs * kBBytes + bp * kBPlane, &tm_w, bFullB + 8 * bs, kc * 64, 0, e, bp);
+              if (++bs == SB) { bs = 0; b_ph ^= 1; }
+            } else {
+              for (int ap = 0; ap < p.planes; ++ap) {
+                const int nb = (ap == 0) ? p.planes : 1;
+                for (int bp = 0; bp < nb; ++bp) {
+                  mbar_wait(bEmptyB + 8 * bs, b_ph ^ 1);
+                  mbar_expect_tx(bFullB + 8 * bs, kBPlane);
+                  tma_load_4d(sB + bs * kBBytes, &tm_w, bFullB + 8 * bs, kc * 64, 0, e, bp);
+                  if (++bs == SB) { bs = 0; b_ph ^= 1; }
+                }
+              }
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    constexpr uint32_t idesc = umma_idesc_bf16(128, CO);
+    int a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, buf = 0, t_ph = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int w = item % p.V;
+      mbar_wait(bTmemEmpty + 8 * buf, t_ph ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * CO;
+      uint32_t acc = 0;
+      for (int e = s_ptr[w]; e < s_ptr[w + 1]; ++e)
+        for (int kc = 0; kc < KC; ++kc) {
+          if (MERGE) {
+            mbar_wait(bFullA + 8 * a_s, a_ph);
+            mbar_wait(bFullB + 8 * b_s, b_ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_hi = umma_desc_lo(sA + a_s * kABytes), a_lo = umma_desc_lo(sA + a_s * kABytes + kAPlane);
+              const uint32_t b_hi = umma_desc_lo(sB + b_s * kBBytes), b_lo = umma_desc_lo(sB + b_s * kBBytes + kBPlane);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tacc, umma_desc_join(a_hi + 2 * k), umma_desc_join(b_hi + 2 * k), idesc, acc | (uint32_t)k);
+              if (p.planes == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tacc, umma_desc_join(a_hi + 2 * k), umma_desc_join(b_lo + 2 * k), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tacc, umma_desc_join(a_lo + 2 * k), umma_desc_join(b_hi + 2 * k), idesc, 1u);
+              }
+              umma_commit(bEmptyB + 8 * b_s);
+              umma_commit(bEmptyA + 8 * a_s);
+            }
+            __syncwarp();
+            acc = 1;
+            if (++b_s == SB) { b_s = 0; b_ph ^= 1; }
+            if (++a_s == SA) { a_s = 0; a_ph ^= 1; }
+            continue;
+          }
+          for (int ap = 0; ap < p.planes; ++ap) {
+            mbar_wait(bFullA + 8 * a_s, a_ph);
+            tc_fence_after();
+            const uint32_t a_lo = umma_desc_lo(sA + a_s * kABytes);
+            const int nb = (ap == 0) ? p.planes : 1;
+            for (int bp = 0; bp < nb; ++bp) {
+              mbar_wait(bFullB + 8 * b_s, b_ph);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t b_lo = umma_desc_lo(sB + b_s * kBBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tacc, umma_desc_join(a_lo + 2 * k), umma_desc_join(b_lo + 2 * k), idesc, acc | (uint32_t)k);
+                umma_commit(bEmptyB + 8 * b_s);
+              }
+              __syncwarp();
+              acc = 1;
+              if (++b_s == SB) { b_s = 0; b_ph ^= 1; }
+            }
+            if (elect_one()) umma_commit(bEmptyA + 8 * a_s);
+            __syncwarp();
+            if (++a_s == SA) { a_s = 0; a_ph ^= 1; }
+          }
+        }
+      if (elect_one()) umma_commit(bTmemFull + 8 * buf);
+      __syncwarp();
+      buf ^= 1;
+      if (buf == 0) t_ph ^= 1;
+    }
+  } else {
+    // ---- epilogue: z = acc + bias, rows (frames) leave through the warp's patch as whole 128-B lines ----
+    const int q = warp & 3;
+    const int h = (warp - 3) >> 2;
+    constexpr int CH = CO / kEpiNH;
+    const int c0 = h * CH;
+    uint8_t *patch = s_patch + (warp - 3) * kPatchBytes;
+    uint8_t *mine = patch + lane * kPatchPitch;
+    int buf = 0, t_ph = 0;
+    float v[16];
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int w = item % p.V;
+      const int tb = (item / p.V) % p.tblocks, n = item / (p.V * p.tblocks);
+      const bool has_edges = s_ptr[w + 1] > s_ptr[w];
+      const int t = tb * 128 + q * 32 + lane;
+      const bool row_ok = t < p.T;
+      const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+      const long long row0 = ((long long)n * p.T + tb * 128 + q * 32) * p.V + w;     // row of lane 0; lane rr: + rr*V
+      const int pstep = p.bias_sw ? p.V : 1;
+      const float4 *bias4 =
+          p.bias ? reinterpret_cast<const float4 *>(p.bias) + (c0 >> 2) * pstep + (p.bias_sw ? w : 0) : nullptr;
+      mbar_wait(bTmemFull + 8 * buf, t_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * CO);
+#pragma unroll 1
+      for (int sb = 0; sb < CH; sb += 32) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int cb = sb + half * 16;
+          tmem_ld16(taddr + c0 + cb, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias4) b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
+            float4 o = has_edges ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            *reinterpret_cast<float4 *>(mine + half * 64 + i * 16) = o;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
+          if ((okmask >> rr) & 1)
+            *reinterpret_cast<float4 *>(p.out + (row0 + (long long)rr * p.V) * CO + c0 + sb + qq * 4) =
+                *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + qq * 16);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTmemEmpty + 8 * buf);
+      buf ^= 1;
+      if (buf == 0) t_ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// LayerNorm(C,V) (+ ReLU) of z fp32 frames as a streaming kernel: one block per frame; output fp32 rows
+// or bf16 hi/lo planes (frame t of trial n stored at frame t + out_t0 of out_T frames).
+struct LnStreamArgs {
+  long long frames;
+  int T, V, C;
+  const float *z;
+  const float *n_wT, *n_bT;       // [C/4][V][4]
+  int relu;
+  float eps;
+  float *out_f32;
+  __nv_bfloat16 *out_hi, *out_lo;
+  int out_T, out_t0;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256, 2) k_ln_stream(LnStreamArgs p) {
+  __shared__ float s_red[32];
+  const long long f = blockIdx.x;
+  const int VC4 = (p.V * p.C) >> 2, C4 = p.C >> 2;
+  const float *zp = p.z + f * (long long)p.V * p.C;
+  float4 a[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < VC4) {
+      a[j] = ld_stream(reinterpret_cast<const float4 *>(zp) + i);
+      s += (a[j].x + a[j].y) + (a[j].z + a[j].w);
+    }
+  }
+  const float inv_n = 1.f / (float)(p.V * p.C), inv_nm1 = 1.f / (float)(p.V * p.C - 1);
+  const float mean = block_sum(s, s_red) * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < VC4) {
+      const float d0 = a[j].x - mean, d1 = a[j].y - mean, d2 = a[j].z - mean, d3 = a[j].w - mean;
+      q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+    }
+  }
+  const float rstd = 1.f / sqrtf(block_sum(q, s_red) * inv_nm1 + p.eps);
+  const float nmr = -mean * rstd;
+  const long long n = f / p.T;
+  const long long fo = p.out_T ? n * p.out_T + (f - n * p.T) + p.out_t0 : f;
+  const long long ob = fo * (long long)p.V * p.C;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < VC4) {
+      const int w = i / C4, g = i - w * C4;
+      const int ti = (g * p.V + w) * 4;
+      const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.n_wT + ti));
+      const float4 o4 = __ldg(reinterpret_cast<const float4 *>(p.n_bT + ti));
+      float4 v;
+      v.x = fmaf(fmaf(a[j].x, rstd, nmr), g4.x, o4.x);
+      v.y = fmaf(fmaf(a[j].y, rstd, nmr), g4.y, o4.y);
+      v.z = fmaf(fmaf(a[j].z, rstd, nmr), g4.z, o4.z);
+      v.w = fmaf(fmaf(a[j].w, rstd, nmr), g4.w, o4.w);
+      if (p.relu) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      if (p.out_f32) {
+        *reinterpret_cast<float4 *>(p.out_f32 + ob + 4 * i) = v;
+      } else {
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2 *>(p.out_hi + ob + 4 * i) =
+            make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+        if (p.out_lo) {
+          const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+          const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+          const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+          *reinterpret_cast<uint2 *>(p.out_lo + ob + 4 * i) =
+              make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+        }
+      }
+    }
+  }
+}
+
+inline int launch_ln_stream(const LnStreamArgs &a, cudaStream_t st) {
+  const int nv = (a.V * a.C / 4 + 255) / 256;
+  if (a.frames <= 0) return 0;
+  if (a.frames > 0x7fffffffLL) return fail("ln stream: too many frames");
+  if (nv <= 2) k_ln_stream<2><<<(unsigned)a.frames, 256, 0, st>>>(a);
+  else if (nv <= 4) k_ln_stream<4><<<(unsigned)a.frames, 256, 0, st>>>(a);
+  else if (nv <= 7) k_ln_stream<7><<<(unsigned)a.frames, 256, 0, st>>>(a);
+  else return fail("ln stream: V*C = %d too large", a.V * a.C);
+  return 0;
+}
+
+inline bool gcnw_supported(int c_in, int c_out, int V, int K) {
+  return (c_out == 64 || c_out == 128 || c_out == 256) && c_in % 64 == 0 && c_in >= 64 && V >= 2 && V <= kGwMaxV &&
+         K >= 1 && (V * c_out / 4 + 255) / 256 <= 7;
+}
+inline bool gcnw_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_GCNW");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
+
+// x planes: bf16 [planes][N][T_full][V][Cin] (the view takes every fstride-th frame, T frames);
+// wsc: k_gcnw_pack tiles [2][cap][CO][Cin]
+template <int CO>
+int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p, int T_full, int fstride, int cap,
+                  cudaStream_t st) {
+  const int V = p.V, kMaxSmem = 232448;
+  p.tblocks = (p.T + 127) / 128;
+  p.items = p.N * p.tblocks * V;
+  const int fixed = kPatchTotal + 1024 + 512 + 1024;
+  constexpr bool MERGE = CO <= 128;
+  constexpr int kA = MERGE ? 2 * 128 * 128 : 128 * 128, kB = MERGE ? 2 * CO * 128 : CO * 128;
+  // weight stages first (they are the long-latency stream for C >= 128), then activation stages
+  int SB = MERGE ? (CO >= 128 ? 2 : 3) : 3;
+  int SA = (kMaxSmem - fixed - SB * kB) / kA;
+  if (SA > (MERGE ? 4 : 8)) SA = MERGE ? 4 : 8;
+  if (SA < 2) return fail("gcnw: shared memory does not fit");
+  if (MERGE && SA >= 4 && (kMaxSmem - fixed - SB * kB - SA * kA) >= kB) ++SB;
+  p.a_stages = SA; p.b_stages = SB;
+  const int smem = fixed + SA * kA + SB * kB;
+  CUtensorMap tm_x, tm_w;
+  const uint64_t xd[5] = {(uint64_t)p.Cin, (uint64_t)V, (uint64_t)p.T, (uint64_t)p.N, (uint64_t)p.planes};
+  const uint64_t xs[4] = {(uint64_t)p.Cin * 2, (uint64_t)fstride * V * p.Cin * 2, (uint64_t)T_full * V * p.Cin * 2,
+                          (uint64_t)p.N * T_full * V * p.Cin * 2};
+  const uint32_t xb[5] = {64, 1, 128, 1, 1};
+  if (make_tmap_bf16(&tm_x, x, 5, xd, xs, xb)) return 1;
+  const uint64_t wd[4] = {(uint64_t)p.Cin, (uint64_t)CO, (uint64_t)cap, 2};
+  const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)cap * CO * p.Cin * 2};
+  const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
+  if (make_tmap_bf16(&tm_w, wsc, 4, wd, wst, wb)) return 1;
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcnw<CO, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_gcnw<CO, MERGE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_w, p);
+  return 0;
+}
+
+inline int launch_gcnw(int CO, const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, const GcnwParams &p, int T_full,
+                       int fstride, int cap, cudaStream_t st) {
+  switch (CO) {
+    case 64: return launch_gcnw_c<64>(x, wsc, p, T_full, fstride, cap, st);
+    case 128: return launch_gcnw_c<128>(x, wsc, p, T_full, fstride, cap, st);
+    case 256: return launch_gcnw_c<256>(x, wsc, p, T_full, fstride, cap, st);
+  }
+  return fail("gcnw: unsupported channel count %d", CO);
+}
+
+}  // namespace tc
+}  // namespace stgcn

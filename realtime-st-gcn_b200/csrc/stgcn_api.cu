@@ -8,6 +8,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_tc_pair.cuh"
 #include "kernels_gcn3.cuh"
+#include "kernels_gcnw.cuh"
 #include "kernels_rt_small.cuh"
 
 using namespace stgcn;
@@ -169,9 +170,13 @@ struct LayerPrep {
   tc::Gcn3Tables *tab = nullptr, *tabr = nullptr;
   __nv_bfloat16 *wg3 = nullptr, *wr3 = nullptr;
   float *bzR = nullptr, *n1R = nullptr, *nrR = nullptr;
+  // graph conv with per-joint pre-scaled weights (kernels_gcnw.cuh): edge tables + weight tiles
+  bool gw = false, gwr = false;
+  tc::GcnwTables *gwtab = nullptr, *gwtabr = nullptr;
+  __nv_bfloat16 *wsc = nullptr, *wscr = nullptr;
 };
 
-LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws) {
+LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws, bool sparse_adj = false) {
   LayerPrep P;
   const bool ln = d.norm == STGCN_NORM_LAYERNORM;
   P.gcn = ln && !d.a_per_sample && tc::gcn_tc_supported(d.c_in, d.c_out, V, K);
@@ -194,7 +199,19 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws) {
   }
   if (P.gcn) P.n1T = ws.take<float>((size_t)2 * d.c_out * V);
   if (P.tcn) P.n2T = ws.take<float>((size_t)2 * d.c_out * V);
-  P.g3 = P.gcn && !d.rt && tc::gcn3_enabled() && tc::gcn3_supported(d.c_in, d.c_out, V, K) &&
+  P.gw = sparse_adj && P.gcn && !d.rt && tc::gcnw_enabled() && tc::gcnw_supported(d.c_in, d.c_out, V, K) &&
+         (d.residual != STGCN_RES_CONV || P.res);
+  P.gwr = P.gw && d.residual == STGCN_RES_CONV;
+  if (P.gw) {
+    const size_t cap = (size_t)tc::gcnw_edge_cap(V);
+    P.gwtab = ws.take<tc::GcnwTables>(1);
+    P.wsc = ws.take<__nv_bfloat16>(2 * cap * d.c_out * d.c_in);
+    if (P.gwr) {
+      P.gwtabr = ws.take<tc::GcnwTables>(1);
+      P.wscr = ws.take<__nv_bfloat16>(2 * cap * d.c_out * d.c_in);
+    }
+  }
+  P.g3 = !P.gw && P.gcn && !d.rt && tc::gcn3_enabled() && tc::gcn3_supported(d.c_in, d.c_out, V, K) &&
          (d.residual != STGCN_RES_CONV || (P.res && tc::gcn3_supported(d.c_in, d.c_out, V, 1)));
   P.g3r = P.g3 && d.residual == STGCN_RES_CONV;
   if (P.g3) {
@@ -235,6 +252,20 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
     tc::k_split_bf16<<<cdiv(nwr, 256), 256, 0, st>>>(d.res_w, P.wr16, nwr);
     STGCN_LAUNCH_OK();
     STGCN_CUDA_OK(cudaMemsetAsync(P.zero, 0, sizeof(float) * d.c_out, st));
+  }
+  if (P.gw) {
+    const int cap = tc::gcnw_edge_cap(V);
+    const long long per = (long long)d.c_out * d.c_in;
+    tc::k_gcnw_tables<<<1, 32, 0, st>>>(d.a_eff, K, V, 0, cap, P.gwtab);
+    STGCN_LAUNCH_OK();
+    tc::k_gcnw_pack<<<cdiv(per * cap, 256), 256, 0, st>>>(d.gcn_w, P.gwtab, d.c_out, d.c_in, cap, P.wsc);
+    STGCN_LAUNCH_OK();
+    if (P.gwr) {
+      tc::k_gcnw_tables<<<1, 32, 0, st>>>(nullptr, 1, V, 1, cap, P.gwtabr);
+      STGCN_LAUNCH_OK();
+      tc::k_gcnw_pack<<<cdiv(per * cap, 256), 256, 0, st>>>(d.res_w, P.gwtabr, d.c_out, d.c_in, cap, P.wscr);
+      STGCN_LAUNCH_OK();
+    }
   }
   if (P.g3) {
     const long long nw = (long long)K * d.c_out * d.c_in;
@@ -283,7 +314,7 @@ constexpr int kHalo = 4;   // halo frames carried on each side of the temporal-c
 int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        int N, int T, Bump &ws, cudaStream_t st, const LayerPrep *pp = nullptr,
                        const stgcn_halo_desc *halo = nullptr, int layer_index = 0, bool x_planes = false,
-                       bool out_planes = false) {
+                       bool out_planes = false, bool sparse_adj = false) {
   if (check_layer(d)) return 1;
   const size_t mark = ws.mark();
   const int T_out = (T - 1) / d.stride + 1;
@@ -291,7 +322,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   const bool bn = d.norm == STGCN_NORM_BATCHNORM;
   LayerPrep local;
   if (!pp && math != STGCN_MATH_FP32) {
-    local = prep_take(d, K, V, ws);
+    local = prep_take(d, K, V, ws, sparse_adj);
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer operands)");
       if (prep_run(d, K, V, local, st)) return 1;
@@ -305,7 +336,8 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   // tensor-core graph-convolution stage: LayerNorm, shared adjacency, C_in % 64 == 0
   const bool tc_gcn = math != STGCN_MATH_FP32 && pp && pp->gcn;
   // graph-conv v3: reference operation order on CTA pairs, input as bf16 planes
-  const bool use_g3 = tc_gcn && tc_tcn && pp->g3;
+  const bool use_gw = tc_gcn && tc_tcn && pp->gw;
+  const bool use_g3 = (tc_gcn && tc_tcn && pp->g3) || use_gw;     // bf16-plane input / residual plumbing (shared)
   STGCN_REQUIRE(use_g3 || (!x_planes && !out_planes), "bf16-plane activations need the graph-conv v3 path");
   const __nv_bfloat16 *xh = nullptr, *xl = nullptr;
   if (use_g3) {
@@ -336,7 +368,34 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   __nv_bfloat16 *u16 = tc_tcn ? ws.take<__nv_bfloat16>((size_t)planes * rows_u * d.c_out) : nullptr;
   __nv_bfloat16 *u16_lo = (tc_tcn && planes == 2 && u16) ? u16 + (size_t)rows_u * d.c_out : nullptr;
   double *sums = bn ? ws.take<double>((size_t)4 * d.c_out) : nullptr;
-  if (use_g3) {
+  if (use_gw) {
+    // GEMM with per-joint pre-scaled weights -> z (fp32), then the streaming LayerNorm + ReLU + split
+    float *zb = ws.take<float>((size_t)rows * d.c_out);
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
+      tc::GcnwParams g{};
+      g.T = T; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
+      g.tab = pp->gwtab;
+      g.bias = pp->bzT; g.bias_sw = 1;
+      g.out = zb;
+      g.debug = debug_mode();
+      {
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcnw(d.c_out, xh, pp->wsc, g, T, 1, tc::gcnw_edge_cap(V), st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      tc::LnStreamArgs l{};
+      l.frames = (long long)N * T; l.T = T; l.V = V; l.C = d.c_out;
+      l.z = zb;
+      l.n_wT = pp->n1T; l.n_bT = pp->n1T + (size_t)d.c_out * V;
+      l.relu = 1; l.eps = kEps;
+      l.out_hi = u16; l.out_lo = u16_lo;
+      if (hf) { l.out_T = T + 2 * hf; l.out_t0 = hf; }
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_ln_stream(l, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+  } else if (use_g3) {
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
       tc::Gcn3Params g{};
@@ -416,9 +475,32 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     const bool res_tc = res_conv && pp->res;
     float *resb = res_conv ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
     float *qr = (res_conv && !res_tc) ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
+    float *qz = (res_tc && use_gw) ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
-      if (res_tc && use_g3) {
+      if (res_tc && use_gw) {
+        // residual 1x1 conv with the same GEMM kernel (identity edges), then LayerNorm_R as a stream
+        tc::GcnwParams g{};
+        g.T = T_out; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
+        g.tab = pp->gwtabr;
+        g.bias = d.res_b; g.bias_sw = 0;
+        g.out = qz;
+        g.debug = debug_mode();
+        {
+          ProfScope ps(KC_GEMM_1X1, st);
+          if (tc::launch_gcnw(d.c_out, xh, pp->wscr, g, T, d.stride, tc::gcnw_edge_cap(V), st)) return 1;
+          STGCN_LAUNCH_OK();
+        }
+        tc::LnStreamArgs l{};
+        l.frames = (long long)N * T_out; l.T = T_out; l.V = V; l.C = d.c_out;
+        l.z = qz;
+        l.n_wT = pp->nrT; l.n_bT = pp->nrT + (size_t)d.c_out * V;
+        l.relu = 0; l.eps = kEps;
+        l.out_f32 = resb;
+        ProfScope ps(KC_FRAME, st);
+        if (tc::launch_ln_stream(l, st)) return 1;
+        STGCN_LAUNCH_OK();
+      } else if (res_tc && use_g3) {
         tc::Gcn3Params g{};
         g.T = T_out; g.V = V; g.Cin = d.c_in; g.planes = planes;
         g.tab = pp->tabr;
@@ -826,7 +908,7 @@ inline bool use_prepared(const stgcn_model_desc &m) {
 size_t model_prepare_layout(const stgcn_model_desc &m, void *base, size_t cap, LayerPrep *out) {
   Bump pb(base, cap);
   for (int i = 0; i < m.num_layers; ++i) {
-    LayerPrep P = prep_take(m.layers[i], m.partitions, m.num_joints, pb);
+    LayerPrep P = prep_take(m.layers[i], m.partitions, m.num_joints, pb, (m.reserved & 2) != 0);
     if (out) out[i] = P;
   }
   return pb.peak;
@@ -857,8 +939,9 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     int tt = T;
     for (int i = 0; i < m.num_layers; ++i) {
       const stgcn_layer_desc &d = m.layers[i];
-      const LayerPrep P = prep_take(d, K, V, pm);
-      g3[i] = m.math != STGCN_MATH_FP32 && P.g3 && P.tcn && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, tt);
+      const LayerPrep P = prep_take(d, K, V, pm, (m.reserved & 2) != 0);
+      g3[i] = m.math != STGCN_MATH_FP32 && (P.g3 || P.gw) && P.tcn &&
+              tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, tt);
       tt = (tt - 1) / d.stride + 1;
     }
   }
@@ -873,10 +956,10 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     STGCN_REQUIRE(!d.rt, "stgcn_model_forward needs ST-GCN layers (rt == 0)");
     STGCN_REQUIRE(!d.a_per_sample, "per-sample adjacency is only supported by the layer-level API");
     LayerPrep P;
-    if (have) P = prep_take(d, K, V, pb);
+    if (have) P = prep_take(d, K, V, pb, (m.reserved & 2) != 0);
     const bool out_planes = g3[i] && g3[i + 1];
     if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st, have ? &P : nullptr, halo, i,
-                           x_planes, out_planes))
+                           x_planes, out_planes, (m.reserved & 2) != 0))
       return 1;
     x_planes = out_planes;
     t = (t - 1) / d.stride + 1;

@@ -89,6 +89,10 @@ class Model(nn.Module):
         m.fcn_out_w, m.fcn_out_b = self.fcn_out.weight.data_ptr(), self.fcn_out.bias.data_ptr()
         m.layers = ctypes.cast(layers, ctypes.POINTER(_lib.LayerDesc))
         keep.append(layers)
+        # host-known sparsity of the partitioned adjacency (the edge importance can only remove entries):
+        # bit 1 allows the kernels that hold one pre-scaled weight copy per edge (at most 6 V edges)
+        if int((self.graph.A != 0).sum()) <= 6 * self.A.size(1):
+            m.reserved |= 2
         if self.fcn_in.weight.is_cuda:
             keep.append(_lib.prepare_model(m, self.fcn_in.weight.device))
         self._desc = (fp, (m, keep))
