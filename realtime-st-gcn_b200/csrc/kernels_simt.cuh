@@ -534,6 +534,8 @@ struct RtUpdateArgs {
   const float *n_wT, *n_bT;       // LayerNorm affine as [C/4][V][4]
   int res_mode;                   // 0 none, 1 raw rows, 2 LayerNorm_R(rows)
   const float *res;               // [B*V, C]
+  const __nv_bfloat16 *res_hi, *res_lo;   // res_mode 1 with the rows as bf16 hi/lo planes (res == null)
+  __nv_bfloat16 *out_hi, *out_lo; // also / instead write the output as bf16 planes (next layer's GEMM operand)
   const float *r_wT, *r_bT;       // affine of the residual norm, [C/4][V][4]
   float eps;
   float *out;                     // [B*V, C]
@@ -544,6 +546,12 @@ __device__ __forceinline__ float4 ld_nc_stream4(const float *p) {
   asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ uint2 ld_nc_stream2(const __nv_bfloat16 *p) {
+  uint2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
 
@@ -567,14 +575,32 @@ __global__ void __launch_bounds__(256, 2) k_rt_update(RtUpdateArgs p) {
       zz[j] = ld_nc_stream4(zp + 4 * i);
       ff[j] = ld_nc_stream4(fp + 4 * i);
       a[j] = ld_nc_stream4(ap + 4 * i);
-      if (p.res_mode) r[j] = ld_nc_stream4(rp + 4 * i);
+      if (rp) {
+        r[j] = ld_nc_stream4(rp + 4 * i);
+      } else if (p.res_mode == 1 && p.res_hi) {
+        // raw bits only: converting here would make every iteration wait for its own load and
+        // serialise the loads of the following iterations
+        const uint2 rh = ld_nc_stream2(p.res_hi + base + 4 * i);
+        const uint2 rl = p.res_lo ? ld_nc_stream2(p.res_lo + base + 4 * i) : make_uint2(0u, 0u);
+        r[j] = make_float4(__uint_as_float(rh.x), __uint_as_float(rh.y), __uint_as_float(rl.x), __uint_as_float(rl.y));
+      }
     }
   }
   float s = 0.f, sr = 0.f;
+  const bool res_planes = p.res_mode == 1 && !rp && p.res_hi;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int i = threadIdx.x + 256 * j;
     if (i < VC4) {
+      if (res_planes) {
+        const uint32_t h0 = __float_as_uint(r[j].x), h1 = __float_as_uint(r[j].y);
+        const uint32_t l0 = __float_as_uint(r[j].z), l1 = __float_as_uint(r[j].w);
+        const float2 a01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&h0));
+        const float2 a23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&h1));
+        const float2 b01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&l0));
+        const float2 b23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&l1));
+        r[j] = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+      }
       a[j].x = (a[j].x + zz[j].x) + (-ff[j].x);
       a[j].y = (a[j].y + zz[j].y) + (-ff[j].y);
       a[j].z = (a[j].z + zz[j].z) + (-ff[j].z);
@@ -602,7 +628,7 @@ __global__ void __launch_bounds__(256, 2) k_rt_update(RtUpdateArgs p) {
   }
   const float rstd = 1.f / sqrtf(block_sum(q, s_red) * inv_nm1 + p.eps);
   if (p.res_mode == 2) rstd_r = 1.f / sqrtf(block_sum(qr, s_red) * inv_nm1 + p.eps);
-  float *op = p.out + base;
+  float *op = p.out ? p.out + base : nullptr;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int i = threadIdx.x + 256 * j;
@@ -627,7 +653,19 @@ __global__ void __launch_bounds__(256, 2) k_rt_update(RtUpdateArgs p) {
         v.w += (r[j].w - mean_r) * rstd_r * rg.w + ro.w;
       }
       v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-      *reinterpret_cast<float4 *>(op + 4 * i) = v;
+      if (p.out) *reinterpret_cast<float4 *>(op + 4 * i) = v;
+      if (p.out_hi) {
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2 *>(p.out_hi + base + 4 * i) =
+            make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+        if (p.out_lo) {
+          const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+          const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+          const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+          *reinterpret_cast<uint2 *>(p.out_lo + base + 4 * i) =
+              make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+        }
+      }
     }
   }
 }

@@ -199,7 +199,7 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws, bool spar
   }
   if (P.gcn) P.n1T = ws.take<float>((size_t)2 * d.c_out * V);
   if (P.tcn) P.n2T = ws.take<float>((size_t)2 * d.c_out * V);
-  P.gw = sparse_adj && P.gcn && !d.rt && tc::gcnw_enabled() && tc::gcnw_supported(d.c_in, d.c_out, V, K) &&
+  P.gw = sparse_adj && P.gcn && tc::gcnw_enabled() && tc::gcnw_supported(d.c_in, d.c_out, V, K) &&
          (d.residual != STGCN_RES_CONV || P.res);
   P.gwr = P.gw && d.residual == STGCN_RES_CONV;
   if (P.gw) {
@@ -656,7 +656,8 @@ inline bool rt_split_enabled() {
 // x [B*V, c_in] -> out [B*V, c_out]; fifo [F][B][V][C], acc [S][B][V][C]; counter[B].
 int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st,
-                       const LayerPrep *pp = nullptr) {
+                       const LayerPrep *pp = nullptr, bool use_gw = false, bool x_planes = false,
+                       bool out_planes = false) {
   if (check_layer(d)) return 1;
   STGCN_REQUIRE(d.norm == STGCN_NORM_LAYERNORM,
                 "continual inference needs LayerNorm: batch statistics of a single frame are undefined "
@@ -679,6 +680,65 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     const long long rows = (long long)B * V;
     float *zb = ws.take<float>((size_t)rows * d.c_out);
     float *qr = d.residual == STGCN_RES_CONV ? ws.take<float>((size_t)rows * d.c_out) : nullptr;
+    STGCN_REQUIRE(use_gw || (!x_planes && !out_planes), "rt layer: bf16-plane activations need the per-joint-weight GEMM");
+    if (use_gw && !ws.measuring()) {
+      // ---- GEMM with per-joint pre-scaled weights (kernels_gcnw.cuh): streams are the frames of one
+      // trial, the input arrives as bf16 planes ----
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer)");
+      STGCN_REQUIRE(pp->gw && x_planes, "rt layer: per-joint-weight GEMM needs prepared operands and plane input");
+      const __nv_bfloat16 *xh = reinterpret_cast<const __nv_bfloat16 *>(x);
+      const __nv_bfloat16 *xl = planes == 2 ? xh + (size_t)rows * d.c_in : nullptr;
+      const int cap = tc::gcnw_edge_cap(V);
+      if (qr) {
+        tc::GcnwParams g{};
+        g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = 1;
+        g.tab = pp->gwtabr;
+        g.out = qr;                            // no bias (rtstgcn.py:503)
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcnw(d.c_out, xh, pp->wscr, g, B, 1, cap, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      {
+        tc::GcnwParams g{};
+        g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = 1;
+        g.tab = pp->gwtab;
+        g.bias = pp->bzT; g.bias_sw = 1;
+        g.out = zb;
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcnw(d.c_out, xh, pp->wsc, g, B, 1, cap, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      RtUpdateArgs u{};
+      u.B = B; u.V = V; u.C = d.c_out;
+      u.z = zb;
+      u.fifo = fifo; u.acc = acc; u.counter = counter;
+      u.F = d.stride * (d.kernel - 1) + 1;
+      u.S = d.stride;
+      u.slot = rows * d.c_out;
+      u.n_wT = pp->n1T; u.n_bT = pp->n1T + (size_t)d.c_out * V;
+      if (d.residual == STGCN_RES_IDENTITY) { u.res_mode = 1; u.res_hi = xh; u.res_lo = xl; }
+      else if (d.residual == STGCN_RES_CONV) {
+        u.res_mode = 2; u.res = qr;
+        u.r_wT = pp->nrT; u.r_bT = pp->nrT + (size_t)d.c_out * V;
+      }
+      u.eps = kEps;
+      if (debug_mode() & 256) { u.res_mode = 0; }                     // timing experiments only
+      if (out_planes && !(debug_mode() & 512)) {
+        u.out_hi = reinterpret_cast<__nv_bfloat16 *>(out);
+        u.out_lo = planes == 2 ? u.out_hi + (size_t)rows * d.c_out : nullptr;
+      } else {
+        u.out = out;
+      }
+      ProfScope ps(KC_FRAME, st);
+      if (launch_rt_update(u, st)) return 1;
+      STGCN_LAUNCH_OK();
+      ws.release(mark0);
+      return 0;
+    }
+    if (use_gw) {          // measuring pass: same workspace as above
+      ws.release(mark0);
+      return 0;
+    }
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (rt layer)");
       if (qr) {
@@ -983,10 +1043,22 @@ size_t model_chunk_bytes(const stgcn_model_desc &m, int n, int T) {
 // rows (trial-frames * V) one chunk of trials should carry when chunking is allowed
 constexpr long long kChunkRows = 3200000;
 
+// STGCN_CHUNK_ROWS overrides the chunk size (tuning aid: smaller chunks keep more of a layer's
+// intermediates in the 126 MB L2, larger ones amortise launches and tails)
+inline long long chunk_rows() {
+  static long long r = -1;
+  if (r < 0) {
+    const char *e = getenv("STGCN_CHUNK_ROWS");
+    r = e ? atoll(e) : kChunkRows;
+    if (r <= 0) r = kChunkRows;
+  }
+  return r;
+}
+
 int default_chunk(const stgcn_model_desc &m, int N, int T) {
   if (m.norm == STGCN_NORM_BATCHNORM) return N;  // batch statistics span the whole call
   long long per_trial = (long long)T * m.num_joints;
-  long long n = kChunkRows / (per_trial > 0 ? per_trial : 1);
+  long long n = chunk_rows() / (per_trial > 0 ? per_trial : 1);
   if (n < 1) n = 1;
   if (n > N) n = N;
   return (int)n;
@@ -1061,9 +1133,9 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
       const stgcn_layer_desc &d = m.layers[i];
       LayerPrep lp;
       if (have) {
-        lp = prep_take(d, K, V, pb);
+        lp = prep_take(d, K, V, pb, (m.reserved & 2) != 0);
       } else {
-        lp = prep_take(d, K, V, ws);
+        lp = prep_take(d, K, V, ws, (m.reserved & 2) != 0);
         if (!ws.measuring()) {
           STGCN_REQUIRE(!ws.overflow, "workspace too small (rt step operands)");
           if (prep_run(d, K, V, lp, st)) return 1;
@@ -1108,7 +1180,19 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
   }
   float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
   const bool have = use_prepared(m);
-  if (embed(m, x, buf[0], B, 1, ws, st)) return 1;
+  const bool sparse = (m.reserved & 2) != 0;
+  // per-joint-weight GEMM path: all layers or none (the activations then travel as bf16 planes)
+  bool all_gw = have && sparse && m.math != STGCN_MATH_FP32 && rt_split_enabled() && embed_warp_path(m);
+  {
+    Bump pm(nullptr, 0);
+    for (int i = 0; i < m.num_layers && all_gw; ++i) {
+      const stgcn_layer_desc &d = m.layers[i];
+      const LayerPrep Q = prep_take(d, K, V, pm, sparse);
+      all_gw = Q.gw && (d.residual != STGCN_RES_CONV || Q.res) && rt_update_supported(V, d.c_out);
+    }
+  }
+  const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
+  if (embed(m, x, buf[0], B, 1, ws, st, nullptr, all_gw ? planes : 0)) return 1;
   char *sb = static_cast<char *>(state);
   int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters);
   int cur = 0;
@@ -1119,9 +1203,10 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     float *fifo = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.fifo[i]);
     float *acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]);
     LayerPrep P;
-    if (have) P = prep_take(d, K, V, pb);
+    if (have) P = prep_take(d, K, V, pb, sparse);
+    const bool last = i + 1 == m.num_layers;
     if (rt_layer_step_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], fifo, acc, counter, B, ws, st,
-                           have ? &P : nullptr))
+                           have ? &P : nullptr, all_gw, all_gw, all_gw && !last))
       return 1;
     cur ^= 1;
   }

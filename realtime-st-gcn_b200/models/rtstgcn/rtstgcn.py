@@ -121,6 +121,8 @@ class Model(nn.Module):
         m.norm = _lib.NORM_LAYERNORM if self.normalization == 'LayerNorm' else _lib.NORM_BATCHNORM
         m.math = _lib.MATH_NAMES[self.math]
         m.reserved = 0 if self.small_batch_kernel else 1
+        if int((self.graph.A != 0).sum()) <= 6 * self.A.size(1):      # sparse adjacency: per-joint-weight GEMM allowed
+            m.reserved |= 2
         nin = self.norm_in if self.normalization == 'LayerNorm' else self.norm_in.norm
         m.norm_in_w, m.norm_in_b = nin.weight.data_ptr(), nin.bias.data_ptr()
         m.fcn_in_w, m.fcn_in_b = self.fcn_in.weight.data_ptr(), self.fcn_in.bias.data_ptr()
