@@ -1717,7 +1717,10 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
     // temporal class in bf16 mode (one MMA per product: the kernel is epilogue-bound), +1 % in
     // bf16x3 mode (MMA / operand-bound; fewer weight stages and 96 registers per thread cost more
     // than the second set gains) -- so only bf16 mode uses it unless STGCN_TCN_SETS forces it.
-    const int want = tcn_sets_wanted() ? tcn_sets_wanted() : (p.planes == 1 ? 2 : 1);
+    // (also with bf16-plane residual / output: the extra split and unpack work makes the C = 64 epilogue the
+    // bottleneck again, +1.5 % on the whole step)
+    const int want = tcn_sets_wanted() ? tcn_sets_wanted()
+                                       : ((p.planes == 1 || p.epi.res_hi || (p.epi.out_hi && !p.epi.out_f32)) ? 2 : 1);
     int sets = (p.NT == 2 && want >= 2 &&
                 (kMaxSmem - 2 * p.a_stage_bytes - 2 * (kPartBytes + kPatchTotal) - 1536) / kBHalf >= 3) ? 2 : 1;
     const int fixed_p = sets * (kPartBytes + kPatchTotal) + 512 + 1024;
