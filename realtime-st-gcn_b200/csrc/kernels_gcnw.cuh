@@ -128,6 +128,13 @@ __global__ void __launch_bounds__(kGwThreads, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.Cin / 64;
+  if (__ldg(&p.tab->nedge) < 0) {
+    // the caller vouched for a sparse adjacency (stgcn_model_desc.reserved bit 1) that is not sparse:
+    // fail loudly instead of computing with a truncated edge list
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+      printf("stgcn_b200: adjacency has more than 6*V non-zeros but the model descriptor says it is sparse\n");
+    __trap();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
@@ -360,6 +367,8 @@ __global__ void __launch_bounds__(256, 2) k_ln_stream(LnStreamArgs p) {
   __shared__ float s_red[32];
   const long long f = blockIdx.x;
   const int VC4 = (p.V * p.C) >> 2, C4 = p.C >> 2;
+  const bool c4_pow2 = (C4 & (C4 - 1)) == 0;
+  const int c4_sh = __ffs(C4) - 1;
   const float *zp = p.z + f * (long long)p.V * p.C;
   float4 a[NV];
   float s = 0.f;
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(256, 2) k_ln_stream(LnStreamArgs p) {
   for (int j = 0; j < NV; ++j) {
     const int i = threadIdx.x + 256 * j;
     if (i < VC4) {
-      const int w = i / C4, g = i - w * C4;
+      const int w = c4_pow2 ? (i >> c4_sh) : (i / C4), g = i - w * C4;   // no integer division for C = 64/128/256
       const int ti = (g * p.V + w) * 4;
       const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.n_wT + ti));
       const float4 o4 = __ldg(reinterpret_cast<const float4 *>(p.n_bT + ti));

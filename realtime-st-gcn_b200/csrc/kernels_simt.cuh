@@ -560,6 +560,8 @@ __global__ void __launch_bounds__(256, 2) k_rt_update(RtUpdateArgs p) {
   __shared__ float s_red[32];
   const int b = blockIdx.x;
   const int VC4 = (p.V * p.C) >> 2, C4 = p.C >> 2;
+  const bool c4_pow2 = (C4 & (C4 - 1)) == 0;
+  const int c4_sh = __ffs(C4) - 1;
   const int cnt = __ldg(p.counter + b);
   const long long base = (long long)b * p.V * p.C;
   float *fp = p.fifo + (long long)(cnt % p.F) * p.slot + base;
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(256, 2) k_rt_update(RtUpdateArgs p) {
   for (int j = 0; j < NV; ++j) {
     const int i = threadIdx.x + 256 * j;
     if (i < VC4) {
-      const int w = i / C4, g = i - w * C4;                 // joint, channel group
+      const int w = c4_pow2 ? (i >> c4_sh) : (i / C4), g = i - w * C4;   // no integer division for C = 64/128/256                 // joint, channel group
       const int ti = (g * p.V + w) * 4;                     // [C/4][V][4]
       const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.n_wT + ti));
       const float4 o4 = __ldg(reinterpret_cast<const float4 *>(p.n_bT + ti));
