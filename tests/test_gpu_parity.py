@@ -647,17 +647,21 @@ def test_stgcn_sliding_windows(pkg, syn, cuda):
     assert rel_err(out[0, :, pick].t().unsqueeze(-1), ref) < TOL
 
 
-# ------------------------------------------------------------------ opt-in graph-conv v3 path
-def test_stgcn_model_gcn3_path_subprocess(cuda):
-    """The opt-in graph-conv v3 kernels (STGCN_GCN3=1: reference operation order on CTA pairs, bf16-plane
-    activations between layers) against the oracle: models of growing depth incl. strided /
-    channel-changing layers, both arithmetic modes.  The switch is read once per process, so the
-    check runs tools/debug_g3.py in a child process."""
+# ------------------------------------------------------------------ non-default graph-conv paths
+@pytest.mark.parametrize('switches', [{'STGCN_GCNW': '0'}, {'STGCN_GCNW': '0', 'STGCN_GCN3': '1'}],
+                         ids=['fused-v2', 'opt-in-v3'])
+def test_stgcn_model_other_graphconv_paths_subprocess(cuda, switches):
+    """Model forwards default to the per-joint-weight GEMM + streaming LayerNorm (kernels_gcnw.cuh).  The two
+    other graph-conv implementations stay covered at model level: the fused k_gcn_tc2 kernels
+    (STGCN_GCNW=0) and the opt-in v3 kernels (STGCN_GCN3=1: reference operation order on CTA pairs, bf16-plane
+    activations) -- models of growing depth incl. strided / channel-changing layers, both arithmetic
+    modes, against the oracle.  The switches are read once per process, so tools/debug_g3.py runs in a
+    child process."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, STGCN_GCN3='1')
+    env = dict(os.environ, **switches)
     out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'debug_g3.py')], env=env, capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]

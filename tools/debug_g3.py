@@ -1,4 +1,5 @@
-"""Development aid: ST-GCN models of growing depth on the GPU path vs the oracle (GPU box only)."""
+"""ST-GCN models of growing depth on the GPU path vs the oracle (GPU box only); run by
+tests/test_gpu_parity.py in child processes with the graph-conv path switches set."""
 import importlib, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
