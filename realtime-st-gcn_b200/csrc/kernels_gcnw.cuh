@@ -7,16 +7,38 @@
 // per edge, built once per parameter set), and a tile is 128 consecutive frames of ONE output joint
 // w: its A operands are plain strided TMA boxes of the bf16-plane input (joint v_e, 128 frames), its
 // B operands the edge's weight tiles.  No CUDA-core arithmetic before the MMA, no gather after it; the
-// epilogue only adds the bias and stores z (fp32, rows strided by V).  LayerNorm(C,V) + ReLU + the
-// bf16 split for the temporal kernel run in the streaming kernel k_ln_stream (one block per frame),
-// i.e. the stage trades one extra HBM round trip of z for kernels that are bandwidth- / MMA-bound
-// instead of latency-bound.  Tree-structured adjacency only: the weight buffer
-// holds 6*V edges.
+// epilogue only adds the bias and stores z (fp32).
+//
+// LayerNorm(C,V) needs all V joints of a frame, i.e. V different tiles.  Default (FUSE): the stage is
+// ONE persistent kernel with two halves connected through L2.  The GEMM epilogue writes its z tile into
+// a ring of frame-group slots (a group = the V tiles of 128 frames; a few tens of MB, so the lines stay
+// dirty in the 126 MB L2 and are overwritten there) together with each row's partial statistics
+// (mean, M2 over its channels), and counts the tile in ready[group].  Eight more warps per CTA (the
+// "LN warps") take the groups round-robin: wait for ready[group] == all tiles, merge the row partials
+// of every frame (Chan et al., exact), then stream the slot once -- LayerNorm affine, ReLU, bf16 split
+// -- into the temporal kernel's operand planes and release the slot (done[group]).  z never travels
+// to HBM and back, and the HBM-bound normalisation overlaps the MMA-bound GEMM on the same SMs.
+// Producers only ever wait for consumers of EARLIER groups and consumers never wait for producers of
+// later ones, so the schedule cannot deadlock as long as all CTAs are resident (cooperative launch).
+// Two-kernel form (STGCN_GCNW_FUSE=0, and the continual step, whose state update is its own kernel):
+// z goes to HBM and k_ln_stream (one block per frame) normalises it.
+// Tree-structured adjacency only: the weight buffer holds 6*V edges.
 #pragma once
 #include "kernels_tc.cuh"
 
 namespace stgcn {
 namespace tc {
+
+// fp32 rows -> bf16 hi/lo planes (layer-level entry points; the model path writes planes directly)
+__global__ void k_rows_to_planes(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi,
+                                 __nv_bfloat16 *__restrict__ lo, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  __nv_bfloat16 h, l;
+  split_bf16(x[i], h, l);
+  hi[i] = h;
+  if (lo) lo[i] = l;
+}
 
 constexpr int kGwMaxV = 32;
 constexpr int kGwEdgeCap = 6 * kGwMaxV;
@@ -94,15 +116,61 @@ struct GcnwParams {
   int bias_sw;
   float *out;                   // z fp32 rows [(n*T + t)*V + w][CO]
   int debug;
+  // fused LayerNorm stage (k_gcnw<.., FUSE = true>)
+  float *zring;                 // [R][128 frames][V][CO] fp32
+  float2 *sring;                // [R][128][V][kEpiNH] (mean, M2) of every (frame, joint, column group)
+  unsigned *ready, *done;       // [N * tblocks] tile-arrival count / slot-released flag per frame group
+  int R;                        // ring slots
+  const float *n_wT, *n_bT;     // LayerNorm affine, [C/4][V][4]
+  int relu;
+  float eps;
+  float *out_f32;               // normalised output: fp32 rows, or
+  __nv_bfloat16 *out_hi, *out_lo;   // bf16 hi / lo planes (frame t of trial n at frame t + out_t0 of out_T)
+  int out_T, out_t0;
 };
+
+// ---- inter-CTA flags of the fused stage -------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded spin (a protocol bug must trap, never hang the GPU)
+template <bool ACQ>
+__device__ __forceinline__ void wait_flag(const unsigned *p, unsigned target, unsigned have) {
+  long long t0 = 0;
+  unsigned spins = 0;
+  while (have < target) {
+    __nanosleep(200);
+    have = ACQ ? ld_acquire_gpu(p) : ld_relaxed_gpu(p);
+    if ((++spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ll) {
+        printf("stgcn_b200: gcnw flag timeout (block %d thread %d have %u want %u)\n", blockIdx.x, threadIdx.x, have,
+               target);
+        __trap();
+      }
+    }
+  }
+}
+constexpr int kGwLnThreads = 256;     // LN warps of the fused stage
 
 constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B producer, 3.. epilogue
 
 // MERGE (C_out <= 128): one activation stage holds both bf16 planes of an (edge, 64-channel chunk)
 // and one weight stage both weight planes, so the MMA issuer waits on two barriers per twelve MMAs
 // instead of five per twelve, and the weight hi plane is loaded once instead of twice.
-template <int CO, bool MERGE>
-__global__ void __launch_bounds__(kGwThreads, 1)
+template <int CO, bool MERGE, bool FUSE>
+__global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
     k_gcnw(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GcnwParams p) {
   constexpr int kAPlane = 128 * 128;            // [128 frames][64 ch] bf16
   constexpr int kBPlane = CO * 128;             // [CO][64 ch] bf16
@@ -116,7 +184,8 @@ __global__ void __launch_bounds__(kGwThreads, 1)
   const uint32_t sB = sA + SA * kABytes;
   const uint32_t sPatch = sB + SB * kBBytes;
   const uint32_t sTab = sPatch + kPatchTotal;                    // ptr[33] + src[192]
-  const uint32_t sBar = sTab + 1024;
+  const uint32_t sMr = sTab + 1024;                              // FUSE: (mean, rstd) of the group's 128 frames
+  const uint32_t sBar = sMr + 1024;
   const uint32_t bTmemFull = sBar, bTmemEmpty = sBar + 16;
   const uint32_t bFullA = sBar + 32, bEmptyA = bFullA + 8 * SA;
   const uint32_t bFullB = bEmptyA + 8 * SA, bEmptyB = bFullB + 8 * SB;
@@ -125,6 +194,7 @@ __global__ void __launch_bounds__(kGwThreads, 1)
   uint8_t *s_patch = gen_base + (sPatch - smem_base);
   int *s_ptr = reinterpret_cast<int *>(gen_base + (sTab - smem_base));
   int *s_src = s_ptr + 40;
+  float2 *s_mr = reinterpret_cast<float2 *>(gen_base + (sMr - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.Cin / 64;
@@ -284,7 +354,7 @@ __global__ void __launch_bounds__(kGwThreads, 1)
       buf ^= 1;
       if (buf == 0) t_ph ^= 1;
     }
-  } else {
+  } else if (warp < 3 + 4 * kEpiNH) {
     // ---- epilogue: z = acc + bias, rows (frames) leave through the warp's patch as whole 128-B lines ----
     const int q = warp & 3;
     const int h = (warp - 3) >> 2;
@@ -296,18 +366,34 @@ __global__ void __launch_bounds__(kGwThreads, 1)
     float v[16];
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int w = item % p.V;
-      const int tb = (item / p.V) % p.tblocks, n = item / (p.V * p.tblocks);
+      const int grp = item / p.V;                                  // frame group (n, tb)
+      const int tb = grp % p.tblocks, n = grp / p.tblocks;
       const bool has_edges = s_ptr[w + 1] > s_ptr[w];
       const int t = tb * 128 + q * 32 + lane;
       const bool row_ok = t < p.T;
       const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-      const long long row0 = ((long long)n * p.T + tb * 128 + q * 32) * p.V + w;     // row of lane 0; lane rr: + rr*V
+      // FUSE: rows go to the group's ring slot [128 frames][V][CO]; otherwise to the z tensor
+      const int slot = FUSE ? grp % p.R : 0;
+      float *zout = FUSE ? p.zring + (size_t)slot * (128 * p.V) * CO : p.out;
+      const long long row0 = FUSE ? (long long)(q * 32) * p.V + w
+                                  : ((long long)n * p.T + tb * 128 + q * 32) * p.V + w;   // row of lane 0; lane rr: + rr*V
       const int pstep = p.bias_sw ? p.V : 1;
       const float4 *bias4 =
           p.bias ? reinterpret_cast<const float4 *>(p.bias) + (c0 >> 2) * pstep + (p.bias_sw ? w : 0) : nullptr;
+      // the slot must have been released by the LN warps that read its previous group; the flag load is
+      // issued before the accumulator wait so that its L2 latency is hidden.  Relaxed on purpose: only
+      // stores follow (they cannot be speculated), and an acquire would invalidate the L1 that holds
+      // the bias tables once per tile.
+      unsigned freed = 1;
+      if (FUSE && grp >= p.R && lane == 0) freed = ld_relaxed_gpu(p.done + (grp - p.R));
       mbar_wait(bTmemFull + 8 * buf, t_ph);
       tc_fence_after();
+      if (FUSE) {
+        if (grp >= p.R && lane == 0) wait_flag<false>(p.done + (grp - p.R), 1u, freed);
+        __syncwarp();
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * CO);
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;          // FUSE: statistics of this row's CH columns about their first value
 #pragma unroll 1
       for (int sb = 0; sb < CH; sb += 32) {
 #pragma unroll
@@ -320,6 +406,12 @@ __global__ void __launch_bounds__(kGwThreads, 1)
             if (bias4) b4 = __ldg(bias4 + ((cb >> 2) + i) * pstep);
             float4 o = has_edges ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (FUSE) {
+              if (cb == 0 && i == 0) shift = o.x;
+              const float d0 = o.x - shift, d1 = o.y - shift, d2 = o.z - shift, d3 = o.w - shift;
+              s1 += (d0 + d1) + (d2 + d3);
+              s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+            }
             *reinterpret_cast<float4 *>(mine + half * 64 + i * 16) = o;
           }
         }
@@ -328,7 +420,7 @@ __global__ void __launch_bounds__(kGwThreads, 1)
         for (int i = 0; i < 8; ++i) {
           const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
           if ((okmask >> rr) & 1)
-            *reinterpret_cast<float4 *>(p.out + (row0 + (long long)rr * p.V) * CO + c0 + sb + qq * 4) =
+            *reinterpret_cast<float4 *>(zout + (row0 + (long long)rr * p.V) * CO + c0 + sb + qq * 4) =
                 *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + qq * 16);
         }
         __syncwarp();
@@ -336,8 +428,116 @@ __global__ void __launch_bounds__(kGwThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bTmemEmpty + 8 * buf);
+      if (FUSE) {
+        // publish the row partial (mean, M2), then count this warp's share of the tile in ready[group]
+        if (row_ok) {
+          const float m_r = shift + s1 * (1.f / (float)CH);
+          const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)CH), 0.f);
+          p.sring[(((size_t)slot * 128 + q * 32 + lane) * p.V + w) * kEpiNH + h] = make_float2(m_r, M2_r);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.ready + grp, 1u);
+      }
       buf ^= 1;
       if (buf == 0) t_ph ^= 1;
+    }
+  } else if (FUSE) {
+    // ---- LN warps: normalise complete frame groups out of their ring slots ----
+    constexpr int C4 = CO / 4, kSh = (CO == 64) ? 4 : (CO == 128 ? 5 : 6);
+    const int lt = threadIdx.x - kGwThreads, lw = lt >> 5;
+    const int V = p.V, NP = V * kEpiNH;                     // row partials per frame
+    const int groups = p.N * p.tblocks;
+    const unsigned target = (unsigned)(V * 4 * kEpiNH);     // epilogue warps per group
+    const uint32_t vmagic = (uint32_t)((0x100000000ull + (unsigned)V - 1) / (unsigned)V);   // x / V for x < 65536
+    const float inv_np = 1.f / (float)NP, inv_cv = 1.f / (float)(V * CO - 1);
+    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+      const int slot = grp % p.R;
+      const int tb = grp % p.tblocks, n = grp / p.tblocks;
+      const int nf = p.T - tb * 128 < 128 ? p.T - tb * 128 : 128;
+      if (lt == 0) {
+        // relaxed polls (an acquire per poll would invalidate the SM's L1 under the epilogue warps), then
+        // one fence: relaxed load + fence = acquire.  The slot is read with ld.global.cg (L2) anyway.
+        wait_flag<false>(p.ready + grp, target, ld_relaxed_gpu(p.ready + grp));
+        __threadfence();
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
+      // per-frame statistics: warp lw merges the V * kEpiNH row partials of frames lw, lw + 8, ...
+      const float2 *sp = p.sring + (size_t)slot * 128 * NP;
+      for (int f = lw; f < nf; f += kGwLnThreads / 32) {
+        const float2 a0 = lane < NP ? __ldcg(sp + (size_t)f * NP + lane) : make_float2(0.f, 0.f);
+        const float2 a1 = lane + 32 < NP ? __ldcg(sp + (size_t)f * NP + lane + 32) : make_float2(0.f, 0.f);
+        const float ref = __shfl_sync(0xffffffffu, a0.x, 0);
+        const float e0 = lane < NP ? a0.x - ref : 0.f, e1 = lane + 32 < NP ? a1.x - ref : 0.f;
+        float sd = e0 + e1, sdd = fmaf(e0, e0, e1 * e1), sm2 = a0.y + a1.y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sd += __shfl_xor_sync(0xffffffffu, sd, o);
+          sdd += __shfl_xor_sync(0xffffffffu, sdd, o);
+          sm2 += __shfl_xor_sync(0xffffffffu, sm2, o);
+        }
+        const float mean = ref + sd * inv_np;
+        const float tq = sm2 + (float)(CO / kEpiNH) * fmaxf(sdd - sd * sd * inv_np, 0.f);
+        if (lane == 0) s_mr[f] = make_float2(mean, 1.f / sqrtf(tq * inv_cv + p.eps));
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
+      // one streaming pass over the slot: element i = (frame, joint, channel quad), contiguous in the slot
+      // and in the output
+      const float4 *zs = reinterpret_cast<const float4 *>(p.zring + (size_t)slot * (128 * V) * CO);
+      const int total = nf * V * C4;
+      const long long fo = p.out_T ? (long long)n * p.out_T + p.out_t0 + tb * 128 : (long long)n * p.T + tb * 128;
+      const size_t ob = (size_t)fo * V * CO;
+      constexpr int U = 4;
+#pragma unroll 1
+      for (int i0 = lt; i0 < total; i0 += kGwLnThreads * U) {
+        float4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * kGwLnThreads;
+          a[u] = i < total ? __ldcg(zs + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * kGwLnThreads;
+          if (i < total) {
+            const int row = i >> kSh, g4 = i & (C4 - 1);
+            const int f = (int)__umulhi((uint32_t)row, vmagic), w = row - f * V;
+            const float2 mr = s_mr[f];
+            const float nmr = -mr.x * mr.y;
+            const int ti = (g4 * V + w) * 4;
+            const float4 gg = __ldg(reinterpret_cast<const float4 *>(p.n_wT + ti));
+            const float4 oo = __ldg(reinterpret_cast<const float4 *>(p.n_bT + ti));
+            float4 r;
+            r.x = fmaf(fmaf(a[u].x, mr.y, nmr), gg.x, oo.x);
+            r.y = fmaf(fmaf(a[u].y, mr.y, nmr), gg.y, oo.y);
+            r.z = fmaf(fmaf(a[u].z, mr.y, nmr), gg.z, oo.z);
+            r.w = fmaf(fmaf(a[u].w, mr.y, nmr), gg.w, oo.w);
+            if (p.relu) {
+              r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+            }
+            if (p.out_f32) {
+              *reinterpret_cast<float4 *>(p.out_f32 + ob + 4 * (size_t)i) = r;
+            } else {
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(r.x, r.y), h23 = __floats2bfloat162_rn(r.z, r.w);
+              *reinterpret_cast<uint2 *>(p.out_hi + ob + 4 * (size_t)i) =
+                  make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+              if (p.out_lo) {
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(r.x - f01.x, r.y - f01.y);
+                const __nv_bfloat162 l23 = __floats2bfloat162_rn(r.z - f23.x, r.w - f23.y);
+                *reinterpret_cast<uint2 *>(p.out_lo + ob + 4 * (size_t)i) =
+                    make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+              }
+            }
+          }
+        }
+      }
+      // every LN thread has consumed its loads of the slot: release it to the epilogue of group grp + R
+      asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
+      if (lt == 0) {
+        __threadfence();
+        st_release_gpu(p.done + grp, 1u);
+      }
     }
   }
   tc_fence_before();
@@ -455,15 +655,34 @@ inline bool gcnw_enabled() {
   return on != 0;
 }
 
-// x planes: bf16 [planes][N][T_full][V][Cin] (the view takes every fstride-th frame, T frames);
-// wsc: k_gcnw_pack tiles [2][cap][CO][Cin]
-template <int CO>
+inline bool gcnw_fuse_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_GCNW_FUSE");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
+// ring geometry of the fused stage: slots of [128 frames][V][CO] fp32, at most ~40 MB so that the ring
+// stays L2-resident, at least 8 slots (148 CTAs work on ~148 / V groups at a time)
+inline int gcnw_ring_slots(int V, int CO) {
+  const size_t slot = (size_t)128 * V * CO * sizeof(float);
+  int R = (int)((size_t)40 * 1024 * 1024 / slot);
+  return R > 24 ? 24 : (R < 8 ? 8 : R);
+}
+inline size_t gcnw_ring_floats(int V, int CO) { return (size_t)gcnw_ring_slots(V, CO) * 128 * V * CO; }
+inline size_t gcnw_sring_float2(int V, int CO) { return (size_t)gcnw_ring_slots(V, CO) * 128 * V * kEpiNH; }
+
+// x planes: bf16 [planes][N_full][T_full][V][Cin] (the view takes every fstride-th frame, T frames, of the
+// first p.N trials from `x`); wsc: k_gcnw_pack tiles [2][cap][CO][Cin].  FUSE: p.zring .. p.out_t0 set and
+// p.ready / p.done zeroed by the caller (N * tblocks counters each).
+template <int CO, bool FUSE>
 int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p, int T_full, int fstride, int cap,
-                  cudaStream_t st) {
+                  long long plane_stride, cudaStream_t st) {
   const int V = p.V, kMaxSmem = 232448;
   p.tblocks = (p.T + 127) / 128;
   p.items = p.N * p.tblocks * V;
-  const int fixed = kPatchTotal + 1024 + 512 + 1024;
+  const int fixed = kPatchTotal + 1024 + 1024 + 512 + 1024;
   constexpr bool MERGE = CO <= 128;
   constexpr int kA = MERGE ? 2 * 128 * 128 : 128 * 128, kB = MERGE ? 2 * CO * 128 : CO * 128;
   // weight stages first (they are the long-latency stream for C >= 128), then activation stages
@@ -477,7 +696,7 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
   CUtensorMap tm_x, tm_w;
   const uint64_t xd[5] = {(uint64_t)p.Cin, (uint64_t)V, (uint64_t)p.T, (uint64_t)p.N, (uint64_t)p.planes};
   const uint64_t xs[4] = {(uint64_t)p.Cin * 2, (uint64_t)fstride * V * p.Cin * 2, (uint64_t)T_full * V * p.Cin * 2,
-                          (uint64_t)p.N * T_full * V * p.Cin * 2};
+                          (uint64_t)plane_stride * 2};
   const uint32_t xb[5] = {64, 1, 128, 1, 1};
   if (make_tmap_bf16(&tm_x, x, 5, xd, xs, xb)) return 1;
   const uint64_t wd[4] = {(uint64_t)p.Cin, (uint64_t)CO, (uint64_t)cap, 2};
@@ -485,17 +704,29 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
   const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
   if (make_tmap_bf16(&tm_w, wsc, 4, wd, wst, wb)) return 1;
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcnw<CO, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_gcnw<CO, MERGE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_w, p);
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcnw<CO, MERGE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (FUSE) {
+    // producers wait for consumers in other CTAs: every CTA must be resident -> cooperative launch
+    void *args[3] = {&tm_x, &tm_w, &p};
+    STGCN_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_gcnw<CO, MERGE, FUSE>), dim3(grid),
+                                              dim3(kGwThreads + kGwLnThreads), args, (size_t)smem, st));
+  } else {
+    k_gcnw<CO, MERGE, FUSE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_w, p);
+  }
   return 0;
 }
 
+// plane_stride: elements between the hi and lo planes of x (= rows of the whole buffer * Cin)
 inline int launch_gcnw(int CO, const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, const GcnwParams &p, int T_full,
-                       int fstride, int cap, cudaStream_t st) {
+                       int fstride, int cap, long long plane_stride, cudaStream_t st) {
+  const bool fuse = p.zring != nullptr;
   switch (CO) {
-    case 64: return launch_gcnw_c<64>(x, wsc, p, T_full, fstride, cap, st);
-    case 128: return launch_gcnw_c<128>(x, wsc, p, T_full, fstride, cap, st);
-    case 256: return launch_gcnw_c<256>(x, wsc, p, T_full, fstride, cap, st);
+    case 64: return fuse ? launch_gcnw_c<64, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st)
+                         : launch_gcnw_c<64, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st);
+    case 128: return fuse ? launch_gcnw_c<128, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st)
+                          : launch_gcnw_c<128, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st);
+    case 256: return fuse ? launch_gcnw_c<256, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st)
+                          : launch_gcnw_c<256, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st);
   }
   return fail("gcnw: unsupported channel count %d", CO);
 }

@@ -7,7 +7,6 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc_pair.cuh"
-#include "kernels_gcn3.cuh"
 #include "kernels_gcnw.cuh"
 #include "kernels_rt_small.cuh"
 
@@ -41,8 +40,6 @@ int debug_dump(const char *what, int c, cudaStream_t st) {
   for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%llu", names[i], h[i]);
   if (!strcmp(what, "tcn"))
     fprintf(stderr, " [tcn pass 2 of CTA 0 / row 0: 8 residual load 9 tmem loads 10 tables+math+patch 15 cooperative store]");
-  if (!strcmp(what, "gcn3"))
-    fprintf(stderr, " [gcn3: 6 epi_wait_tmem 7 barA 8 phase1 9 barB 10 gather 12 stats 13 normalise+store]");
   fprintf(stderr, " ph12(pass1|rt_wait)=%llu ph13(bar_stats|rt_update)=%llu ph14(pass2|rt_store)=%llu ph15(rt_finish)=%llu", h[12], h[13], h[14], h[15]);
   fprintf(stderr, "\n");
   memset(h, 0, sizeof(h));
@@ -165,11 +162,6 @@ struct LayerPrep {
   __nv_bfloat16 *wg16 = nullptr, *wp16 = nullptr, *wr16 = nullptr;
   float *zero = nullptr;  // c_out zeros: bias of the bias-free RT residual conv (rtstgcn.py:503)
   float *n1T = nullptr, *n2T = nullptr, *nrT = nullptr;  // LayerNorm affine (V, C): weight then bias
-  // graph-conv v3 (kernels_gcn3.cuh): gather tables, weight tiles, [V][C] parameter tables
-  bool g3 = false, g3r = false;
-  tc::Gcn3Tables *tab = nullptr, *tabr = nullptr;
-  __nv_bfloat16 *wg3 = nullptr, *wr3 = nullptr;
-  float *bzR = nullptr, *n1R = nullptr, *nrR = nullptr;
   // graph conv with per-joint pre-scaled weights (kernels_gcnw.cuh): edge tables + weight tiles
   bool gw = false, gwr = false;
   tc::GcnwTables *gwtab = nullptr, *gwtabr = nullptr;
@@ -210,20 +202,6 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws, bool spar
       P.gwtabr = ws.take<tc::GcnwTables>(1);
       P.wscr = ws.take<__nv_bfloat16>(2 * cap * d.c_out * d.c_in);
     }
-  }
-  P.g3 = !P.gw && P.gcn && !d.rt && tc::gcn3_enabled() && tc::gcn3_supported(d.c_in, d.c_out, V, K) &&
-         (d.residual != STGCN_RES_CONV || (P.res && tc::gcn3_supported(d.c_in, d.c_out, V, 1)));
-  P.g3r = P.g3 && d.residual == STGCN_RES_CONV;
-  if (P.g3) {
-    P.tab = ws.take<tc::Gcn3Tables>(1);
-    P.wg3 = ws.take<__nv_bfloat16>((size_t)2 * K * d.c_out * d.c_in);
-    P.bzR = ws.take<float>((size_t)d.c_out * V);
-    P.n1R = ws.take<float>((size_t)2 * d.c_out * V);
-  }
-  if (P.g3r) {
-    P.tabr = ws.take<tc::Gcn3Tables>(1);
-    P.wr3 = ws.take<__nv_bfloat16>((size_t)2 * d.c_out * d.c_in);
-    P.nrR = ws.take<float>((size_t)2 * d.c_out * V);
   }
   return P;
 }
@@ -267,31 +245,6 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
       STGCN_LAUNCH_OK();
     }
   }
-  if (P.g3) {
-    const long long nw = (long long)K * d.c_out * d.c_in;
-    const int cvn = d.c_out * V;
-    tc::k_gcn3_tables<<<1, 32, 0, st>>>(d.a_eff, K, V, 0, P.tab);
-    STGCN_LAUNCH_OK();
-    tc::k_pack_gcn3_w<<<cdiv(nw, 256), 256, 0, st>>>(d.gcn_w, P.wg3, d.c_out, d.c_in, K);
-    STGCN_LAUNCH_OK();
-    tc::k_bias_through_adj_vc<<<cdiv(cvn, 256), 256, 0, st>>>(d.a_eff, d.gcn_b, K, V, d.c_out, P.bzR);
-    STGCN_LAUNCH_OK();
-    tc::k_transpose_cv<<<cdiv(cvn, 256), 256, 0, st>>>(d.n1_w, P.n1R, d.c_out, V);
-    STGCN_LAUNCH_OK();
-    tc::k_transpose_cv<<<cdiv(cvn, 256), 256, 0, st>>>(d.n1_b, P.n1R + cvn, d.c_out, V);
-    STGCN_LAUNCH_OK();
-    if (P.g3r) {
-      const long long nwr = (long long)d.c_out * d.c_in;
-      tc::k_gcn3_tables<<<1, 32, 0, st>>>(nullptr, 1, V, 1, P.tabr);
-      STGCN_LAUNCH_OK();
-      tc::k_pack_gcn3_w<<<cdiv(nwr, 256), 256, 0, st>>>(d.res_w, P.wr3, d.c_out, d.c_in, 1);
-      STGCN_LAUNCH_OK();
-      tc::k_transpose_cv<<<cdiv(cvn, 256), 256, 0, st>>>(d.nr_w, P.nrR, d.c_out, V);
-      STGCN_LAUNCH_OK();
-      tc::k_transpose_cv<<<cdiv(cvn, 256), 256, 0, st>>>(d.nr_b, P.nrR + cvn, d.c_out, V);
-      STGCN_LAUNCH_OK();
-    }
-  }
   const int cv = d.c_out * V;
   const float *src[3][2] = {{d.n1_w, d.n1_b}, {d.n2_w, d.n2_b}, {d.nr_w, d.nr_b}};
   float *dst[3] = {P.n1T, P.n2T, P.nrT};
@@ -304,13 +257,59 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
   return 0;
 }
 
+// ---- graph-conv stage with per-joint pre-scaled weights (kernels_gcnw.cuh) --------------------
+// z = GEMM(x planes) + bias, then LayerNorm(C,V) (+ ReLU) into l.out_*.  Fused form: one cooperative
+// persistent kernel, z through an L2-resident ring; two-kernel form: z in HBM + k_ln_stream.
+// Scratch comes from `ws` and is released on return.  In measuring mode only the sizes are taken.
+int gcnw_stage(int c_out, const __nv_bfloat16 *xh, const __nv_bfloat16 *wsc, tc::GcnwParams g, tc::LnStreamArgs l,
+               int T_full, int fstride, long long plane_stride, Bump &ws, cudaStream_t st) {
+  const size_t mark = ws.mark();
+  const int V = g.V, cap = tc::gcnw_edge_cap(V);
+  const long long rows = (long long)g.N * g.T * V;
+  if (tc::gcnw_fuse_enabled()) {
+    const int groups = g.N * ((g.T + 127) / 128);
+    g.zring = ws.take<float>(tc::gcnw_ring_floats(V, c_out));
+    g.sring = ws.take<float2>(tc::gcnw_sring_float2(V, c_out));
+    g.ready = ws.take<unsigned>((size_t)2 * groups);
+    g.done = g.ready ? g.ready + groups : nullptr;
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (graph-conv stage ring)");
+      g.R = tc::gcnw_ring_slots(V, c_out);
+      g.n_wT = l.n_wT; g.n_bT = l.n_bT; g.relu = l.relu; g.eps = l.eps;
+      g.out_f32 = l.out_f32; g.out_hi = l.out_hi; g.out_lo = l.out_lo;
+      g.out_T = l.out_T; g.out_t0 = l.out_t0;
+      STGCN_CUDA_OK(cudaMemsetAsync(g.ready, 0, sizeof(unsigned) * 2 * groups, st));
+      ProfScope ps(KC_GEMM_1X1, st);
+      if (tc::launch_gcnw(c_out, xh, wsc, g, T_full, fstride, cap, plane_stride, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+  } else {
+    float *zb = ws.take<float>((size_t)rows * c_out);
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (graph-conv stage)");
+      g.out = zb;
+      {
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcnw(c_out, xh, wsc, g, T_full, fstride, cap, plane_stride, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      l.z = zb;
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_ln_stream(l, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+  }
+  ws.release(mark);
+  return 0;
+}
+
 // ---- ST-GCN layer on channels-last activations --------------------------------
 // x [N*T*V, c_in] -> out [N*T_out*V, c_out].  Scratch comes from `ws` (released on return).
 // `pp`: prepared operands (model path) or null (built here, per call).
 constexpr int kHalo = 4;   // halo frames carried on each side of the temporal-conv input in T-split mode
 
 // x_planes / out_planes: the buffer holds bf16 hi/lo planes [plane][rows][C] (one plane in bf16
-// mode) instead of fp32 rows -- the inter-layer format of the graph-conv v3 path.
+// mode) instead of fp32 rows -- the inter-layer format of the per-joint-weight graph-conv path.
 int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        int N, int T, Bump &ws, cudaStream_t st, const LayerPrep *pp = nullptr,
                        const stgcn_halo_desc *halo = nullptr, int layer_index = 0, bool x_planes = false,
@@ -335,12 +334,11 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
   // tensor-core graph-convolution stage: LayerNorm, shared adjacency, C_in % 64 == 0
   const bool tc_gcn = math != STGCN_MATH_FP32 && pp && pp->gcn;
-  // graph-conv v3: reference operation order on CTA pairs, input as bf16 planes
+  // per-joint-weight GEMM path: the layer input (and the identity residual) travel as bf16 planes
   const bool use_gw = tc_gcn && tc_tcn && pp->gw;
-  const bool use_g3 = (tc_gcn && tc_tcn && pp->g3) || use_gw;     // bf16-plane input / residual plumbing (shared)
-  STGCN_REQUIRE(use_g3 || (!x_planes && !out_planes), "bf16-plane activations need the graph-conv v3 path");
+  STGCN_REQUIRE(use_gw || (!x_planes && !out_planes), "bf16-plane activations need the per-joint-weight graph-conv path");
   const __nv_bfloat16 *xh = nullptr, *xl = nullptr;
-  if (use_g3) {
+  if (use_gw) {
     if (x_planes) {
       xh = reinterpret_cast<const __nv_bfloat16 *>(x);
     } else {
@@ -369,50 +367,20 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
   __nv_bfloat16 *u16_lo = (tc_tcn && planes == 2 && u16) ? u16 + (size_t)rows_u * d.c_out : nullptr;
   double *sums = bn ? ws.take<double>((size_t)4 * d.c_out) : nullptr;
   if (use_gw) {
-    // GEMM with per-joint pre-scaled weights -> z (fp32), then the streaming LayerNorm + ReLU + split
-    float *zb = ws.take<float>((size_t)rows * d.c_out);
-    if (!ws.measuring()) {
-      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
-      tc::GcnwParams g{};
-      g.T = T; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
-      g.tab = pp->gwtab;
-      g.bias = pp->bzT; g.bias_sw = 1;
-      g.out = zb;
-      g.debug = debug_mode();
-      {
-        ProfScope ps(KC_GEMM_1X1, st);
-        if (tc::launch_gcnw(d.c_out, xh, pp->wsc, g, T, 1, tc::gcnw_edge_cap(V), st)) return 1;
-        STGCN_LAUNCH_OK();
-      }
-      tc::LnStreamArgs l{};
-      l.frames = (long long)N * T; l.T = T; l.V = V; l.C = d.c_out;
-      l.z = zb;
-      l.n_wT = pp->n1T; l.n_bT = pp->n1T + (size_t)d.c_out * V;
-      l.relu = 1; l.eps = kEps;
-      l.out_hi = u16; l.out_lo = u16_lo;
-      if (hf) { l.out_T = T + 2 * hf; l.out_t0 = hf; }
-      ProfScope ps(KC_FRAME, st);
-      if (tc::launch_ln_stream(l, st)) return 1;
-      STGCN_LAUNCH_OK();
-    }
-  } else if (use_g3) {
-    if (!ws.measuring()) {
-      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
-      tc::Gcn3Params g{};
-      g.T = T; g.V = V; g.Cin = d.c_in; g.planes = planes;
-      g.tab = pp->tab;
-      g.bias = pp->bzR; g.bias_v = 1;
-      g.n_w = pp->n1R; g.n_b = pp->n1R + (size_t)d.c_out * V;
-      g.out_hi = u16; g.out_lo = u16_lo;
-      if (hf) { g.out_T = T + 2 * hf; g.out_t0 = hf; }
-      g.relu = 1;
-      g.eps = kEps;
-      g.debug = debug_mode();
-      ProfScope ps(KC_GEMM_1X1, st);
-      if (tc::launch_gcn3(d.c_out, K, xh, pp->wg3, g, N, T, 1, st)) return 1;
-      STGCN_LAUNCH_OK();
-      if (debug_dump("gcn3", d.c_out, st)) return 1;
-    }
+    // GEMM with per-joint pre-scaled weights; LayerNorm + ReLU + split either inside the same persistent
+    // kernel (z travels through an L2-resident ring) or, STGCN_GCNW_FUSE=0, as the streaming kernel
+    tc::LnStreamArgs l{};
+    l.frames = (long long)N * T; l.T = T; l.V = V; l.C = d.c_out;
+    l.n_wT = pp->n1T; l.n_bT = pp->n1T + (size_t)d.c_out * V;
+    l.relu = 1; l.eps = kEps;
+    l.out_hi = u16; l.out_lo = u16_lo;
+    if (hf) { l.out_T = T + 2 * hf; l.out_t0 = hf; }
+    tc::GcnwParams g{};
+    g.T = T; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
+    g.tab = pp->gwtab;
+    g.bias = pp->bzT; g.bias_sw = 1;
+    g.debug = debug_mode();
+    if (gcnw_stage(d.c_out, xh, pp->wsc, g, l, T, 1, rows * d.c_in, ws, st)) return 1;
   } else if (tc_gcn) {
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
@@ -475,44 +443,23 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     const bool res_tc = res_conv && pp->res;
     float *resb = res_conv ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
     float *qr = (res_conv && !res_tc) ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
-    float *qz = (res_tc && use_gw) ? ws.take<float>((size_t)rows_out * d.c_out) : nullptr;
+    if (res_tc && use_gw) {
+      // residual 1x1 conv + LayerNorm_R with the same stage (identity edges, strided frames)
+      tc::LnStreamArgs l{};
+      l.frames = (long long)N * T_out; l.T = T_out; l.V = V; l.C = d.c_out;
+      l.n_wT = pp->nrT; l.n_bT = pp->nrT + (size_t)d.c_out * V;
+      l.relu = 0; l.eps = kEps;
+      l.out_f32 = resb;
+      tc::GcnwParams g{};
+      g.T = T_out; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
+      g.tab = pp->gwtabr;
+      g.bias = d.res_b; g.bias_sw = 0;
+      g.debug = debug_mode();
+      if (gcnw_stage(d.c_out, xh, pp->wscr, g, l, T, d.stride, rows * d.c_in, ws, st)) return 1;
+    }
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
       if (res_tc && use_gw) {
-        // residual 1x1 conv with the same GEMM kernel (identity edges), then LayerNorm_R as a stream
-        tc::GcnwParams g{};
-        g.T = T_out; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
-        g.tab = pp->gwtabr;
-        g.bias = d.res_b; g.bias_sw = 0;
-        g.out = qz;
-        g.debug = debug_mode();
-        {
-          ProfScope ps(KC_GEMM_1X1, st);
-          if (tc::launch_gcnw(d.c_out, xh, pp->wscr, g, T, d.stride, tc::gcnw_edge_cap(V), st)) return 1;
-          STGCN_LAUNCH_OK();
-        }
-        tc::LnStreamArgs l{};
-        l.frames = (long long)N * T_out; l.T = T_out; l.V = V; l.C = d.c_out;
-        l.z = qz;
-        l.n_wT = pp->nrT; l.n_bT = pp->nrT + (size_t)d.c_out * V;
-        l.relu = 0; l.eps = kEps;
-        l.out_f32 = resb;
-        ProfScope ps(KC_FRAME, st);
-        if (tc::launch_ln_stream(l, st)) return 1;
-        STGCN_LAUNCH_OK();
-      } else if (res_tc && use_g3) {
-        tc::Gcn3Params g{};
-        g.T = T_out; g.V = V; g.Cin = d.c_in; g.planes = planes;
-        g.tab = pp->tabr;
-        g.bias = d.res_b; g.bias_v = 0;
-        g.n_w = pp->nrR; g.n_b = pp->nrR + (size_t)d.c_out * V;
-        g.out_f32 = resb;
-        g.relu = 0;
-        g.eps = kEps;
-        g.debug = debug_mode();
-        ProfScope ps(KC_GEMM_1X1, st);
-        if (tc::launch_gcn3(d.c_out, 1, xh, pp->wr3, g, N, T, d.stride, st)) return 1;
-        STGCN_LAUNCH_OK();
       } else if (res_tc) {
         tc::GcnTc2Params g{};
         g.T_out = T_out; g.V = V; g.K = 1; g.Cin = d.c_in; g.planes = planes;
@@ -572,7 +519,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       p.planes = planes;
       p.epi.bias = d.tcn_b; p.epi.bias_sw = 0;
       p.epi.n_wT = pp->n2T; p.epi.n_bT = pp->n2T + (size_t)d.c_out * V;
-      if (d.residual == STGCN_RES_IDENTITY && use_g3) {
+      if (d.residual == STGCN_RES_IDENTITY && use_gw) {
         p.epi.res_hi = xh; p.epi.res_lo = xl;            // the layer input as planes (hi + lo = x to 2^-17)
       } else {
         p.epi.res = d.residual == STGCN_RES_IDENTITY ? x : resb;
@@ -695,7 +642,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
         g.tab = pp->gwtabr;
         g.out = qr;                            // no bias (rtstgcn.py:503)
         ProfScope ps(KC_GEMM_1X1, st);
-        if (tc::launch_gcnw(d.c_out, xh, pp->wscr, g, B, 1, cap, st)) return 1;
+        if (tc::launch_gcnw(d.c_out, xh, pp->wscr, g, B, 1, cap, rows * d.c_in, st)) return 1;
         STGCN_LAUNCH_OK();
       }
       {
@@ -705,7 +652,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
         g.bias = pp->bzT; g.bias_sw = 1;
         g.out = zb;
         ProfScope ps(KC_GEMM_1X1, st);
-        if (tc::launch_gcnw(d.c_out, xh, pp->wsc, g, B, 1, cap, st)) return 1;
+        if (tc::launch_gcnw(d.c_out, xh, pp->wsc, g, B, 1, cap, rows * d.c_in, st)) return 1;
         STGCN_LAUNCH_OK();
       }
       RtUpdateArgs u{};
@@ -988,11 +935,11 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     if (a > max_act) max_act = a;
   }
   float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
-  // which layers run the graph-conv v3 path (bf16-plane input); a producer writes planes when its
-  // consumer wants them and it can (warp input stage / tensor-core temporal epilogue)
+  // which layers take bf16-plane input (per-joint-weight graph conv); a producer writes planes when
+  // its consumer wants them and it can (warp input stage / tensor-core temporal epilogue)
   const bool have = use_prepared(m);
   const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
-  bool g3[65] = {false};
+  bool pl[65] = {false};
   STGCN_REQUIRE(m.num_layers <= 64, "too many layers");
   {
     Bump pm(nullptr, 0);
@@ -1000,12 +947,12 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     for (int i = 0; i < m.num_layers; ++i) {
       const stgcn_layer_desc &d = m.layers[i];
       const LayerPrep P = prep_take(d, K, V, pm, (m.reserved & 2) != 0);
-      g3[i] = m.math != STGCN_MATH_FP32 && (P.g3 || P.gw) && P.tcn &&
+      pl[i] = m.math != STGCN_MATH_FP32 && P.gw && P.tcn &&
               tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, tt);
       tt = (tt - 1) / d.stride + 1;
     }
   }
-  const bool in0_planes = g3[0] && embed_warp_path(m);
+  const bool in0_planes = pl[0] && embed_warp_path(m);
   if (embed(m, x, buf[0], n, T, ws, st, xs, in0_planes ? planes : 0)) return 1;
   int cur = 0;
   t = T;
@@ -1017,7 +964,7 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     STGCN_REQUIRE(!d.a_per_sample, "per-sample adjacency is only supported by the layer-level API");
     LayerPrep P;
     if (have) P = prep_take(d, K, V, pb, (m.reserved & 2) != 0);
-    const bool out_planes = g3[i] && g3[i + 1];
+    const bool out_planes = pl[i] && pl[i + 1];
     if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st, have ? &P : nullptr, halo, i,
                            x_planes, out_planes, (m.reserved & 2) != 0))
       return 1;

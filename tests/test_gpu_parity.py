@@ -648,21 +648,21 @@ def test_stgcn_sliding_windows(pkg, syn, cuda):
 
 
 # ------------------------------------------------------------------ non-default graph-conv paths
-@pytest.mark.parametrize('switches', [{'STGCN_GCNW': '0'}, {'STGCN_GCNW': '0', 'STGCN_GCN3': '1'}],
-                         ids=['fused-v2', 'opt-in-v3'])
-def test_stgcn_model_other_graphconv_paths_subprocess(cuda, switches):
-    """Model forwards default to the per-joint-weight GEMM + streaming LayerNorm (kernels_gcnw.cuh).  The two
-    other graph-conv implementations stay covered at model level: the fused k_gcn_tc2 kernels
-    (STGCN_GCNW=0) and the opt-in v3 kernels (STGCN_GCN3=1: reference operation order on CTA pairs, bf16-plane
-    activations) -- models of growing depth incl. strided / channel-changing layers, both arithmetic
-    modes, against the oracle.  The switches are read once per process, so tools/debug_g3.py runs in a
-    child process."""
+@pytest.mark.parametrize('switches', [{}, {'STGCN_GCNW': '0'}, {'STGCN_GCNW_FUSE': '0'}],
+                         ids=['default', 'frame-tile-kernel', 'two-kernel-stage'])
+def test_stgcn_model_graphconv_paths_subprocess(cuda, switches):
+    """Model forwards default to the per-joint-weight GEMM with the LayerNorm stage running inside the same
+    persistent kernel (kernels_gcnw.cuh).  The other graph-conv forms stay covered at model level: the
+    frame-tile k_gcn_tc2 kernel (STGCN_GCNW=0; also what layer-level calls and dense adjacencies use) and
+    the two-kernel form of the stage (STGCN_GCNW_FUSE=0: GEMM -> z in HBM -> k_ln_stream) -- models of
+    growing depth incl. strided / channel-changing layers, both arithmetic modes, against the oracle.  The
+    switches are read once per process, so tools/check_graphconv_paths.py runs in a child process."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, **switches)
-    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'debug_g3.py')], env=env, capture_output=True,
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'check_graphconv_paths.py')], env=env, capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith(('bf16x3', 'bf16 '))]
