@@ -163,6 +163,7 @@ __device__ __forceinline__ void wait_flag(const unsigned *p, unsigned target, un
   }
 }
 constexpr int kGwLnThreads = 256;     // LN warps of the fused stage
+constexpr int kGwLnParts = 8;         // LN work items per frame group (16 frames each)
 
 constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B producer, 3.. epilogue
 
@@ -384,12 +385,12 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
       // issued before the accumulator wait so that its L2 latency is hidden.  Relaxed on purpose: only
       // stores follow (they cannot be speculated), and an acquire would invalidate the L1 that holds
       // the bias tables once per tile.
-      unsigned freed = 1;
+      unsigned freed = kGwLnParts;
       if (FUSE && grp >= p.R && lane == 0) freed = ld_relaxed_gpu(p.done + (grp - p.R));
       mbar_wait(bTmemFull + 8 * buf, t_ph);
       tc_fence_after();
       if (FUSE) {
-        if (grp >= p.R && lane == 0) wait_flag<false>(p.done + (grp - p.R), 1u, freed);
+        if (grp >= p.R && lane == 0) wait_flag<false>(p.done + (grp - p.R), (unsigned)kGwLnParts, freed);
         __syncwarp();
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * CO);
@@ -444,17 +445,24 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
     }
   } else if (FUSE) {
     // ---- LN warps: normalise complete frame groups out of their ring slots ----
+    // Work item = (group, part): kGwLnParts parts of 128 / kGwLnParts frames each, dealt round-robin over
+    // the CTAs, so that every CTA's LN warps are busy on the few groups that are in flight (with one CTA
+    // per group the stage was bound by the ring: R groups in flight x one CTA's load latency each).
     constexpr int C4 = CO / 4, kSh = (CO == 64) ? 4 : (CO == 128 ? 5 : 6);
+    constexpr int FP = 128 / kGwLnParts;                    // frames per part
     const int lt = threadIdx.x - kGwThreads, lw = lt >> 5;
     const int V = p.V, NP = V * kEpiNH;                     // row partials per frame
-    const int groups = p.N * p.tblocks;
+    const int lnitems = p.N * p.tblocks * kGwLnParts;
     const unsigned target = (unsigned)(V * 4 * kEpiNH);     // epilogue warps per group
     const uint32_t vmagic = (uint32_t)((0x100000000ull + (unsigned)V - 1) / (unsigned)V);   // x / V for x < 65536
     const float inv_np = 1.f / (float)NP, inv_cv = 1.f / (float)(V * CO - 1);
-    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    for (int li = blockIdx.x; li < lnitems; li += gridDim.x) {
+      const int grp = li / kGwLnParts, part = li - grp * kGwLnParts;
       const int slot = grp % p.R;
       const int tb = grp % p.tblocks, n = grp / p.tblocks;
-      const int nf = p.T - tb * 128 < 128 ? p.T - tb * 128 : 128;
+      const int f0 = part * FP;
+      int nf = p.T - tb * 128 - f0;                          // valid frames of this part
+      nf = nf < 0 ? 0 : (nf > FP ? FP : nf);
       if (lt == 0) {
         // relaxed polls (an acquire per poll would invalidate the SM's L1 under the epilogue warps), then
         // one fence: relaxed load + fence = acquire.  The slot is read with ld.global.cg (L2) anyway.
@@ -463,7 +471,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
       }
       asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
       // per-frame statistics: warp lw merges the V * kEpiNH row partials of frames lw, lw + 8, ...
-      const float2 *sp = p.sring + (size_t)slot * 128 * NP;
+      const float2 *sp = p.sring + ((size_t)slot * 128 + f0) * NP;
       for (int f = lw; f < nf; f += kGwLnThreads / 32) {
         const float2 a0 = lane < NP ? __ldcg(sp + (size_t)f * NP + lane) : make_float2(0.f, 0.f);
         const float2 a1 = lane + 32 < NP ? __ldcg(sp + (size_t)f * NP + lane + 32) : make_float2(0.f, 0.f);
@@ -481,13 +489,13 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
         if (lane == 0) s_mr[f] = make_float2(mean, 1.f / sqrtf(tq * inv_cv + p.eps));
       }
       asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
-      // one streaming pass over the slot: element i = (frame, joint, channel quad), contiguous in the slot
+      // one streaming pass over the part: element i = (frame, joint, channel quad), contiguous in the slot
       // and in the output
-      const float4 *zs = reinterpret_cast<const float4 *>(p.zring + (size_t)slot * (128 * V) * CO);
+      const float4 *zs = reinterpret_cast<const float4 *>(p.zring + ((size_t)slot * 128 + f0) * V * CO);
       const int total = nf * V * C4;
-      const long long fo = p.out_T ? (long long)n * p.out_T + p.out_t0 + tb * 128 : (long long)n * p.T + tb * 128;
+      const long long fo = (p.out_T ? (long long)n * p.out_T + p.out_t0 : (long long)n * p.T) + tb * 128 + f0;
       const size_t ob = (size_t)fo * V * CO;
-      constexpr int U = 4;
+      constexpr int U = 8;
 #pragma unroll 1
       for (int i0 = lt; i0 < total; i0 += kGwLnThreads * U) {
         float4 a[U];
@@ -532,11 +540,12 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
           }
         }
       }
-      // every LN thread has consumed its loads of the slot: release it to the epilogue of group grp + R
+      // every LN thread has consumed its loads of the part: count it; the slot is released to the epilogue of
+      // group grp + R when all kGwLnParts parts are in
       asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
       if (lt == 0) {
         __threadfence();
-        st_release_gpu(p.done + grp, 1u);
+        atomicAdd(p.done + grp, 1u);
       }
     }
   }

@@ -9,8 +9,10 @@
 // weights from L2 through a cp.async ring); a layer has two exchange steps, both over distributed
 // shared memory with a cluster barrier: (1) the partial LayerNorm statistics of every CTA's slice
 // of the updated accumulator go to ALL CTAs; (2) every CTA normalises its own slice (still in
-// registers) and writes it into ALL CTAs' copy of the next layer's input.  Arithmetic is plain
-// fp32 FMA in the reference's order.
+// registers) and writes it into ALL CTAs' copy of the next layer's input.  The 1x1 feature
+// transforms run as 3xTF32 warp-level MMAs (x = hi + lo, hi*hi + hi*lo + lo*hi: fp32 parity to
+// ~1e-6) in EVERY math mode, including STGCN_MATH_FP32 and STGCN_MATH_BF16 (the latency path is
+// not MMA-bound); adjacency, state update and LayerNorm are fp32 FMAs in the reference's order.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -46,6 +48,7 @@ __device__ unsigned long long g_dbg[8];
 
 struct Params {
   int num_layers, V, K, in_feat, num_classes, B, c_max, debug;
+  int period;                                 // frame counters wrap at this value (0: never)
   float eps;
   const float *x;                             // (B, in_feat, 1, V)
   float *logits;                              // (B, num_classes)
@@ -399,7 +402,7 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) p.logits[(size_t)b * p.num_classes + m] = s + __ldg(p.fcn_out_b + m);
     }
-    if (tid == 0) p.counter[b] = cnt + 1;
+    if (tid == 0) p.counter[b] = (p.period > 0 && cnt + 1 >= p.period) ? 0 : cnt + 1;
   }
   cluster.sync();   // no CTA may exit while others can still write into its shared memory
   lap(5);

@@ -528,6 +528,8 @@ struct RtUpdateArgs {
   int B, V, C;
   const float *z;                 // [B*V, C]
   float *fifo, *acc;              // [F][B*V, C], [S][B*V, C]
+  __nv_bfloat16 *fifo16;          // fifo_bf16: the FIFO as bf16 [F][B*V, C] (k_rt_stream only; fifo == null)
+  int fifo_bf16;
   const int *counter;             // [B]
   int F, S;
   long long slot;                 // B*V*C
@@ -682,9 +684,16 @@ inline int launch_rt_update(const RtUpdateArgs &a, cudaStream_t st) {
 }
 inline bool rt_update_supported(int V, int C) { return C % 4 == 0 && (V * C / 4 + 255) / 256 <= 7; }
 
-__global__ void k_advance_counters(int *counter, int first, int count) {
+// per-stream frame counters advance modulo `period` = lcm of every layer's ring and accumulator sizes
+// (the kernels only use cnt % F and cnt % S), so they never overflow on a long-running stream;
+// period == 0: plain increment
+__global__ void k_advance_counters(int *counter, int first, int count, int period) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) counter[first + i] += 1;
+  if (i < count) {
+    int c = counter[first + i] + 1;
+    if (period > 0 && c >= period) c = 0;
+    counter[first + i] = c;
+  }
 }
 
 // --------------------------------------------------------------------------- //

@@ -9,6 +9,7 @@
 #include "kernels_tc_pair.cuh"
 #include "kernels_gcnw.cuh"
 #include "kernels_rt_small.cuh"
+#include "kernels_rt_stream.cuh"
 
 using namespace stgcn;
 
@@ -599,13 +600,30 @@ inline bool rt_split_enabled() {
   return on != 0;
 }
 
+// STGCN_RT_STREAM=0 selects the register-resident state kernel (k_rt_update) instead of the bulk-copy-staged
+// one (k_rt_stream)
+inline bool rt_stream_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_RT_STREAM");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
+int launch_rt_state(const RtUpdateArgs &u, cudaStream_t st) {
+  if (rt_stream_enabled() && rt_stream_supported(u.V, u.C)) return launch_rt_stream(u, st);
+  if (u.fifo_bf16) return fail("rt step: the bf16 FIFO layout needs the staged state kernel (STGCN_RT_STREAM)");
+  return launch_rt_update(u, st);
+}
+
 // ---- RT online layer on channels-last frames -----------------------------------
 // x [B*V, c_in] -> out [B*V, c_out]; fifo [F][B][V][C], acc [S][B][V][C]; counter[B].
 int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st,
                        const LayerPrep *pp = nullptr, bool use_gw = false, bool x_planes = false,
-                       bool out_planes = false) {
+                       bool out_planes = false, bool fifo_bf16 = false) {
   if (check_layer(d)) return 1;
+  STGCN_REQUIRE(!fifo_bf16 || use_gw, "rt layer: the bf16 FIFO layout needs the per-joint-weight GEMM path");
   STGCN_REQUIRE(d.norm == STGCN_NORM_LAYERNORM,
                 "continual inference needs LayerNorm: batch statistics of a single frame are undefined "
                 "(reference raises at models/utils/batchnorm.py:20)");
@@ -658,7 +676,9 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       RtUpdateArgs u{};
       u.B = B; u.V = V; u.C = d.c_out;
       u.z = zb;
-      u.fifo = fifo; u.acc = acc; u.counter = counter;
+      u.fifo = fifo_bf16 ? nullptr : fifo; u.acc = acc; u.counter = counter;
+      u.fifo16 = fifo_bf16 ? reinterpret_cast<__nv_bfloat16 *>(fifo) : nullptr;
+      u.fifo_bf16 = fifo_bf16 ? 1 : 0;
       u.F = d.stride * (d.kernel - 1) + 1;
       u.S = d.stride;
       u.slot = rows * d.c_out;
@@ -677,7 +697,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
         u.out = out;
       }
       ProfScope ps(KC_FRAME, st);
-      if (launch_rt_update(u, st)) return 1;
+      if (launch_rt_state(u, st)) return 1;
       STGCN_LAUNCH_OK();
       ws.release(mark0);
       return 0;
@@ -729,7 +749,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       u.eps = kEps;
       u.out = out;
       ProfScope ps(KC_FRAME, st);
-      if (launch_rt_update(u, st)) return 1;
+      if (launch_rt_state(u, st)) return 1;
       STGCN_LAUNCH_OK();
     }
     ws.release(mark0);
@@ -1017,8 +1037,10 @@ struct RtLayout {
   size_t fifo[64], acc[64];
   size_t total;
 };
+bool rt_fifo_bf16(const stgcn_model_desc &m, int B);
 int rt_layout(const stgcn_model_desc &m, int B, RtLayout &L) {
   STGCN_REQUIRE(m.num_layers <= 64, "too many layers");
+  const size_t fifo_elt = rt_fifo_bf16(m, B) ? sizeof(__nv_bfloat16) : sizeof(float);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t at = off;
@@ -1028,12 +1050,30 @@ int rt_layout(const stgcn_model_desc &m, int B, RtLayout &L) {
   L.counters = take(sizeof(int32_t) * (size_t)B);
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
-    size_t slot = (size_t)B * m.num_joints * d.c_out * sizeof(float);
-    L.fifo[i] = take(slot * (size_t)(d.stride * (d.kernel - 1) + 1));
-    L.acc[i] = take(slot * (size_t)d.stride);
+    const size_t slot_n = (size_t)B * m.num_joints * d.c_out;
+    L.fifo[i] = take(slot_n * fifo_elt * (size_t)(d.stride * (d.kernel - 1) + 1));
+    L.acc[i] = take(slot_n * sizeof(float) * (size_t)d.stride);
   }
   L.total = off;
   return 0;
+}
+
+// frame counters wrap at the least common multiple of every layer's FIFO / accumulator ring sizes
+inline long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
+inline int rt_counter_period_of(int F, int S, long long run) {
+  run = run / gcd_ll(run, F) * F;
+  run = run / gcd_ll(run, S) * S;
+  return run > (1ll << 30) ? 0 : (int)run;
+}
+int rt_counter_period(const stgcn_model_desc &m) {
+  long long run = 1;
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    const int p = rt_counter_period_of(d.stride * (d.kernel - 1) + 1, d.stride, run);
+    if (p == 0) return 0;
+    run = p;
+  }
+  return (int)run;
 }
 
 // few streams: the whole step as one cluster kernel (kernels_rt_small.cuh)
@@ -1041,7 +1081,8 @@ constexpr int kSmallBatchMax = 16;
 bool rt_small_supported(const stgcn_model_desc &m, int B) {
   if (m.reserved & 1) return false;                      // caller opted out (tests of the batched path)
   if (B > kSmallBatchMax || m.num_layers > rts::kMaxLayers || m.num_joints > 32) return false;
-  if (m.in_feat * m.num_joints > rts::kThreads || m.partitions * m.num_joints + 1 > 1024) return false;
+  // K*V + 1 CSR row pointers and the non-zeros are staged in fixed shared arrays (kernels_rt_small.cuh:31-32)
+  if (m.in_feat * m.num_joints > rts::kThreads || m.partitions * m.num_joints + 1 > rts::kCsrPtrMax) return false;
   int c_max = m.layers[0].c_in;
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
@@ -1052,7 +1093,35 @@ bool rt_small_supported(const stgcn_model_desc &m, int B) {
     c_max = d.c_out > c_max ? d.c_out : c_max;
     c_max = d.c_in > c_max ? d.c_in : c_max;
   }
+  // the y buffer doubles as scratch for the input frame (in_feat * V) and the pooled features (c_last)
+  const long long ybuf = (long long)(m.partitions + 1) * (c_max / rts::kNC) * m.num_joints;
+  if ((long long)m.in_feat * m.num_joints > ybuf || m.layers[m.num_layers - 1].c_out > ybuf) return false;
   return rts::smem_floats(c_max, m.num_joints, m.partitions) * sizeof(float) <= 220 * 1024;
+}
+
+// per-joint-weight GEMM + streaming state kernel for every layer (static properties of the model only,
+// so that the state layout never depends on whether operands were prepared)
+bool rt_all_gw_static(const stgcn_model_desc &m) {
+  if ((m.reserved & 2) == 0 || m.math == STGCN_MATH_FP32 || !rt_split_enabled() || !embed_warp_path(m) ||
+      m.norm != STGCN_NORM_LAYERNORM || !tc::gcnw_enabled())
+    return false;
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    if (d.norm != STGCN_NORM_LAYERNORM || d.a_per_sample || !d.rt) return false;
+    if (!tc::gcn_tc_supported(d.c_in, d.c_out, m.num_joints, m.partitions) ||
+        !tc::gcnw_supported(d.c_in, d.c_out, m.num_joints, m.partitions) || !rt_update_supported(m.num_joints, d.c_out))
+      return false;
+    if (d.residual == STGCN_RES_CONV && !tc::gcn_tc_supported(d.c_in, d.c_out, m.num_joints, 1)) return false;
+  }
+  return true;
+}
+// bf16 mode, many streams: the FIFO is stored as bf16 (the accumulators stay fp32): 2 + 2 + 4 + 4 bytes of
+// state traffic per element and step instead of 16
+bool rt_fifo_bf16(const stgcn_model_desc &m, int B) {
+  if (m.math != STGCN_MATH_BF16 || rt_small_supported(m, B) || !rt_stream_enabled() || !rt_all_gw_static(m)) return false;
+  for (int i = 0; i < m.num_layers; ++i)
+    if (!rt_stream_supported(m.num_joints, m.layers[i].c_out)) return false;
+  return true;
 }
 
 int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logits, int B, Bump &ws,
@@ -1067,6 +1136,7 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     rts::Params P{};
     P.num_layers = m.num_layers; P.V = V; P.K = K; P.in_feat = m.in_feat; P.num_classes = m.num_classes; P.B = B;
     P.eps = kEps;
+    P.period = rt_counter_period(m);
     P.x = x; P.logits = logits;
     P.norm_in_w = m.norm_in_w; P.norm_in_b = m.norm_in_b;
     P.fcn_in_w = m.fcn_in_w; P.fcn_in_b = m.fcn_in_b;
@@ -1082,10 +1152,15 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
       if (have) {
         lp = prep_take(d, K, V, pb, (m.reserved & 2) != 0);
       } else {
-        lp = prep_take(d, K, V, ws, (m.reserved & 2) != 0);
+        // no prepared operands (math = fp32, or the caller did not prepare): the cluster kernel reads
+        // only the (k, w)-ordered adjacency CSR, so build just that -- not the tensor-core operand set
+        lp.kw_ptr = ws.take<int>((size_t)K * V + 1);
+        lp.kw_va = ws.take<int2>((size_t)K * V * V);
         if (!ws.measuring()) {
-          STGCN_REQUIRE(!ws.overflow, "workspace too small (rt step operands)");
-          if (prep_run(d, K, V, lp, st)) return 1;
+          STGCN_REQUIRE(!ws.overflow, "workspace too small (rt step adjacency)");
+          ProfScope ps(KC_MISC, st);
+          tc::k_build_adj_csr_kw<<<1, 128, (K * V + 1) * sizeof(int), st>>>(d.a_eff, K, V, lp.kw_ptr, lp.kw_va);
+          STGCN_LAUNCH_OK();
         }
       }
       rts::Layer &R = P.layer[i];
@@ -1139,6 +1214,11 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     }
   }
   const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
+  const bool fifo16 = rt_fifo_bf16(m, B);
+  STGCN_REQUIRE(!fifo16 || all_gw || ws.measuring(),
+                "rtstgcn_step: bf16 continual mode stores the FIFO as bf16 and needs prepared operands "
+                "(stgcn_model_prepare)");
+  STGCN_REQUIRE(ws.measuring() || !ws.overflow, "rtstgcn_step: workspace too small (%zu B given)", ws.cap);
   if (embed(m, x, buf[0], B, 1, ws, st, nullptr, all_gw ? planes : 0)) return 1;
   char *sb = static_cast<char *>(state);
   int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters);
@@ -1153,14 +1233,14 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     if (have) P = prep_take(d, K, V, pb, sparse);
     const bool last = i + 1 == m.num_layers;
     if (rt_layer_step_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], fifo, acc, counter, B, ws, st,
-                           have ? &P : nullptr, all_gw, all_gw, all_gw && !last))
+                           have ? &P : nullptr, all_gw, all_gw, all_gw && !last, fifo16 && all_gw))
       return 1;
     cur ^= 1;
   }
   const int c_last = m.layers[m.num_layers - 1].c_out;
   if (pool_fc(buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, ws, st)) return 1;
   if (!ws.measuring()) {
-    k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(counter, 0, B);
+    k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(counter, 0, B, rt_counter_period(m));
     STGCN_LAUNCH_OK();
   }
   return 0;
@@ -1494,9 +1574,10 @@ int rtstgcn_state_reset(const stgcn_model_desc *m, void *state, int B, int first
   for (int i = 0; i < m->num_layers; ++i) {
     const stgcn_layer_desc &d = m->layers[i];
     size_t per = (size_t)m->num_joints * d.c_out * sizeof(float);
+    const size_t perf = rt_fifo_bf16(*m, B) ? per / 2 : per;
     int F = d.stride * (d.kernel - 1) + 1;
     for (int f = 0; f < F; ++f)
-      STGCN_CUDA_OK(cudaMemsetAsync(sb + L.fifo[i] + ((size_t)f * B + first) * per, 0, per * count, st));
+      STGCN_CUDA_OK(cudaMemsetAsync(sb + L.fifo[i] + ((size_t)f * B + first) * perf, 0, perf * count, st));
     for (int s = 0; s < d.stride; ++s)
       STGCN_CUDA_OK(cudaMemsetAsync(sb + L.acc[i] + ((size_t)s * B + first) * per, 0, per * count, st));
   }
@@ -1552,7 +1633,8 @@ int rtstgcn_layer_step(const stgcn_layer_desc *d, int K, int V, int math, const 
   float *acc = fifo + (size_t)F * B * V * d->c_out;
   if (to_ntvc(x, xin, B, d->c_in, V, d->c_in, st)) return 1;
   if (rt_layer_step_ntvc(*d, K, V, math, xin, out, fifo, acc, frame_counter, B, ws, st)) return 1;
-  k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(frame_counter, 0, B);
+  k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(frame_counter, 0, B,
+                                                   rt_counter_period_of(F, d->stride, 1));
   STGCN_LAUNCH_OK();
   return to_nctv(out, y, B, d->c_out, V, d->c_out, st);
 }

@@ -11,7 +11,8 @@ tot = 0.0
 for i, (k, v) in enumerate(d.items()):
     us = float(v.get('gpu__time_duration', '0').replace(',', '')) / 1e3
     tot += us
-    print("%3d %-44s %9.1f us  tensor %5s%%  lts %5s%%  dram %5s%%  issue %5s%%" % (
+    mb = lambda key: ('%8.1f' % (float(v[key].replace(',', '')) / 1e6)) if key in v else '       -'
+    print("%3d %-44s %9.1f us  tensor %5s%%  lts %5s%%  dram %5s%%  issue %5s%%  dram rd/wr MB %s %s" % (
         i, v['k'], us, v.get('sm__pipe_tensor_cycles_active', '-'), v.get('lts__throughput', '-'),
-        v.get('dram__throughput', '-'), v.get('smsp__issue_active', '-')))
+        v.get('dram__throughput', '-'), v.get('smsp__issue_active', '-'), mb('dram__bytes_read'), mb('dram__bytes_write')))
 print("total %.1f us" % tot)
