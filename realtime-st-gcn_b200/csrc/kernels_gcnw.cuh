@@ -163,7 +163,9 @@ __device__ __forceinline__ void wait_flag(const unsigned *p, unsigned target, un
   }
 }
 constexpr int kGwLnThreads = 256;     // LN warps of the fused stage
-constexpr int kGwLnParts = 8;         // LN work items per frame group (16 frames each)
+constexpr int kGwLnFrames = 4;        // frames per LN work item (one warp)
+constexpr int kGwLnItems = 128 / kGwLnFrames;   // LN work items per frame group
+constexpr int kGwPubRing = 4;         // tiles the epilogue may run ahead of the publisher warp
 
 constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B producer, 3.. epilogue
 
@@ -171,7 +173,7 @@ constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B 
 // and one weight stage both weight planes, so the MMA issuer waits on two barriers per twelve MMAs
 // instead of five per twelve, and the weight hi plane is loaded once instead of twice.
 template <int CO, bool MERGE, bool FUSE>
-__global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
+__global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1)
     k_gcnw(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GcnwParams p) {
   constexpr int kAPlane = 128 * 128;            // [128 frames][64 ch] bf16
   constexpr int kBPlane = CO * 128;             // [CO][64 ch] bf16
@@ -185,8 +187,8 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
   const uint32_t sB = sA + SA * kABytes;
   const uint32_t sPatch = sB + SB * kBBytes;
   const uint32_t sTab = sPatch + kPatchTotal;                    // ptr[33] + src[192]
-  const uint32_t sMr = sTab + 1024;                              // FUSE: (mean, rstd) of the group's 128 frames
-  const uint32_t sBar = sMr + 1024;
+  const uint32_t sPub = sTab + 1024;                             // FUSE: publisher barriers [kGwPubRing] + published-tile count
+  const uint32_t sBar = sPub + 1024;
   const uint32_t bTmemFull = sBar, bTmemEmpty = sBar + 16;
   const uint32_t bFullA = sBar + 32, bEmptyA = bFullA + 8 * SA;
   const uint32_t bFullB = bEmptyA + 8 * SA, bEmptyB = bFullB + 8 * SB;
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
   uint8_t *s_patch = gen_base + (sPatch - smem_base);
   int *s_ptr = reinterpret_cast<int *>(gen_base + (sTab - smem_base));
   int *s_src = s_ptr + 40;
-  float2 *s_mr = reinterpret_cast<float2 *>(gen_base + (sMr - smem_base));
+  volatile unsigned *s_pubcount = reinterpret_cast<volatile unsigned *>(gen_base + (sPub - smem_base) + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.Cin / 64;
@@ -221,6 +223,10 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
     for (int i = 0; i < SB; ++i) {
       mbar_init(bFullB + 8 * i, 1);
       mbar_init(bEmptyB + 8 * i, 1);
+    }
+    if (FUSE) {
+      for (int i = 0; i < kGwPubRing; ++i) mbar_init(sPub + 8 * i, 4 * kEpiNH);
+      *s_pubcount = 0u;
     }
     fence_barrier_init();
   }
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
     const int c0 = h * CH;
     uint8_t *patch = s_patch + (warp - 3) * kPatchBytes;
     uint8_t *mine = patch + lane * kPatchPitch;
-    int buf = 0, t_ph = 0;
+    int buf = 0, t_ph = 0, tile_k = 0;
     float v[16];
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int w = item % p.V;
@@ -385,12 +391,12 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
       // issued before the accumulator wait so that its L2 latency is hidden.  Relaxed on purpose: only
       // stores follow (they cannot be speculated), and an acquire would invalidate the L1 that holds
       // the bias tables once per tile.
-      unsigned freed = kGwLnParts;
+      unsigned freed = kGwLnItems;
       if (FUSE && grp >= p.R && lane == 0) freed = ld_relaxed_gpu(p.done + (grp - p.R));
       mbar_wait(bTmemFull + 8 * buf, t_ph);
       tc_fence_after();
       if (FUSE) {
-        if (grp >= p.R && lane == 0) wait_flag<false>(p.done + (grp - p.R), (unsigned)kGwLnParts, freed);
+        if (grp >= p.R && lane == 0) wait_flag<false>(p.done + (grp - p.R), (unsigned)kGwLnItems, freed);
         __syncwarp();
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * CO);
@@ -430,54 +436,89 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(bTmemEmpty + 8 * buf);
       if (FUSE) {
-        // publish the row partial (mean, M2), then count this warp's share of the tile in ready[group]
+        // row partial (mean, M2); then hand the tile to the publisher warp through a CTA-scope mbarrier: the
+        // gpu-scope release (a fence that waits for this SM's outstanding stores) must not sit in the
+        // epilogue's critical path
         if (row_ok) {
           const float m_r = shift + s1 * (1.f / (float)CH);
           const float M2_r = fmaxf(s2 - s1 * s1 * (1.f / (float)CH), 0.f);
           p.sring[(((size_t)slot * 128 + q * 32 + lane) * p.V + w) * kEpiNH + h] = make_float2(m_r, M2_r);
         }
-        __threadfence();
         __syncwarp();
-        if (lane == 0) atomicAdd(p.ready + grp, 1u);
+        if (lane == 0) {
+          while (*s_pubcount + (unsigned)kGwPubRing <= (unsigned)tile_k) __nanosleep(64);
+          mbar_arrive(sPub + 8 * (tile_k % kGwPubRing));
+        }
+        ++tile_k;
       }
       buf ^= 1;
       if (buf == 0) t_ph ^= 1;
     }
-  } else if (FUSE) {
+  } else if (FUSE && warp == 3 + 4 * kEpiNH) {
+    // ---- publisher: tiles whose eight epilogue warps have arrived become visible to the other CTAs ----
+    // (bar.sync-style cumulativity: the epilogue's stores happen-before its CTA-scope arrive, the fence
+    // below publishes them at gpu scope; several finished tiles share one fence)
+    if (lane == 0) {
+      const int ntiles = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      int k = 0;
+      while (k < ntiles) {
+        mbar_wait<32>(sPub + 8 * (k % kGwPubRing), (uint32_t)(k / kGwPubRing) & 1u);
+        int k2 = k + 1;
+        while (k2 < ntiles && k2 < k + kGwPubRing - 1 &&
+               mbar_try_wait(sPub + 8 * (k2 % kGwPubRing), (uint32_t)(k2 / kGwPubRing) & 1u))
+          ++k2;
+        __threadfence();
+        for (int j = k; j < k2; ++j)
+          atomicAdd(p.ready + (blockIdx.x + j * gridDim.x) / p.V, (unsigned)(4 * kEpiNH));
+        *s_pubcount = (unsigned)k2;
+        k = k2;
+      }
+    }
+  } else if (FUSE && warp > 3 + 4 * kEpiNH) {
     // ---- LN warps: normalise complete frame groups out of their ring slots ----
-    // Work item = (group, part): kGwLnParts parts of 128 / kGwLnParts frames each, dealt round-robin over
-    // the CTAs, so that every CTA's LN warps are busy on the few groups that are in flight (with one CTA
-    // per group the stage was bound by the ring: R groups in flight x one CTA's load latency each).
+    // Work item = kGwLnFrames consecutive frames of a group, one WARP per item, items handed out in order by
+    // a global ticket counter (work conserving: only the few groups in flight have work).  No block barrier
+    // and no fence: a warp polls ready[group] with relaxed loads and acquires once; it has consumed all its
+    // loads of the slot before it counts the item in done[group].
     constexpr int C4 = CO / 4, kSh = (CO == 64) ? 4 : (CO == 128 ? 5 : 6);
-    constexpr int FP = 128 / kGwLnParts;                    // frames per part
-    const int lt = threadIdx.x - kGwThreads, lw = lt >> 5;
     const int V = p.V, NP = V * kEpiNH;                     // row partials per frame
-    const int lnitems = p.N * p.tblocks * kGwLnParts;
+    const int groups = p.N * p.tblocks;
+    const unsigned lnitems = (unsigned)groups * kGwLnItems;
+    unsigned *ticket = p.ready + 2 * (size_t)groups;        // [ready | done | ticket]
     const unsigned target = (unsigned)(V * 4 * kEpiNH);     // epilogue warps per group
     const uint32_t vmagic = (uint32_t)((0x100000000ull + (unsigned)V - 1) / (unsigned)V);   // x / V for x < 65536
     const float inv_np = 1.f / (float)NP, inv_cv = 1.f / (float)(V * CO - 1);
-    for (int li = blockIdx.x; li < lnitems; li += gridDim.x) {
-      const int grp = li / kGwLnParts, part = li - grp * kGwLnParts;
+    unsigned li = 0;
+    if (lane == 0) li = atomicAdd(ticket, 1u);
+    li = __shfl_sync(0xffffffffu, li, 0);
+    while (li < lnitems) {
+      const int grp = (int)(li / kGwLnItems), it4 = (int)(li % kGwLnItems);
       const int slot = grp % p.R;
       const int tb = grp % p.tblocks, n = grp / p.tblocks;
-      const int f0 = part * FP;
-      int nf = p.T - tb * 128 - f0;                          // valid frames of this part
-      nf = nf < 0 ? 0 : (nf > FP ? FP : nf);
-      if (lt == 0) {
-        // relaxed polls (an acquire per poll would invalidate the SM's L1 under the epilogue warps), then
-        // one fence: relaxed load + fence = acquire.  The slot is read with ld.global.cg (L2) anyway.
+      const int f0 = it4 * kGwLnFrames;
+      int nf = p.T - tb * 128 - f0;                          // valid frames of this item
+      nf = nf < 0 ? 0 : (nf > kGwLnFrames ? kGwLnFrames : nf);
+      unsigned nli = 0;
+      if (lane == 0) {
+        nli = atomicAdd(ticket, 1u);                         // next ticket: its latency hides behind this item
         wait_flag<false>(p.ready + grp, target, ld_relaxed_gpu(p.ready + grp));
-        __threadfence();
+        (void)ld_acquire_gpu(p.ready + grp);
       }
-      asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
-      // per-frame statistics: warp lw merges the V * kEpiNH row partials of frames lw, lw + 8, ...
+      __syncwarp();
+      // statistics of the item's frames (merge of the V * kEpiNH row partials, Chan et al.)
+      float fm[kGwLnFrames], fr[kGwLnFrames];
       const float2 *sp = p.sring + ((size_t)slot * 128 + f0) * NP;
-      for (int f = lw; f < nf; f += kGwLnThreads / 32) {
-        const float2 a0 = lane < NP ? __ldcg(sp + (size_t)f * NP + lane) : make_float2(0.f, 0.f);
-        const float2 a1 = lane + 32 < NP ? __ldcg(sp + (size_t)f * NP + lane + 32) : make_float2(0.f, 0.f);
-        const float ref = __shfl_sync(0xffffffffu, a0.x, 0);
-        const float e0 = lane < NP ? a0.x - ref : 0.f, e1 = lane + 32 < NP ? a1.x - ref : 0.f;
-        float sd = e0 + e1, sdd = fmaf(e0, e0, e1 * e1), sm2 = a0.y + a1.y;
+      float2 a0[kGwLnFrames], a1[kGwLnFrames];
+#pragma unroll
+      for (int f = 0; f < kGwLnFrames; ++f) {
+        a0[f] = (f < nf && lane < NP) ? __ldcg(sp + (size_t)f * NP + lane) : make_float2(0.f, 0.f);
+        a1[f] = (f < nf && lane + 32 < NP) ? __ldcg(sp + (size_t)f * NP + lane + 32) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int f = 0; f < kGwLnFrames; ++f) {
+        const float ref = __shfl_sync(0xffffffffu, a0[f].x, 0);
+        const float e0 = lane < NP ? a0[f].x - ref : 0.f, e1 = lane + 32 < NP ? a1[f].x - ref : 0.f;
+        float sd = e0 + e1, sdd = fmaf(e0, e0, e1 * e1), sm2 = a0[f].y + a1[f].y;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           sd += __shfl_xor_sync(0xffffffffu, sd, o);
@@ -486,10 +527,10 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
         }
         const float mean = ref + sd * inv_np;
         const float tq = sm2 + (float)(CO / kEpiNH) * fmaxf(sdd - sd * sd * inv_np, 0.f);
-        if (lane == 0) s_mr[f] = make_float2(mean, 1.f / sqrtf(tq * inv_cv + p.eps));
+        fr[f] = 1.f / sqrtf(tq * inv_cv + p.eps);
+        fm[f] = -mean * fr[f];
       }
-      asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
-      // one streaming pass over the part: element i = (frame, joint, channel quad), contiguous in the slot
+      // one streaming pass over the item: element i = (frame, joint, channel quad), contiguous in the slot
       // and in the output
       const float4 *zs = reinterpret_cast<const float4 *>(p.zring + ((size_t)slot * 128 + f0) * V * CO);
       const int total = nf * V * C4;
@@ -497,29 +538,31 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
       const size_t ob = (size_t)fo * V * CO;
       constexpr int U = 8;
 #pragma unroll 1
-      for (int i0 = lt; i0 < total; i0 += kGwLnThreads * U) {
+      for (int i0 = lane; i0 < total; i0 += 32 * U) {
         float4 a[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * kGwLnThreads;
+          const int i = i0 + u * 32;
           a[u] = i < total ? __ldcg(zs + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * kGwLnThreads;
+          const int i = i0 + u * 32;
           if (i < total) {
             const int row = i >> kSh, g4 = i & (C4 - 1);
             const int f = (int)__umulhi((uint32_t)row, vmagic), w = row - f * V;
-            const float2 mr = s_mr[f];
-            const float nmr = -mr.x * mr.y;
+            float rs = fr[0], nmr = fm[0];
+#pragma unroll
+            for (int ff = 1; ff < kGwLnFrames; ++ff)
+              if (f == ff) { rs = fr[ff]; nmr = fm[ff]; }
             const int ti = (g4 * V + w) * 4;
             const float4 gg = __ldg(reinterpret_cast<const float4 *>(p.n_wT + ti));
             const float4 oo = __ldg(reinterpret_cast<const float4 *>(p.n_bT + ti));
             float4 r;
-            r.x = fmaf(fmaf(a[u].x, mr.y, nmr), gg.x, oo.x);
-            r.y = fmaf(fmaf(a[u].y, mr.y, nmr), gg.y, oo.y);
-            r.z = fmaf(fmaf(a[u].z, mr.y, nmr), gg.z, oo.z);
-            r.w = fmaf(fmaf(a[u].w, mr.y, nmr), gg.w, oo.w);
+            r.x = fmaf(fmaf(a[u].x, rs, nmr), gg.x, oo.x);
+            r.y = fmaf(fmaf(a[u].y, rs, nmr), gg.y, oo.y);
+            r.z = fmaf(fmaf(a[u].z, rs, nmr), gg.z, oo.z);
+            r.w = fmaf(fmaf(a[u].w, rs, nmr), gg.w, oo.w);
             if (p.relu) {
               r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
             }
@@ -540,13 +583,11 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? kGwLnThreads : 0), 1)
           }
         }
       }
-      // every LN thread has consumed its loads of the part: count it; the slot is released to the epilogue of
-      // group grp + R when all kGwLnParts parts are in
-      asm volatile("bar.sync 2, %0;" ::"n"(kGwLnThreads) : "memory");
-      if (lt == 0) {
-        __threadfence();
-        atomicAdd(p.done + grp, 1u);
-      }
+      // every lane has consumed its loads of the slot (their values were used above): count the item; the slot
+      // is released to the epilogue of group grp + R when all kGwLnItems items are in
+      __syncwarp();
+      if (lane == 0) atomicAdd(p.done + grp, 1u);
+      li = __shfl_sync(0xffffffffu, nli, 0);
     }
   }
   tc_fence_before();
@@ -718,7 +759,7 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
     // producers wait for consumers in other CTAs: every CTA must be resident -> cooperative launch
     void *args[3] = {&tm_x, &tm_w, &p};
     STGCN_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_gcnw<CO, MERGE, FUSE>), dim3(grid),
-                                              dim3(kGwThreads + kGwLnThreads), args, (size_t)smem, st));
+                                              dim3(kGwThreads + 32 + kGwLnThreads), args, (size_t)smem, st));
   } else {
     k_gcnw<CO, MERGE, FUSE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_w, p);
   }

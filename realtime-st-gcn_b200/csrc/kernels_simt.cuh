@@ -684,6 +684,39 @@ inline int launch_rt_update(const RtUpdateArgs &a, cudaStream_t st) {
 }
 inline bool rt_update_supported(int V, int C) { return C % 4 == 0 && (V * C / 4 + 255) / 256 <= 7; }
 
+// --------------------------------------------------------------------------- //
+// RT head: mean over the V joints of every stream + fcn_out (rtstgcn.py:153-157), kRtHeadStreams streams
+// per block so that the classifier matrix is read once per block instead of once per stream (the
+// two-kernel pool + fc cost 57 us of a 1.5 ms step at 4096 streams, mostly re-reading W from L2).
+// x [B*V, C] fp32 rows -> logits [B, classes]
+// --------------------------------------------------------------------------- //
+constexpr int kRtHeadStreams = 16;
+__global__ void __launch_bounds__(256)
+    k_rt_head(const float *__restrict__ x, int B, int V, int C, const float *__restrict__ W,
+              const float *__restrict__ bias, int classes, float *__restrict__ logits) {
+  extern __shared__ float s_pool[];                       // [kRtHeadStreams][C]
+  const int b0 = blockIdx.x * kRtHeadStreams;
+  const int nb = B - b0 < kRtHeadStreams ? B - b0 : kRtHeadStreams;
+  const float inv_v = 1.f / (float)V;
+  for (int idx = threadIdx.x; idx < nb * C; idx += 256) {
+    const int s = idx / C, c = idx - s * C;
+    const float *xp = x + ((long long)(b0 + s) * V) * C + c;
+    float a = 0.f;
+    for (int v = 0; v < V; ++v) a += __ldg(xp + (long long)v * C);
+    s_pool[s * C + c] = a * inv_v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int pair = warp; pair < nb * classes; pair += 8) {
+    const int m = pair / nb, s = pair - m * nb;             // the warps of a block share a W row (L1 hit)
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(W + (long long)m * C + c), s_pool[s * C + c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) logits[(long long)(b0 + s) * classes + m] = a + __ldg(bias + m);
+  }
+}
+
 // per-stream frame counters advance modulo `period` = lcm of every layer's ring and accumulator sizes
 // (the kernels only use cnt % F and cnt % S), so they never overflow on a long-running stream;
 // period == 0: plain increment

@@ -17,15 +17,20 @@ namespace {
 
 constexpr float kEps = 1e-5f;  // reference LayerNorm / BatchNorm eps (layernorm.py:8)
 
-// measurement aid (STGCN_DEBUG=1: skip tensor-core epilogues, 2: skip transform math); results are
-// then wrong on purpose -- used only to attribute time between pipeline roles
+// Measurement aid, compiled in only with -DSTGCN_DEBUG_BUILD (STGCN_NVCC_EXTRA): STGCN_DEBUG bits skip
+// parts of the kernels (1: tensor-core epilogues, 2: transform math, ...) to attribute time between
+// pipeline roles -- results are then wrong on purpose.  The shipped library ignores the variable.
 inline int debug_mode() {
+#ifdef STGCN_DEBUG_BUILD
   static int m = -1;
   if (m < 0) {
     const char *e = getenv("STGCN_DEBUG");
     m = e ? atoi(e) : 0;
   }
   return m;
+#else
+  return 0;
+#endif
 }
 
 // STGCN_DEBUG & 4: after a tensor-core launch, synchronise and print CTA 0's role/wait cycle counters
@@ -271,7 +276,7 @@ int gcnw_stage(int c_out, const __nv_bfloat16 *xh, const __nv_bfloat16 *wsc, tc:
     const int groups = g.N * ((g.T + 127) / 128);
     g.zring = ws.take<float>(tc::gcnw_ring_floats(V, c_out));
     g.sring = ws.take<float2>(tc::gcnw_sring_float2(V, c_out));
-    g.ready = ws.take<unsigned>((size_t)2 * groups);
+    g.ready = ws.take<unsigned>((size_t)2 * groups + 1);           // [ready | done | LN ticket counter]
     g.done = g.ready ? g.ready + groups : nullptr;
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (graph-conv stage ring)");
@@ -279,7 +284,7 @@ int gcnw_stage(int c_out, const __nv_bfloat16 *xh, const __nv_bfloat16 *wsc, tc:
       g.n_wT = l.n_wT; g.n_bT = l.n_bT; g.relu = l.relu; g.eps = l.eps;
       g.out_f32 = l.out_f32; g.out_hi = l.out_hi; g.out_lo = l.out_lo;
       g.out_T = l.out_T; g.out_t0 = l.out_t0;
-      STGCN_CUDA_OK(cudaMemsetAsync(g.ready, 0, sizeof(unsigned) * 2 * groups, st));
+      STGCN_CUDA_OK(cudaMemsetAsync(g.ready, 0, sizeof(unsigned) * (2 * groups + 1), st));
       ProfScope ps(KC_GEMM_1X1, st);
       if (tc::launch_gcnw(c_out, xh, wsc, g, T_full, fstride, cap, plane_stride, st)) return 1;
       STGCN_LAUNCH_OK();
@@ -1238,7 +1243,12 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     cur ^= 1;
   }
   const int c_last = m.layers[m.num_layers - 1].c_out;
-  if (pool_fc(buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, ws, st)) return 1;
+  if (!ws.measuring()) {
+    ProfScope ps(KC_POOL, st);
+    k_rt_head<<<cdiv(B, kRtHeadStreams), 256, sizeof(float) * kRtHeadStreams * c_last, st>>>(
+        buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits);
+    STGCN_LAUNCH_OK();
+  }
   if (!ws.measuring()) {
     k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(counter, 0, B, rt_counter_period(m));
     STGCN_LAUNCH_OK();

@@ -164,6 +164,9 @@ class Model(nn.Module):
         if self.normalization != 'LayerNorm' or self.math == 'fp32':
             raise RuntimeError("T-split needs LayerNorm and math in {'bf16x3','bf16'}: batch statistics "
                                "would span ranks, and the halo lives in the tensor-core operand layout")
+        # same check on every rank, before anything is launched (a rank-local failure would leave the
+        # other ranks blocked in the halo exchange)
+        tsplit.validate_chunks(total_frames, getattr(exchange, 'world', 1), [g.stride for g in self.gcn_networks])
         lib = _lib.load()
         m, _ = self._descriptor()
         need = lib.stgcn_model_halo_bytes(ctypes.byref(m), n)

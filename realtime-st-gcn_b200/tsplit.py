@@ -50,6 +50,25 @@ def chunk_bounds(num_frames, world, align):
     return bounds
 
 
+def validate_chunks(num_frames, world, strides):
+    """Host-side precondition of the T-split forward, evaluated identically on EVERY rank from the
+    globally known sizes (so a bad split raises everywhere instead of failing on one rank while the
+    others block in the halo exchange): every chunk must keep at least ``HALO_FRAMES`` frames at every
+    layer's resolution, because a rank can only send halo frames it owns."""
+    bounds = chunk_bounds(num_frames, world, total_stride(strides))
+    if world == 1:
+        return bounds
+    for r, (a, b) in enumerate(bounds):
+        t = b - a
+        for i, s in enumerate(strides):
+            if t < HALO_FRAMES:
+                raise ValueError("T-split: rank %d holds %d frame(s) at layer %d (< %d halo frames); use fewer "
+                                 "ranks or a longer trial (%d frames over %d ranks)"
+                                 % (r, t, i, HALO_FRAMES, num_frames, world))
+            t = (t - 1) // int(s) + 1
+    return bounds
+
+
 def frames_after(t, strides):
     """Frames left after the trunk's temporal down-sampling (T_out = (T-1)//s + 1 per layer)."""
     for s in strides:

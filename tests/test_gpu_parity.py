@@ -260,7 +260,8 @@ def test_rt_batchnorm_rejected(pkg, syn, cuda):
 
 
 # ------------------------------------------------------------------ tensor-core (tcgen05) arithmetic
-BF16_TOL = 3e-2      # stated bf16 tolerance (single-pass bf16 operands, fp32 accumulate/statistics)
+BF16_TOL = 2e-2      # stated bf16 tolerance (SURVEY 8d anchor; single-pass bf16 operands, fp32 accumulate/statistics)
+BF16_TOP1 = 0.98     # and top-1 agreement with the fp32 reference
 
 
 def _layer_case(cuda, c, stride, residual, v_graph, n, t, seed):
@@ -375,7 +376,7 @@ def test_rt_full_tensor_core(pkg, syn, cuda, tag, math, tol):
     assert err < tol, err
     if math == 'bf16':
         agree = (out.cpu().argmax(1) == ref.argmax(1)).float().mean().item()
-        assert agree >= 0.95, agree          # stated bf16 tolerance: top-1 agreement with fp32
+        assert agree >= BF16_TOP1, agree     # stated bf16 tolerance: top-1 agreement with fp32
 
 
 def test_rt_cuda_graph_and_many_streams_tensor_core(pkg, syn, cuda):
@@ -464,7 +465,8 @@ class _LocalExchange:
 
 
 @pytest.mark.parametrize('world,total_frames,math,tol', [(2, 64, 'bf16x3', TOL), (3, 93, 'bf16x3', TOL),
-                                                         (2, 40, 'bf16', BF16_TOL)])
+                                                         (2, 40, 'bf16', BF16_TOL), (2, 4096, 'bf16x3', TOL),
+                                                         (4, 4101, 'bf16x3', TOL)])
 def test_tsplit_emulated_ranks(pkg, syn, cuda, world, total_frames, math, tol):
     """T-split forward through the C ABI: per-layer halo frames packed, swapped and unpacked in the
     tensor-core operand layout (stride-1 and stride-2 layers, channel-changing layers), pooled sums

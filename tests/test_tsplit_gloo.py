@@ -30,6 +30,20 @@ def test_chunk_bounds(pkg):
     assert ts.frames_after(301, [2, 2]) == 76
 
 
+def test_validate_chunks_is_collective(pkg):
+    """a ragged tail of fewer than HALO_FRAMES frames (at any layer's resolution) must be
+    rejected from the globally known sizes -- identically on every rank, before any launch."""
+    ts = pkg.tsplit
+    strides = [1, 1, 1, 2, 1, 1, 2, 1, 1]
+    assert ts.validate_chunks(262144, 8, strides) == ts.chunk_bounds(262144, 8, 4)
+    assert ts.validate_chunks(17, 1, strides) == [(0, 17)]          # a single rank needs no halo
+    assert ts.validate_chunks(64, 4, strides)[-1] == (48, 64)       # 16 frames per rank -> 4 at the last layers
+    with pytest.raises(ValueError, match='halo'):
+        ts.validate_chunks(5, 2, strides)                            # the ragged tail: rank 1 would hold 1 frame
+    with pytest.raises(ValueError, match='halo'):
+        ts.validate_chunks(32, 4, strides)                           # 8 frames per rank -> 2 at the last layers
+
+
 def test_trial_sharding_partition():
     """Trial/stream sharding needs no collective: the per-rank slices tile the batch exactly."""
     def shard(n, world, rank):
