@@ -11,7 +11,8 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p, POINTE
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, 'csrc', 'libstgcn_b200.so')
+# STGCN_LIB: alternative build of the same library (e.g. a -DSTGCN_DEBUG_BUILD measurement build)
+_LIB_PATH = os.environ.get('STGCN_LIB') or os.path.join(_HERE, 'csrc', 'libstgcn_b200.so')
 
 ABI_VERSION = 2
 NORM_LAYERNORM, NORM_BATCHNORM = 0, 1

@@ -28,20 +28,26 @@ def stale():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """``out``/``extra_flags``: build a variant next to the library (e.g. the measurement build
+    ``libstgcn_b200_dbg.so`` with ``-DSTGCN_DEBUG_BUILD``, selected at run time with ``STGCN_LIB``)."""
+    if out is None and not force and not stale():
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
-    extra = os.environ.get('STGCN_NVCC_EXTRA', '').split()     # e.g. -DSTGCN_G3_DEBUG (role cycle counters)
+    extra = os.environ.get('STGCN_NVCC_EXTRA', '').split() + list(extra_flags)
+    out = out or LIB
     cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
-          ['-o', LIB] + [os.path.join(HERE, s) for s in SOURCES]
+          ['-o', out] + [os.path.join(HERE, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (proc.stdout, proc.stderr))
     if verbose:
         print(proc.stderr)
-    return LIB
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--debug' in sys.argv:
+        print(build(out=os.path.join(HERE, 'libstgcn_b200_dbg.so'), extra_flags=['-DSTGCN_DEBUG_BUILD']))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
         while (k2 < ntiles && k2 < k + kGwPubRing - 1 &&
                mbar_try_wait(sPub + 8 * (k2 % kGwPubRing), (uint32_t)(k2 / kGwPubRing) & 1u))
           ++k2;
-        __threadfence();
+        if (!(p.debug & 1024)) __threadfence();             // (debug bit: timing without the release fence)
         for (int j = k; j < k2; ++j)
           atomicAdd(p.ready + (blockIdx.x + j * gridDim.x) / p.V, (unsigned)(4 * kEpiNH));
         *s_pubcount = (unsigned)k2;
@@ -505,6 +505,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
         (void)ld_acquire_gpu(p.ready + grp);
       }
       __syncwarp();
+      if (p.debug & 4096) nf = 0;                            // (debug bit: LN warps only hand the slots back)
       // statistics of the item's frames (merge of the V * kEpiNH row partials, Chan et al.)
       float fm[kGwLnFrames], fr[kGwLnFrames];
       const float2 *sp = p.sring + ((size_t)slot * 128 + f0) * NP;
@@ -566,6 +567,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
             if (p.relu) {
               r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
             }
+            if ((p.debug & 2048) && r.x != 12345.678f) continue;   // (debug bit: no LN stores)
             if (p.out_f32) {
               *reinterpret_cast<float4 *>(p.out_f32 + ob + 4 * (size_t)i) = r;
             } else {

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(TH + 32, TH == 512 ? 1 : (TH == 256 ? 2 : 4)) 
         if (++s == kRtStages) { s = 0; ph ^= 1u; }
       }
     }
+    if (p.debug & 8192) continue;                              // (measurement build: streaming pass only)
     const float mean = rt_block_sum<TH>(sum, s_red) * inv_n;
     float mean_r = 0.f, rstd_r = 1.f;
     if (p.res_mode == 2) mean_r = rt_block_sum<TH>(sum_r, s_red) * inv_n;

@@ -541,6 +541,7 @@ struct RtUpdateArgs {
   const float *r_wT, *r_bT;       // affine of the residual norm, [C/4][V][4]
   float eps;
   float *out;                     // [B*V, C]
+  int debug;                      // measurement build only (STGCN_DEBUG bits)
 };
 
 __device__ __forceinline__ float4 ld_nc_stream4(const float *p) {
@@ -690,7 +691,7 @@ inline bool rt_update_supported(int V, int C) { return C % 4 == 0 && (V * C / 4 
 // two-kernel pool + fc cost 57 us of a 1.5 ms step at 4096 streams, mostly re-reading W from L2).
 // x [B*V, C] fp32 rows -> logits [B, classes]
 // --------------------------------------------------------------------------- //
-constexpr int kRtHeadStreams = 16;
+constexpr int kRtHeadStreams = 8;
 __global__ void __launch_bounds__(256)
     k_rt_head(const float *__restrict__ x, int B, int V, int C, const float *__restrict__ W,
               const float *__restrict__ bias, int classes, float *__restrict__ logits) {
@@ -698,12 +699,35 @@ __global__ void __launch_bounds__(256)
   const int b0 = blockIdx.x * kRtHeadStreams;
   const int nb = B - b0 < kRtHeadStreams ? B - b0 : kRtHeadStreams;
   const float inv_v = 1.f / (float)V;
-  for (int idx = threadIdx.x; idx < nb * C; idx += 256) {
-    const int s = idx / C, c = idx - s * C;
-    const float *xp = x + ((long long)(b0 + s) * V) * C + c;
-    float a = 0.f;
-    for (int v = 0; v < V; ++v) a += __ldg(xp + (long long)v * C);
-    s_pool[s * C + c] = a * inv_v;
+  // pooling: float4 lanes over the channels, 256 / (C/4) streams in parallel, all V loads of a stream in flight
+  const int C4 = C >> 2;
+  if ((C & 3) == 0 && C4 <= 256) {
+    const int c4 = threadIdx.x % C4, sg = threadIdx.x / C4, SG = 256 / C4;
+    if (sg < SG)
+      for (int s = sg; s < nb; s += SG) {
+        const float4 *xp = reinterpret_cast<const float4 *>(x + ((long long)(b0 + s) * V) * C) + c4;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        int v = 0;
+        for (; v + 1 < V; v += 2) {
+          const float4 u0 = __ldg(xp + (long long)v * C4), u1 = __ldg(xp + (long long)(v + 1) * C4);
+          a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+          a1.x += u1.x; a1.y += u1.y; a1.z += u1.z; a1.w += u1.w;
+        }
+        if (v < V) {
+          const float4 u0 = __ldg(xp + (long long)v * C4);
+          a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+        }
+        reinterpret_cast<float4 *>(s_pool + s * C)[c4] =
+            make_float4((a0.x + a1.x) * inv_v, (a0.y + a1.y) * inv_v, (a0.z + a1.z) * inv_v, (a0.w + a1.w) * inv_v);
+      }
+  } else {
+    for (int idx = threadIdx.x; idx < nb * C; idx += 256) {
+      const int s = idx / C, c = idx - s * C;
+      const float *xp = x + ((long long)(b0 + s) * V) * C + c;
+      float a = 0.f;
+      for (int v = 0; v < V; ++v) a += __ldg(xp + (long long)v * C);
+      s_pool[s * C + c] = a * inv_v;
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

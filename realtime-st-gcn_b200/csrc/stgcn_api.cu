@@ -681,6 +681,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       RtUpdateArgs u{};
       u.B = B; u.V = V; u.C = d.c_out;
       u.z = zb;
+      u.debug = debug_mode();
       u.fifo = fifo_bf16 ? nullptr : fifo; u.acc = acc; u.counter = counter;
       u.fifo16 = fifo_bf16 ? reinterpret_cast<__nv_bfloat16 *>(fifo) : nullptr;
       u.fifo_bf16 = fifo_bf16 ? 1 : 0;

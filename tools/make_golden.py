@@ -245,9 +245,48 @@ def gen_rt_offline():
     save('rtstgcn_offline', x=x, logits=logits, h=h, y1=y1, y2=y2, **sd_arrays(sd))
 
 
+def cost_config(**kw):
+    """CoST-GCN reads the 'st-gcn' group plus a per-layer 'dilation' list (costgcn.py:34-63)."""
+    cfg = syn.arch_config('st-gcn', **kw)
+    cfg['st-gcn']['dilation'] = [1] * cfg['st-gcn']['layers']
+    return cfg
+
+
+def run_ref_cost(cfg, sd, x):
+    """Reference CoST-GCN continual loop, one fresh model per stream (its FIFOs are batch-1 plain tensors)."""
+    from models.costgcn.costgcn import Model as RefCost
+    outs = []
+    for b in range(x.shape[0]):
+        m = RefCost(**cfg)
+        m.load_state_dict(sd)
+        m.eval()
+        with torch.no_grad():
+            o = [m(x[b:b + 1, :, t:t + 1]).clone() for t in range(x.shape[2])]
+        outs.append(torch.cat(o, dim=2))
+    return torch.cat(outs, dim=0)
+
+
+def gen_cost_models():
+    """CoST-GCN (models/costgcn/costgcn.py:81-99, 190-211): small model with a stride-2 / channel-changing
+    layer (weights and input stored) and the full PKU trunk (seeds + digest)."""
+    from models.costgcn.costgcn import Model as RefCost
+    cfg = cost_config(num_classes=12, **SMALL)
+    sd = syn.synth_state_dict(RefCost(**cfg).state_dict(), 81)
+    x = syn.synth_input((2, 3, 40, 25), 82)
+    save('costgcn_small', x=x, logits=run_ref_cost(cfg, sd, x), **sd_arrays(sd))
+    cfg = cost_config()
+    sd = syn.synth_state_dict(RefCost(**cfg).state_dict(), 83)
+    x = syn.synth_input((2, 3, 48, 25), 84)
+    save('costgcn_pku', logits=run_ref_cost(cfg, sd, x), seeds=np.array([83, 84]),
+         digest=np.array(syn.state_digest(sd)))
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'offline':
         gen_rt_offline()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'cost':
+        gen_cost_models()
         sys.exit(0)
     gen_graphs()
     gen_primitives()
@@ -255,3 +294,4 @@ if __name__ == '__main__':
     gen_stgcn_models()
     gen_rt_models()
     gen_rt_offline()
+    gen_cost_models()
