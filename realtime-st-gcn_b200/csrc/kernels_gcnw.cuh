@@ -40,6 +40,14 @@ __global__ void k_rows_to_planes(const float *__restrict__ x, __nv_bfloat16 *__r
   if (lo) lo[i] = l;
 }
 
+// LayerNorm affine (C, 1, V) -> [V][C]
+__global__ void k_transpose_cv(const float *__restrict__ in, float *__restrict__ out, int C, int V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * V) return;
+  const int v = i / C, c = i - v * C;
+  out[i] = in[c * V + v];
+}
+
 constexpr int kGwMaxV = 32;
 constexpr int kGwEdgeCap = 6 * kGwMaxV;
 inline int gcnw_edge_cap(int V) { return 6 * V; }
@@ -121,7 +129,8 @@ struct GcnwParams {
   float2 *sring;                // [R][128][V][kEpiNH] (mean, M2) of every (frame, joint, column group)
   unsigned *ready, *done;       // [N * tblocks] tile-arrival count / slot-released flag per frame group
   int R;                        // ring slots
-  const float *n_wT, *n_bT;     // LayerNorm affine, [C/4][V][4]
+  int npc;                      // position chunks per frame block (LN items per group = kGwLnBlocks * npc)
+  const float *n_wV, *n_bV;     // LayerNorm affine as [V][C] (the order in which the LN warps stream a frame)
   int relu;
   float eps;
   float *out_f32;               // normalised output: fp32 rows, or
@@ -163,8 +172,10 @@ __device__ __forceinline__ void wait_flag(const unsigned *p, unsigned target, un
   }
 }
 constexpr int kGwLnThreads = 256;     // LN warps of the fused stage
-constexpr int kGwLnFrames = 4;        // frames per LN work item (one warp)
-constexpr int kGwLnItems = 128 / kGwLnFrames;   // LN work items per frame group
+constexpr int kGwLnFrames = 8;        // frames per LN work item (one warp)
+constexpr int kGwLnBlocks = 128 / kGwLnFrames;  // frame blocks per group; x npc position chunks = LN items per group
+constexpr int kGwLnIters = 13;        // at most this many 32-position steps per item (bounds an item's latency, and
+                                      // with it the number of groups the ring must hold)
 constexpr int kGwPubRing = 4;         // tiles the epilogue may run ahead of the publisher warp
 
 constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B producer, 3.. epilogue
@@ -391,12 +402,13 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
       // issued before the accumulator wait so that its L2 latency is hidden.  Relaxed on purpose: only
       // stores follow (they cannot be speculated), and an acquire would invalidate the L1 that holds
       // the bias tables once per tile.
-      unsigned freed = kGwLnItems;
+      const unsigned ln_per_group = (unsigned)(kGwLnBlocks * p.npc);
+      unsigned freed = ln_per_group;
       if (FUSE && grp >= p.R && lane == 0) freed = ld_relaxed_gpu(p.done + (grp - p.R));
       mbar_wait(bTmemFull + 8 * buf, t_ph);
       tc_fence_after();
       if (FUSE) {
-        if (grp >= p.R && lane == 0) wait_flag<false>(p.done + (grp - p.R), (unsigned)kGwLnItems, freed);
+        if (grp >= p.R && lane == 0) wait_flag<false>(p.done + (grp - p.R), ln_per_group, freed);
         __syncwarp();
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * CO);
@@ -483,7 +495,9 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
     constexpr int C4 = CO / 4, kSh = (CO == 64) ? 4 : (CO == 128 ? 5 : 6);
     const int V = p.V, NP = V * kEpiNH;                     // row partials per frame
     const int groups = p.N * p.tblocks;
-    const unsigned lnitems = (unsigned)groups * kGwLnItems;
+    const unsigned per_group = (unsigned)(kGwLnBlocks * p.npc);
+    const unsigned lnitems = (unsigned)groups * per_group;
+    const int pc_len = ((V * C4 + 31) / 32 + p.npc - 1) / p.npc * 32;   // positions per chunk (multiple of 32)
     unsigned *ticket = p.ready + 2 * (size_t)groups;        // [ready | done | ticket]
     const unsigned target = (unsigned)(V * 4 * kEpiNH);     // epilogue warps per group
     const uint32_t vmagic = (uint32_t)((0x100000000ull + (unsigned)V - 1) / (unsigned)V);   // x / V for x < 65536
@@ -492,10 +506,11 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
     if (lane == 0) li = atomicAdd(ticket, 1u);
     li = __shfl_sync(0xffffffffu, li, 0);
     while (li < lnitems) {
-      const int grp = (int)(li / kGwLnItems), it4 = (int)(li % kGwLnItems);
+      const int grp = (int)(li / per_group), sub = (int)(li % per_group);
+      const int fb = sub / p.npc, pc = sub - fb * p.npc;          // frame block, position chunk
       const int slot = grp % p.R;
       const int tb = grp % p.tblocks, n = grp / p.tblocks;
-      const int f0 = it4 * kGwLnFrames;
+      const int f0 = fb * kGwLnFrames;
       int nf = p.T - tb * 128 - f0;                          // valid frames of this item
       nf = nf < 0 ? 0 : (nf > kGwLnFrames ? kGwLnFrames : nf);
       unsigned nli = 0;
@@ -531,54 +546,50 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
         fr[f] = 1.f / sqrtf(tq * inv_cv + p.eps);
         fm[f] = -mean * fr[f];
       }
-      // one streaming pass over the item: element i = (frame, joint, channel quad), contiguous in the slot
-      // and in the output
+      // streaming pass, position-major: a lane owns the positions p = lane, lane + 32, ... of a frame ((joint,
+      // channel quad), contiguous in the slot, in the output and in the [V][C] affine tables) and applies each
+      // position's affine to all frames of the item -- the two table loads are amortised over kGwLnFrames
+      // elements and every load instruction of the warp covers 512 contiguous bytes (this kernel leaves
+      // ~8 KB of L1: per-element table loads in the [C/4][V][4] epilogue layout ran at L2 latency each)
+      const int VC4 = V * C4;
       const float4 *zs = reinterpret_cast<const float4 *>(p.zring + ((size_t)slot * 128 + f0) * V * CO);
-      const int total = nf * V * C4;
+      const float4 *gw = reinterpret_cast<const float4 *>(p.n_wV), *gb = reinterpret_cast<const float4 *>(p.n_bV);
       const long long fo = (p.out_T ? (long long)n * p.out_T + p.out_t0 : (long long)n * p.T) + tb * 128 + f0;
       const size_t ob = (size_t)fo * V * CO;
-      constexpr int U = 8;
+      (void)kSh; (void)vmagic;
 #pragma unroll 1
-      for (int i0 = lane; i0 < total; i0 += 32 * U) {
-        float4 a[U];
+      const int pos_end = (pc + 1) * pc_len < VC4 ? (pc + 1) * pc_len : VC4;
+      for (int pos = pc * pc_len + lane; pos < pos_end && nf > 0; pos += 32) {
+        float4 a[kGwLnFrames];
+        const float4 gg = __ldg(gw + pos), oo = __ldg(gb + pos);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * 32;
-          a[u] = i < total ? __ldcg(zs + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int f = 0; f < kGwLnFrames; ++f)
+          a[f] = f < nf ? __ldcg(zs + (size_t)f * VC4 + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * 32;
-          if (i < total) {
-            const int row = i >> kSh, g4 = i & (C4 - 1);
-            const int f = (int)__umulhi((uint32_t)row, vmagic), w = row - f * V;
-            float rs = fr[0], nmr = fm[0];
-#pragma unroll
-            for (int ff = 1; ff < kGwLnFrames; ++ff)
-              if (f == ff) { rs = fr[ff]; nmr = fm[ff]; }
-            const int ti = (g4 * V + w) * 4;
-            const float4 gg = __ldg(reinterpret_cast<const float4 *>(p.n_wT + ti));
-            const float4 oo = __ldg(reinterpret_cast<const float4 *>(p.n_bT + ti));
+        for (int f = 0; f < kGwLnFrames; ++f) {
+          if (f < nf) {
+            const float rs = fr[f], nmr = fm[f];
+            const size_t i = (size_t)f * VC4 + pos;
             float4 r;
-            r.x = fmaf(fmaf(a[u].x, rs, nmr), gg.x, oo.x);
-            r.y = fmaf(fmaf(a[u].y, rs, nmr), gg.y, oo.y);
-            r.z = fmaf(fmaf(a[u].z, rs, nmr), gg.z, oo.z);
-            r.w = fmaf(fmaf(a[u].w, rs, nmr), gg.w, oo.w);
+            r.x = fmaf(fmaf(a[f].x, rs, nmr), gg.x, oo.x);
+            r.y = fmaf(fmaf(a[f].y, rs, nmr), gg.y, oo.y);
+            r.z = fmaf(fmaf(a[f].z, rs, nmr), gg.z, oo.z);
+            r.w = fmaf(fmaf(a[f].w, rs, nmr), gg.w, oo.w);
             if (p.relu) {
               r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
             }
             if ((p.debug & 2048) && r.x != 12345.678f) continue;   // (debug bit: no LN stores)
             if (p.out_f32) {
-              *reinterpret_cast<float4 *>(p.out_f32 + ob + 4 * (size_t)i) = r;
+              *reinterpret_cast<float4 *>(p.out_f32 + ob + 4 * i) = r;
             } else {
               const __nv_bfloat162 h01 = __floats2bfloat162_rn(r.x, r.y), h23 = __floats2bfloat162_rn(r.z, r.w);
-              *reinterpret_cast<uint2 *>(p.out_hi + ob + 4 * (size_t)i) =
+              *reinterpret_cast<uint2 *>(p.out_hi + ob + 4 * i) =
                   make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
               if (p.out_lo) {
                 const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
                 const __nv_bfloat162 l01 = __floats2bfloat162_rn(r.x - f01.x, r.y - f01.y);
                 const __nv_bfloat162 l23 = __floats2bfloat162_rn(r.z - f23.x, r.w - f23.y);
-                *reinterpret_cast<uint2 *>(p.out_lo + ob + 4 * (size_t)i) =
+                *reinterpret_cast<uint2 *>(p.out_lo + ob + 4 * i) =
                     make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
               }
             }
@@ -715,12 +726,17 @@ inline bool gcnw_fuse_enabled() {
   }
   return on != 0;
 }
-// ring geometry of the fused stage: slots of [128 frames][V][CO] fp32, at most ~40 MB so that the ring
-// stays L2-resident, at least 8 slots (148 CTAs work on ~148 / V groups at a time)
+// ring geometry of the fused stage: slots of [128 frames][V][CO] fp32.  The ring must hold the groups
+// the GEMM side produces during one LN item's latency (~15 us: up to ~45 groups for C = 64, ~10 for
+// C = 256) and stay L2-resident: ~48 MB, 8..64 slots
 inline int gcnw_ring_slots(int V, int CO) {
   const size_t slot = (size_t)128 * V * CO * sizeof(float);
-  int R = (int)((size_t)40 * 1024 * 1024 / slot);
-  return R > 24 ? 24 : (R < 8 ? 8 : R);
+  int R = (int)((size_t)48 * 1024 * 1024 / slot);
+  return R > 64 ? 64 : (R < 8 ? 8 : R);
+}
+inline int gcnw_ln_chunks(int V, int CO) {
+  const int steps = (V * CO / 4 + 31) / 32;
+  return (steps + kGwLnIters - 1) / kGwLnIters;
 }
 inline size_t gcnw_ring_floats(int V, int CO) { return (size_t)gcnw_ring_slots(V, CO) * 128 * V * CO; }
 inline size_t gcnw_sring_float2(int V, int CO) { return (size_t)gcnw_ring_slots(V, CO) * 128 * V * kEpiNH; }

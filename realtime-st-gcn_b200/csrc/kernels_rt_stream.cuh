@@ -39,7 +39,8 @@ __device__ __forceinline__ uint2 f4_to_bf16x4(float4 v) {
   return make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&c));
 }
 
-constexpr int kRtStages = 6;     // ring of chunk stages per CTA
+constexpr int kRtStages = 3;     // ring of chunk stages per CTA (2-8 CTAs per SM: while one CTA reduces and
+                                 // normalises a stream, the others keep the loads flowing)
 constexpr int kRtMaxChunks = 4;  // chunks (of TH float4 per array) per stream
 
 // sum over the TH compute threads (the producer warp does not take part): named barrier 1
@@ -62,7 +63,7 @@ __device__ __forceinline__ float rt_block_sum(float v, float *s_red) {
 // across stream boundaries, kRtStages ahead; a compute thread keeps its (at most kRtMaxChunks) updated
 // accumulator values and residuals in registers until the stream's LayerNorm statistics are known.
 template <int TH>
-__global__ void __launch_bounds__(TH + 32, TH == 512 ? 1 : (TH == 256 ? 2 : 4)) k_rt_stream(const RtUpdateArgs p) {
+__global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) k_rt_stream(const RtUpdateArgs p) {
   extern __shared__ __align__(128) uint8_t rt_smem[];
   __shared__ float s_red[32];
   __shared__ __align__(8) unsigned long long s_bar[2 * kRtStages];
@@ -248,7 +249,7 @@ template <int TH>
 int launch_rt_stream_t(const RtUpdateArgs &a, cudaStream_t st) {
   const size_t smem = (size_t)kRtStages * 4 * TH * 16;
   int per_sm = (int)((size_t)225 * 1024 / (smem + 1024));
-  const int cap = TH == 512 ? 1 : (TH == 256 ? 2 : 4);
+  const int cap = TH == 512 ? 2 : (TH == 256 ? 4 : 6);
   if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)tc::num_sms() * per_sm;

@@ -172,6 +172,7 @@ struct LayerPrep {
   bool gw = false, gwr = false;
   tc::GcnwTables *gwtab = nullptr, *gwtabr = nullptr;
   __nv_bfloat16 *wsc = nullptr, *wscr = nullptr;
+  float *n1V = nullptr, *nrV = nullptr;   // LayerNorm affine as [V][C] (LN warps of the fused stage): weight then bias
 };
 
 LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws, bool sparse_adj = false) {
@@ -204,7 +205,9 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws, bool spar
     const size_t cap = (size_t)tc::gcnw_edge_cap(V);
     P.gwtab = ws.take<tc::GcnwTables>(1);
     P.wsc = ws.take<__nv_bfloat16>(2 * cap * d.c_out * d.c_in);
+    P.n1V = ws.take<float>((size_t)2 * d.c_out * V);
     if (P.gwr) {
+      P.nrV = ws.take<float>((size_t)2 * d.c_out * V);
       P.gwtabr = ws.take<tc::GcnwTables>(1);
       P.wscr = ws.take<__nv_bfloat16>(2 * cap * d.c_out * d.c_in);
     }
@@ -244,7 +247,16 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
     STGCN_LAUNCH_OK();
     tc::k_gcnw_pack<<<cdiv(per * cap, 256), 256, 0, st>>>(d.gcn_w, P.gwtab, d.c_out, d.c_in, cap, P.wsc);
     STGCN_LAUNCH_OK();
+    const int cvv = d.c_out * V;
+    tc::k_transpose_cv<<<cdiv(cvv, 256), 256, 0, st>>>(d.n1_w, P.n1V, d.c_out, V);
+    STGCN_LAUNCH_OK();
+    tc::k_transpose_cv<<<cdiv(cvv, 256), 256, 0, st>>>(d.n1_b, P.n1V + cvv, d.c_out, V);
+    STGCN_LAUNCH_OK();
     if (P.gwr) {
+      tc::k_transpose_cv<<<cdiv(cvv, 256), 256, 0, st>>>(d.nr_w, P.nrV, d.c_out, V);
+      STGCN_LAUNCH_OK();
+      tc::k_transpose_cv<<<cdiv(cvv, 256), 256, 0, st>>>(d.nr_b, P.nrV + cvv, d.c_out, V);
+      STGCN_LAUNCH_OK();
       tc::k_gcnw_tables<<<1, 32, 0, st>>>(nullptr, 1, V, 1, cap, P.gwtabr);
       STGCN_LAUNCH_OK();
       tc::k_gcnw_pack<<<cdiv(per * cap, 256), 256, 0, st>>>(d.res_w, P.gwtabr, d.c_out, d.c_in, cap, P.wscr);
@@ -268,7 +280,7 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
 // persistent kernel, z through an L2-resident ring; two-kernel form: z in HBM + k_ln_stream.
 // Scratch comes from `ws` and is released on return.  In measuring mode only the sizes are taken.
 int gcnw_stage(int c_out, const __nv_bfloat16 *xh, const __nv_bfloat16 *wsc, tc::GcnwParams g, tc::LnStreamArgs l,
-               int T_full, int fstride, long long plane_stride, Bump &ws, cudaStream_t st) {
+               const float *affine_vc, int T_full, int fstride, long long plane_stride, Bump &ws, cudaStream_t st) {
   const size_t mark = ws.mark();
   const int V = g.V, cap = tc::gcnw_edge_cap(V);
   const long long rows = (long long)g.N * g.T * V;
@@ -281,7 +293,8 @@ int gcnw_stage(int c_out, const __nv_bfloat16 *xh, const __nv_bfloat16 *wsc, tc:
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (graph-conv stage ring)");
       g.R = tc::gcnw_ring_slots(V, c_out);
-      g.n_wT = l.n_wT; g.n_bT = l.n_bT; g.relu = l.relu; g.eps = l.eps;
+      g.npc = tc::gcnw_ln_chunks(V, c_out);
+      g.n_wV = affine_vc; g.n_bV = affine_vc + (size_t)c_out * V; g.relu = l.relu; g.eps = l.eps;
       g.out_f32 = l.out_f32; g.out_hi = l.out_hi; g.out_lo = l.out_lo;
       g.out_T = l.out_T; g.out_t0 = l.out_t0;
       STGCN_CUDA_OK(cudaMemsetAsync(g.ready, 0, sizeof(unsigned) * (2 * groups + 1), st));
@@ -386,7 +399,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
     g.tab = pp->gwtab;
     g.bias = pp->bzT; g.bias_sw = 1;
     g.debug = debug_mode();
-    if (gcnw_stage(d.c_out, xh, pp->wsc, g, l, T, 1, rows * d.c_in, ws, st)) return 1;
+    if (gcnw_stage(d.c_out, xh, pp->wsc, g, l, pp->n1V, T, 1, rows * d.c_in, ws, st)) return 1;
   } else if (tc_gcn) {
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer gcn stage)");
@@ -461,7 +474,7 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       g.tab = pp->gwtabr;
       g.bias = d.res_b; g.bias_sw = 0;
       g.debug = debug_mode();
-      if (gcnw_stage(d.c_out, xh, pp->wscr, g, l, T, d.stride, rows * d.c_in, ws, st)) return 1;
+      if (gcnw_stage(d.c_out, xh, pp->wscr, g, l, pp->nrV, T, d.stride, rows * d.c_in, ws, st)) return 1;
     }
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (layer tcn stage)");
