@@ -61,7 +61,7 @@ typedef struct stgcn_layer_desc {
   int32_t stride;
   int32_t residual;      /* STGCN_RES_* */
   int32_t norm;          /* STGCN_NORM_* */
-  int32_t rt;            /* 0: ST-GCN layer, 1: RT-ST-GCN online layer */
+  int32_t rt;            /* 0: ST-GCN layer, 1: RT-ST-GCN online layer, 2: CoST-GCN layer */
   int32_t a_per_sample;  /* 0: a_eff is (K,V,V); 1: (N,K,V,V) */
   const float *gcn_w, *gcn_b, *a_eff;
   const float *n1_w, *n1_b;
@@ -236,6 +236,25 @@ int stgcn_model_forward_host(const stgcn_model_desc *m, const float *x_host, flo
 int rtstgcn_step_host(const stgcn_model_desc *m, const float *x_host, void *state,
                       float *logits_host, int B, void *device_io, void *workspace,
                       size_t workspace_bytes, void *stream);
+
+/* ---- CoST-GCN continual step -----------------------------------------------
+ * Replaces models.costgcn.Model.forward on one frame (reference
+ * models/costgcn/costgcn.py:81-99) with its StgcnLayer.forward (:190-211): per
+ * layer a FIFO of graph-convolved frames, LayerNorm + ReLU, a learnable
+ * Gamma x 1 convolution with dilation = stride over the FIFO, second LayerNorm,
+ * plus the residual of Gamma/2 frames ago.  Layers are stgcn_layer_desc with
+ * rt == 2 (same parameter pointers as an ST-GCN layer; res_b is the bias of
+ * the residual conv).  B streams share the caller's frame index t (0, 1, ...);
+ * costgcn_state_reset initialises (or re-initialises, for a stream range) the
+ * rings and must be called before the first step.  LayerNorm, math in
+ * {bf16x3, bf16}, channels in {64,128,256}, sparse adjacency, prepared
+ * operands (stgcn_model_prepare) only.
+ * x (B, in_feat, 1, V) -> logits (B, num_classes). */
+size_t costgcn_state_bytes(const stgcn_model_desc *m, int B);
+int costgcn_state_reset(const stgcn_model_desc *m, void *state, int B, int first, int count, void *stream);
+size_t costgcn_step_workspace_bytes(const stgcn_model_desc *m, int B);
+int costgcn_step(const stgcn_model_desc *m, const float *x, void *state, long long t, float *logits, int B,
+                 void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,11 @@ SYMBOLS = {
     'stgcn_mean_joints_forward': (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     'stgcn_model_forward_host': (c_int, [_P_MODEL, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                          c_size_t, c_void_p]),
+    'costgcn_state_bytes': (c_size_t, [_P_MODEL, c_int]),
+    'costgcn_state_reset': (c_int, [_P_MODEL, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'costgcn_step_workspace_bytes': (c_size_t, [_P_MODEL, c_int]),
+    'costgcn_step': (c_int, [_P_MODEL, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_int, c_void_p, c_size_t,
+                     c_void_p]),
     'rtstgcn_step_host': (c_int, [_P_MODEL, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
 }

@@ -124,6 +124,10 @@ struct GcnwParams {
   int bias_sw;
   float *out;                   // z fp32 rows [(n*T + t)*V + w][CO]
   int debug;
+  // tap mode (CoST-GCN temporal convolution over a ring of frames, ntaps > 0): V == 1, the "edges" of the
+  // single joint are the taps, "source joint" of tap j = ring slot tap_src[j]; tab is not used
+  int ntaps;
+  int tap_src[16];
   // fused LayerNorm stage (k_gcnw<.., FUSE = true>)
   float *zring;                 // [R][128 frames][V][CO] fp32
   float2 *sring;                // [R][128][V][kEpiNH] (mean, M2) of every (frame, joint, column group)
@@ -152,6 +156,33 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// L2 eviction priorities of the fused stage: the z ring must stay resident (written, read once ~10 us later,
+// overwritten in place a few hundred us later) while ~4x as many bytes stream through L2 once (x in, u out)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_hint16(void *p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_hint8(void *p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ld_hint16(const float4 *p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
 // bounded spin (a protocol bug must trap, never hang the GPU)
 template <bool ACQ>
 __device__ __forceinline__ void wait_flag(const unsigned *p, unsigned target, unsigned have) {
@@ -174,7 +205,7 @@ __device__ __forceinline__ void wait_flag(const unsigned *p, unsigned target, un
 constexpr int kGwLnThreads = 256;     // LN warps of the fused stage
 constexpr int kGwLnFrames = 8;        // frames per LN work item (one warp)
 constexpr int kGwLnBlocks = 128 / kGwLnFrames;  // frame blocks per group; x npc position chunks = LN items per group
-constexpr int kGwLnIters = 13;        // at most this many 32-position steps per item (bounds an item's latency, and
+constexpr int kGwLnIters = 7;         // at most this many 32-position steps per item (bounds an item's latency, and
                                       // with it the number of groups the ring must hold)
 constexpr int kGwPubRing = 4;         // tiles the epilogue may run ahead of the publisher warp
 
@@ -212,7 +243,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.Cin / 64;
-  if (__ldg(&p.tab->nedge) < 0) {
+  if (p.tab && __ldg(&p.tab->nedge) < 0) {
     // the caller vouched for a sparse adjacency (stgcn_model_desc.reserved bit 1) that is not sparse:
     // fail loudly instead of computing with a truncated edge list
     if (threadIdx.x == 0 && blockIdx.x == 0)
@@ -242,8 +273,13 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(sTmemPtr, 512);
-  for (int i = threadIdx.x; i <= p.V; i += blockDim.x) s_ptr[i] = __ldg(&p.tab->ptr[i]);
-  for (int i = threadIdx.x; i < kGwEdgeCap; i += blockDim.x) s_src[i] = __ldg(&p.tab->src[i]);
+  if (p.ntaps > 0) {
+    if (threadIdx.x == 0) { s_ptr[0] = 0; s_ptr[1] = p.ntaps; }
+    if (threadIdx.x < 16) s_src[threadIdx.x] = p.tap_src[threadIdx.x];
+  } else {
+    for (int i = threadIdx.x; i <= p.V; i += blockDim.x) s_ptr[i] = __ldg(&p.tab->ptr[i]);
+    for (int i = threadIdx.x; i < kGwEdgeCap; i += blockDim.x) s_src[i] = __ldg(&p.tab->src[i]);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -254,6 +290,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
     // chunk and plane ----
     if (lane == 0) {
       int as = 0, a_ph = 0;
+      const bool tap = p.ntaps > 0;      // tap mode: tensor-map dimension 1 = rows, 2 = ring slots
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int w = item % p.V;
         const int tb = (item / p.V) % p.tblocks, n = item / (p.V * p.tblocks);
@@ -263,13 +300,15 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
               mbar_wait(bEmptyA + 8 * as, a_ph ^ 1);
               mbar_expect_tx(bFullA + 8 * as, (uint32_t)(p.planes * kAPlane));
               for (int ap = 0; ap < p.planes; ++ap)
-                tma_load_5d(sA + as * kABytes + ap * kAPlane, &tm_x, bFullA + 8 * as, kc * 64, s_src[e], tb * 128, n, ap);
+                tma_load_5d(sA + as * kABytes + ap * kAPlane, &tm_x, bFullA + 8 * as, kc * 64, tap ? tb * 128 : s_src[e],
+                            tap ? s_src[e] : tb * 128, n, ap);
               if (++as == SA) { as = 0; a_ph ^= 1; }
             } else {
               for (int ap = 0; ap < p.planes; ++ap) {
                 mbar_wait(bEmptyA + 8 * as, a_ph ^ 1);
                 mbar_expect_tx(bFullA + 8 * as, kAPlane);
-                tma_load_5d(sA + as * kABytes, &tm_x, bFullA + 8 * as, kc * 64, s_src[e], tb * 128, n, ap);
+                tma_load_5d(sA + as * kABytes, &tm_x, bFullA + 8 * as, kc * 64, tap ? tb * 128 : s_src[e], tap ? s_src[e] : tb * 128,
+                            n, ap);
                 if (++as == SA) { as = 0; a_ph ^= 1; }
               }
             }
@@ -381,6 +420,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
     uint8_t *patch = s_patch + (warp - 3) * kPatchBytes;
     uint8_t *mine = patch + lane * kPatchPitch;
     int buf = 0, t_ph = 0, tile_k = 0;
+    const uint64_t pol_keep = FUSE ? l2_policy_evict_last() : 0ull;
     float v[16];
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int w = item % p.V;
@@ -438,9 +478,12 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int pc = i * 32 + lane, rr = pc >> 3, qq = pc & 7;
-          if ((okmask >> rr) & 1)
-            *reinterpret_cast<float4 *>(zout + (row0 + (long long)rr * p.V) * CO + c0 + sb + qq * 4) =
-                *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + qq * 16);
+          if ((okmask >> rr) & 1) {
+            float *dst = zout + (row0 + (long long)rr * p.V) * CO + c0 + sb + qq * 4;
+            const float4 val = *reinterpret_cast<const float4 *>(patch + rr * kPatchPitch + qq * 16);
+            if (FUSE) st_hint16(dst, val, pol_keep);
+            else *reinterpret_cast<float4 *>(dst) = val;
+          }
         }
         __syncwarp();
       }
@@ -502,6 +545,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
     const unsigned target = (unsigned)(V * 4 * kEpiNH);     // epilogue warps per group
     const uint32_t vmagic = (uint32_t)((0x100000000ull + (unsigned)V - 1) / (unsigned)V);   // x / V for x < 65536
     const float inv_np = 1.f / (float)NP, inv_cv = 1.f / (float)(V * CO - 1);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     unsigned li = 0;
     if (lane == 0) li = atomicAdd(ticket, 1u);
     li = __shfl_sync(0xffffffffu, li, 0);
@@ -517,7 +561,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
       if (lane == 0) {
         nli = atomicAdd(ticket, 1u);                         // next ticket: its latency hides behind this item
         wait_flag<false>(p.ready + grp, target, ld_relaxed_gpu(p.ready + grp));
-        (void)ld_acquire_gpu(p.ready + grp);
+        __threadfence();                                     // relaxed load + fence = acquire
       }
       __syncwarp();
       if (p.debug & 4096) nf = 0;                            // (debug bit: LN warps only hand the slots back)
@@ -564,7 +608,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
         const float4 gg = __ldg(gw + pos), oo = __ldg(gb + pos);
 #pragma unroll
         for (int f = 0; f < kGwLnFrames; ++f)
-          a[f] = f < nf ? __ldcg(zs + (size_t)f * VC4 + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
+          a[f] = f < nf ? ld_hint16(zs + (size_t)f * VC4 + pos, pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int f = 0; f < kGwLnFrames; ++f) {
           if (f < nf) {
@@ -580,17 +624,17 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1
             }
             if ((p.debug & 2048) && r.x != 12345.678f) continue;   // (debug bit: no LN stores)
             if (p.out_f32) {
-              *reinterpret_cast<float4 *>(p.out_f32 + ob + 4 * i) = r;
+              st_hint16(p.out_f32 + ob + 4 * i, r, pol_stream);
             } else {
               const __nv_bfloat162 h01 = __floats2bfloat162_rn(r.x, r.y), h23 = __floats2bfloat162_rn(r.z, r.w);
-              *reinterpret_cast<uint2 *>(p.out_hi + ob + 4 * i) =
-                  make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+              st_hint8(p.out_hi + ob + 4 * i,
+                       make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23)), pol_stream);
               if (p.out_lo) {
                 const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
                 const __nv_bfloat162 l01 = __floats2bfloat162_rn(r.x - f01.x, r.y - f01.y);
                 const __nv_bfloat162 l23 = __floats2bfloat162_rn(r.z - f23.x, r.w - f23.y);
-                *reinterpret_cast<uint2 *>(p.out_lo + ob + 4 * i) =
-                    make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+                st_hint8(p.out_lo + ob + 4 * i,
+                         make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23)), pol_stream);
               }
             }
           }
@@ -623,6 +667,11 @@ struct LnStreamArgs {
   float *out_f32;
   __nv_bfloat16 *out_hi, *out_lo;
   int out_T, out_t0;
+  // optional residual added after the norm (and after relu_mid), before the final relu (CoST-GCN:
+  // relu(LN2(q) + res)): rows of frame f at res + f*V*C, as fp32 or as bf16 hi (+ lo) planes
+  const float *res_f32;
+  const __nv_bfloat16 *res_hi, *res_lo;
+  int relu_mid;
 };
 
 template <int NV>
@@ -673,6 +722,25 @@ __global__ void __launch_bounds__(256, 2) k_ln_stream(LnStreamArgs p) {
       v.y = fmaf(fmaf(a[j].y, rstd, nmr), g4.y, o4.y);
       v.z = fmaf(fmaf(a[j].z, rstd, nmr), g4.z, o4.z);
       v.w = fmaf(fmaf(a[j].w, rstd, nmr), g4.w, o4.w);
+      if (p.relu_mid) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      const long long ib = f * (long long)p.V * p.C + 4 * i;
+      if (p.res_f32) {
+        const float4 r4 = ld_stream(reinterpret_cast<const float4 *>(p.res_f32 + ib));
+        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+      } else if (p.res_hi) {
+        const uint2 rh = *reinterpret_cast<const uint2 *>(p.res_hi + ib);
+        const float2 h01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rh.x));
+        const float2 h23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rh.y));
+        v.x += h01.x; v.y += h01.y; v.z += h23.x; v.w += h23.y;
+        if (p.res_lo) {
+          const uint2 rl = *reinterpret_cast<const uint2 *>(p.res_lo + ib);
+          const float2 l01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rl.x));
+          const float2 l23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rl.y));
+          v.x += l01.x; v.y += l01.y; v.z += l23.x; v.w += l23.y;
+        }
+      }
       if (p.relu) {
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
       }
@@ -729,14 +797,20 @@ inline bool gcnw_fuse_enabled() {
 // ring geometry of the fused stage: slots of [128 frames][V][CO] fp32.  The ring must hold the groups
 // the GEMM side produces during one LN item's latency (~15 us: up to ~45 groups for C = 64, ~10 for
 // C = 256) and stay L2-resident: ~48 MB, 8..64 slots
+inline int gcnw_env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e && atoi(e) > 0 ? atoi(e) : dflt;
+}
 inline int gcnw_ring_slots(int V, int CO) {
+  static const int mb = gcnw_env_int("STGCN_GCNW_RING_MB", 24);       // tuning aid
   const size_t slot = (size_t)128 * V * CO * sizeof(float);
-  int R = (int)((size_t)48 * 1024 * 1024 / slot);
-  return R > 64 ? 64 : (R < 8 ? 8 : R);
+  int R = (int)((size_t)mb * 1024 * 1024 / slot);
+  return R > 64 ? 64 : (R < 6 ? 6 : R);
 }
 inline int gcnw_ln_chunks(int V, int CO) {
+  static const int iters = gcnw_env_int("STGCN_GCNW_LN_ITERS", kGwLnIters);   // tuning aid
   const int steps = (V * CO / 4 + 31) / 32;
-  return (steps + kGwLnIters - 1) / kGwLnIters;
+  return (steps + iters - 1) / iters;
 }
 inline size_t gcnw_ring_floats(int V, int CO) { return (size_t)gcnw_ring_slots(V, CO) * 128 * V * CO; }
 inline size_t gcnw_sring_float2(int V, int CO) { return (size_t)gcnw_ring_slots(V, CO) * 128 * V * kEpiNH; }
@@ -744,9 +818,15 @@ inline size_t gcnw_sring_float2(int V, int CO) { return (size_t)gcnw_ring_slots(
 // x planes: bf16 [planes][N_full][T_full][V][Cin] (the view takes every fstride-th frame, T frames, of the
 // first p.N trials from `x`); wsc: k_gcnw_pack tiles [2][cap][CO][Cin].  FUSE: p.zring .. p.out_t0 set and
 // p.ready / p.done zeroed by the caller (N * tblocks counters each).
+// tap mode view of the activations: a ring [planes][slots][rows][C]; tensor-map dimensions (C, rows, slots, 1,
+// planes) with a {64, 128, 1, 1, 1} box (strides stay increasing)
+struct GcnwXView {
+  long long slots = 0;       // 0: ordinary (C, V, T, N, planes) view
+  long long slot_stride = 0; // elements between ring slots
+};
 template <int CO, bool FUSE>
 int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p, int T_full, int fstride, int cap,
-                  long long plane_stride, cudaStream_t st) {
+                  long long plane_stride, cudaStream_t st, const GcnwXView &xv) {
   const int V = p.V, kMaxSmem = 232448;
   p.tblocks = (p.T + 127) / 128;
   p.items = p.N * p.tblocks * V;
@@ -762,10 +842,17 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
   p.a_stages = SA; p.b_stages = SB;
   const int smem = fixed + SA * kA + SB * kB;
   CUtensorMap tm_x, tm_w;
-  const uint64_t xd[5] = {(uint64_t)p.Cin, (uint64_t)V, (uint64_t)p.T, (uint64_t)p.N, (uint64_t)p.planes};
-  const uint64_t xs[4] = {(uint64_t)p.Cin * 2, (uint64_t)fstride * V * p.Cin * 2, (uint64_t)T_full * V * p.Cin * 2,
-                          (uint64_t)plane_stride * 2};
-  const uint32_t xb[5] = {64, 1, 128, 1, 1};
+  uint64_t xd[5] = {(uint64_t)p.Cin, (uint64_t)V, (uint64_t)p.T, (uint64_t)p.N, (uint64_t)p.planes};
+  uint64_t xs[4] = {(uint64_t)p.Cin * 2, (uint64_t)fstride * V * p.Cin * 2, (uint64_t)T_full * V * p.Cin * 2,
+                    (uint64_t)plane_stride * 2};
+  uint32_t xb[5] = {64, 1, 128, 1, 1};
+  if (xv.slots > 0) {
+    xd[1] = (uint64_t)p.T; xd[2] = (uint64_t)xv.slots;
+    xs[0] = (uint64_t)p.Cin * 2;
+    xs[1] = (uint64_t)xv.slot_stride * 2;
+    xs[2] = (uint64_t)xv.slot_stride * xv.slots * 2;     // N == 1
+    xb[1] = 128; xb[2] = 1;
+  }
   if (make_tmap_bf16(&tm_x, x, 5, xd, xs, xb)) return 1;
   const uint64_t wd[4] = {(uint64_t)p.Cin, (uint64_t)CO, (uint64_t)cap, 2};
   const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)cap * CO * p.Cin * 2};
@@ -786,15 +873,16 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
 
 // plane_stride: elements between the hi and lo planes of x (= rows of the whole buffer * Cin)
 inline int launch_gcnw(int CO, const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, const GcnwParams &p, int T_full,
-                       int fstride, int cap, long long plane_stride, cudaStream_t st) {
+                       int fstride, int cap, long long plane_stride, cudaStream_t st,
+                       const GcnwXView &xv = GcnwXView()) {
   const bool fuse = p.zring != nullptr;
   switch (CO) {
-    case 64: return fuse ? launch_gcnw_c<64, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st)
-                         : launch_gcnw_c<64, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st);
-    case 128: return fuse ? launch_gcnw_c<128, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st)
-                          : launch_gcnw_c<128, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st);
-    case 256: return fuse ? launch_gcnw_c<256, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st)
-                          : launch_gcnw_c<256, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st);
+    case 64: return fuse ? launch_gcnw_c<64, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st, xv)
+                         : launch_gcnw_c<64, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st, xv);
+    case 128: return fuse ? launch_gcnw_c<128, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st, xv)
+                          : launch_gcnw_c<128, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st, xv);
+    case 256: return fuse ? launch_gcnw_c<256, true>(x, wsc, p, T_full, fstride, cap, plane_stride, st, xv)
+                          : launch_gcnw_c<256, false>(x, wsc, p, T_full, fstride, cap, plane_stride, st, xv);
   }
   return fail("gcnw: unsupported channel count %d", CO);
 }

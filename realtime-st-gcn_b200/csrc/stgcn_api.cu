@@ -180,7 +180,7 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws, bool spar
   const bool ln = d.norm == STGCN_NORM_LAYERNORM;
   P.gcn = ln && !d.a_per_sample && tc::gcn_tc_supported(d.c_in, d.c_out, V, K);
   P.csr = !d.a_per_sample && K * V + 1 <= 1024;
-  P.tcn = ln && !d.rt && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, 2);
+  P.tcn = ln && d.rt != 1 && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, 2);
   P.res = ln && d.residual == STGCN_RES_CONV && tc::gcn_tc_supported(d.c_in, d.c_out, V, 1);
   if (P.csr) {
     P.kw_ptr = ws.take<int>((size_t)K * V + 1);
@@ -1105,7 +1105,7 @@ bool rt_small_supported(const stgcn_model_desc &m, int B) {
   int c_max = m.layers[0].c_in;
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
-    if (!d.rt || d.norm != STGCN_NORM_LAYERNORM || d.a_per_sample) return false;
+    if (d.rt != 1 || d.norm != STGCN_NORM_LAYERNORM || d.a_per_sample) return false;
     if (d.c_out % rts::kNC || d.c_in % rts::kChunk) return false;
     if (m.num_joints * (d.c_out / rts::kNC) > 4 * rts::kThreads) return false;
     if ((m.partitions + 1) * (d.c_out / rts::kNC) > 128) return false;   // rows per CTA (register tile bound)
@@ -1126,7 +1126,7 @@ bool rt_all_gw_static(const stgcn_model_desc &m) {
     return false;
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
-    if (d.norm != STGCN_NORM_LAYERNORM || d.a_per_sample || !d.rt) return false;
+    if (d.norm != STGCN_NORM_LAYERNORM || d.a_per_sample || d.rt != 1) return false;
     if (!tc::gcn_tc_supported(d.c_in, d.c_out, m.num_joints, m.partitions) ||
         !tc::gcnw_supported(d.c_in, d.c_out, m.num_joints, m.partitions) || !rt_update_supported(m.num_joints, d.c_out))
       return false;
@@ -1245,7 +1245,7 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
   Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
   for (int i = 0; i < m.num_layers; ++i) {
     const stgcn_layer_desc &d = m.layers[i];
-    STGCN_REQUIRE(d.rt, "rtstgcn_step needs online layers (rt == 1)");
+    STGCN_REQUIRE(d.rt == 1, "rtstgcn_step needs online layers (rt == 1)");
     float *fifo = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.fifo[i]);
     float *acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]);
     LayerPrep P;
@@ -1270,6 +1270,206 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
   return 0;
 }
 
+
+// ---- CoST-GCN continual step (models/costgcn/costgcn.py:81-99, 190-211) ---------------------------
+// Per layer and stream: a ring of the last F = stride*(kernel-1)+1 frames u = relu(LN1(gcn(x))) and a ring
+// of the last kernel/2 + 1 residuals, both as bf16 hi/lo planes [plane][slot][B*V][C] (the reference
+// keeps newest-first FIFOs of z and re-normalises the whole FIFO every step; LayerNorm is per frame, so
+// storing u once per frame is the same thing -- including the never-written slots, which the reference
+// reads as LN(0) = bias: the ring is initialised with relu(tcn.0.bias)).  The ring position is the
+// caller's frame index t, common to all streams; resetting a stream re-initialises its ring entries.
+struct CostLayout {
+  size_t u[64], r[64];
+  size_t total;
+};
+inline int cost_res_slots(const stgcn_layer_desc &d) { return d.residual == STGCN_RES_NONE ? 0 : d.kernel / 2 + 1; }
+int cost_layout(const stgcn_model_desc &m, int B, CostLayout &L) {
+  STGCN_REQUIRE(m.num_layers <= 64, "too many layers");
+  const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off += (bytes + 255) & ~size_t(255);
+    return at;
+  };
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    const size_t slot = (size_t)B * m.num_joints * d.c_out * sizeof(__nv_bfloat16);
+    L.u[i] = take(slot * planes * (size_t)(d.stride * (d.kernel - 1) + 1));
+    L.r[i] = take(slot * planes * (size_t)cost_res_slots(d));
+  }
+  L.total = off;
+  return 0;
+}
+
+int cost_check(const stgcn_model_desc &m) {
+  STGCN_REQUIRE(m.norm == STGCN_NORM_LAYERNORM && m.math != STGCN_MATH_FP32 && (m.reserved & 2) && embed_warp_path(m),
+                "costgcn: the B200 path needs LayerNorm, math in {bf16x3, bf16} and a sparse (tree) adjacency");
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    STGCN_REQUIRE(d.rt == 2 && d.norm == STGCN_NORM_LAYERNORM && !d.a_per_sample, "costgcn: layer %d is not a CoST-GCN layer", i);
+    STGCN_REQUIRE(d.kernel % 2 == 1 && d.kernel <= 15, "costgcn: temporal kernel must be odd and <= 15 (got %d)", d.kernel);
+    STGCN_REQUIRE(tc::gcnw_supported(d.c_in, d.c_out, m.num_joints, m.partitions) &&
+                      tc::gcnw_supported(d.c_out, d.c_out, m.num_joints, 1),
+                  "costgcn: layer %d: channels must be 64, 128 or 256 (got %d -> %d)", i, d.c_in, d.c_out);
+  }
+  return 0;
+}
+
+// u ring entries of streams [first, first + count) <- relu(tcn.0.bias) (hi / lo planes); n1_b is (C, V)
+__global__ void k_cost_ring_init(const float *__restrict__ n1_b, __nv_bfloat16 *__restrict__ ring, int planes, int slots,
+                                 int B, int V, int C, int first, int count) {
+  const long long per = (long long)count * V * C;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per * slots) return;
+  const int sl = (int)(i / per);
+  const long long r = i - (long long)sl * per;
+  const int c = (int)(r % C);
+  const int v = (int)((r / C) % V);
+  const long long b = first + r / ((long long)V * C);
+  const float val = fmaxf(n1_b[c * V + v], 0.f);
+  __nv_bfloat16 hi, lo;
+  tc::split_bf16(val, hi, lo);
+  const long long slot_n = (long long)B * V * C;
+  const long long at = (long long)sl * slot_n + (b * V + v) * C + c;
+  ring[at] = hi;
+  if (planes == 2) ring[(long long)slots * slot_n + at] = lo;
+}
+
+int cost_step(const stgcn_model_desc &m, const float *x, void *state, long long t, float *logits, int B, Bump &ws,
+              cudaStream_t st) {
+  const int V = m.num_joints, K = m.partitions;
+  if (cost_check(m)) return 1;
+  STGCN_REQUIRE(ws.measuring() || use_prepared(m), "costgcn_step needs prepared operands (stgcn_model_prepare)");
+  CostLayout L;
+  if (cost_layout(m, B, L)) return 1;
+  const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
+  const long long rows = (long long)B * V;
+  size_t max_act = (size_t)rows * m.layers[0].c_in;
+  for (int i = 0; i < m.num_layers; ++i) {
+    const size_t a = (size_t)rows * m.layers[i].c_out;
+    if (a > max_act) max_act = a;
+  }
+  // activations between layers travel as bf16 planes; the last layer writes fp32 rows for the head
+  __nv_bfloat16 *buf[2] = {ws.take<__nv_bfloat16>(planes * max_act), ws.take<__nv_bfloat16>(planes * max_act)};
+  float *zq = ws.take<float>(max_act);
+  float *qres = ws.take<float>(max_act);
+  float *last = ws.take<float>(max_act);
+  if (ws.measuring()) return 0;
+  STGCN_REQUIRE(!ws.overflow, "costgcn_step: workspace too small (%zu B given)", ws.cap);
+  if (embed(m, x, reinterpret_cast<float *>(buf[0]), B, 1, ws, st, nullptr, planes)) return 1;
+  char *sb = static_cast<char *>(state);
+  Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
+  const int cap = tc::gcnw_edge_cap(V);
+  int cur = 0;
+  for (int i = 0; i < m.num_layers; ++i) {
+    const stgcn_layer_desc &d = m.layers[i];
+    const LayerPrep P = prep_take(d, K, V, pb, true);
+    STGCN_REQUIRE(P.gw && P.tcn && (d.residual != STGCN_RES_CONV || P.gwr), "costgcn: layer %d has no tensor-core operands", i);
+    const int F = d.stride * (d.kernel - 1) + 1, R2 = cost_res_slots(d);
+    const long long slot_in = rows * d.c_in, slot_n = rows * d.c_out;
+    const __nv_bfloat16 *xh = buf[cur];
+    __nv_bfloat16 *ur = reinterpret_cast<__nv_bfloat16 *>(sb + L.u[i]);
+    __nv_bfloat16 *rr = reinterpret_cast<__nv_bfloat16 *>(sb + L.r[i]);
+    const int su = (int)(t % F);
+    const bool is_last = i + 1 == m.num_layers;
+    // ---- residual of this frame -> ring slot t mod R2 (costgcn.py:193-198) ----
+    if (d.residual == STGCN_RES_IDENTITY) {
+      const int sr = (int)(t % R2);
+      for (int pl = 0; pl < planes; ++pl)
+        STGCN_CUDA_OK(cudaMemcpyAsync(rr + ((size_t)pl * R2 + sr) * slot_n, xh + (size_t)pl * slot_in,
+                                      (size_t)slot_n * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
+    } else if (d.residual == STGCN_RES_CONV) {
+      const int sr = (int)(t % R2);
+      tc::GcnwParams g{};
+      g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = 1;
+      g.tab = P.gwtabr;
+      g.bias = d.res_b; g.bias_sw = 0;
+      g.out = qres;
+      {
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcnw(d.c_out, xh, P.wscr, g, B, 1, cap, slot_in, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      tc::LnStreamArgs l{};
+      l.frames = B; l.T = B; l.V = V; l.C = d.c_out;
+      l.z = qres;
+      l.n_wT = P.nrT; l.n_bT = P.nrT + (size_t)d.c_out * V;
+      l.relu = 0; l.eps = kEps;
+      l.out_hi = rr + (size_t)sr * slot_n;
+      l.out_lo = planes == 2 ? rr + ((size_t)R2 + sr) * slot_n : nullptr;
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_ln_stream(l, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    // ---- graph convolution, LayerNorm 1, ReLU -> u ring slot t mod F (costgcn.py:200-207) ----
+    {
+      tc::GcnwParams g{};
+      g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = 1;
+      g.tab = P.gwtab;
+      g.bias = P.bzT; g.bias_sw = 1;
+      g.out = zq;
+      {
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcnw(d.c_out, xh, P.wsc, g, B, 1, cap, slot_in, st)) return 1;
+        STGCN_LAUNCH_OK();
+      }
+      tc::LnStreamArgs l{};
+      l.frames = B; l.T = B; l.V = V; l.C = d.c_out;
+      l.z = zq;
+      l.n_wT = P.n1T; l.n_bT = P.n1T + (size_t)d.c_out * V;
+      l.relu = 1; l.eps = kEps;
+      l.out_hi = ur + (size_t)su * slot_n;
+      l.out_lo = planes == 2 ? ur + ((size_t)F + su) * slot_n : nullptr;
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_ln_stream(l, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    // ---- Gamma x 1 convolution over the ring: tap j reads the frame j*stride steps in the past ----
+    {
+      tc::GcnwParams g{};
+      g.T = (int)rows; g.V = 1; g.Cin = d.c_out; g.planes = planes; g.N = 1;
+      g.bias = d.tcn_b; g.bias_sw = 0;
+      g.out = zq;
+      g.ntaps = d.kernel;
+      for (int j = 0; j < d.kernel; ++j) g.tap_src[j] = (int)((((t - (long long)j * d.stride) % F) + F) % F);
+      tc::GcnwXView xv;
+      xv.slots = F; xv.slot_stride = slot_n;
+      ProfScope ps(KC_GEMM_TCN, st);
+      if (tc::launch_gcnw(d.c_out, ur, P.wp16, g, (int)rows, 1, d.kernel, (long long)F * slot_n, st, xv)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    // ---- LayerNorm 2, + residual of kernel/2 frames ago, ReLU (costgcn.py:209-211) ----
+    {
+      tc::LnStreamArgs l{};
+      l.frames = B; l.T = B; l.V = V; l.C = d.c_out;
+      l.z = zq;
+      l.n_wT = P.n2T; l.n_bT = P.n2T + (size_t)d.c_out * V;
+      l.relu = 1; l.eps = kEps;
+      if (R2 > 0) {
+        const int rd = (int)((((t - d.kernel / 2) % R2) + R2) % R2);
+        l.res_hi = rr + (size_t)rd * slot_n;
+        l.res_lo = planes == 2 ? rr + ((size_t)R2 + rd) * slot_n : nullptr;
+      }
+      if (is_last) {
+        l.out_f32 = last;
+      } else {
+        l.out_hi = buf[cur ^ 1];
+        l.out_lo = planes == 2 ? buf[cur ^ 1] + slot_n : nullptr;
+      }
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_ln_stream(l, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    cur ^= 1;
+  }
+  const int c_last = m.layers[m.num_layers - 1].c_out;
+  ProfScope ps(KC_POOL, st);
+  k_rt_head<<<cdiv(B, kRtHeadStreams), 256, sizeof(float) * kRtHeadStreams * c_last, st>>>(
+      last, B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
 }  // namespace
 
 // =============================================================================
@@ -1734,6 +1934,50 @@ int stgcn_mean_joints_forward(const float *x, float *y, long long rows, int V, v
   k_mean_joints<<<cdiv(rows, 256), 256, 0, as_stream(stream)>>>(x, y, rows, V);
   STGCN_LAUNCH_OK();
   return 0;
+}
+
+// ---- CoST-GCN continual step (costgcn.py:81-99, 190-211) ---------------------------------------
+size_t costgcn_state_bytes(const stgcn_model_desc *m, int B) {
+  CostLayout L;
+  if (check_model(m) || cost_layout(*m, B, L)) return 0;
+  return L.total;
+}
+
+int costgcn_state_reset(const stgcn_model_desc *m, void *state, int B, int first, int count, void *stream) {
+  if (check_model(m) || cost_check(*m)) return 1;
+  STGCN_REQUIRE(state && first >= 0 && count >= 0 && first + count <= B, "costgcn_state_reset: bad stream range");
+  CostLayout L;
+  if (cost_layout(*m, B, L)) return 1;
+  cudaStream_t st = as_stream(stream);
+  const int planes = m->math == STGCN_MATH_BF16X3 ? 2 : 1, V = m->num_joints;
+  char *sb = static_cast<char *>(state);
+  for (int i = 0; i < m->num_layers && count > 0; ++i) {
+    const stgcn_layer_desc &d = m->layers[i];
+    const int F = d.stride * (d.kernel - 1) + 1, R2 = cost_res_slots(d);
+    const long long tot = (long long)count * V * d.c_out * F;
+    k_cost_ring_init<<<cdiv(tot, 256), 256, 0, st>>>(d.n1_b, reinterpret_cast<__nv_bfloat16 *>(sb + L.u[i]), planes, F, B,
+                                                    V, d.c_out, first, count);
+    STGCN_LAUNCH_OK();
+    const size_t per = (size_t)V * d.c_out * sizeof(__nv_bfloat16);
+    for (int sl = 0; sl < planes * R2; ++sl)
+      STGCN_CUDA_OK(cudaMemsetAsync(sb + L.r[i] + ((size_t)sl * B + first) * per, 0, per * count, st));
+  }
+  return 0;
+}
+
+size_t costgcn_step_workspace_bytes(const stgcn_model_desc *m, int B) {
+  if (check_model(m)) return 0;
+  Bump ws(nullptr, 0);
+  if (cost_step(*m, nullptr, nullptr, 0, nullptr, B, ws, nullptr)) return 0;
+  return ws.peak;
+}
+
+int costgcn_step(const stgcn_model_desc *m, const float *x, void *state, long long t, float *logits, int B,
+                 void *workspace, size_t workspace_bytes, void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(x && state && logits && workspace && B > 0 && t >= 0, "costgcn_step: null argument, empty batch or t < 0");
+  Bump ws(workspace, workspace_bytes);
+  return cost_step(*m, x, state, t, logits, B, ws, as_stream(stream));
 }
 
 // ---- host-buffer entry points --------------------------------------------------------

@@ -9,7 +9,7 @@ from conftest import ROOT
 def _declared_symbols():
     text = open(os.path.join(ROOT, 'include', 'stgcn_b200.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    names = re.findall(r'\b(?:int|size_t|long long|const char \*)\s*\*?\s*((?:stgcn|rtstgcn)_\w+)\s*\(', text)
+    names = re.findall(r'\b(?:int|size_t|long long|const char \*)\s*\*?\s*((?:stgcn|rtstgcn|costgcn)_\w+)\s*\(', text)
     return sorted(set(names))
 
 

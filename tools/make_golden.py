@@ -270,10 +270,18 @@ def gen_cost_models():
     """CoST-GCN (models/costgcn/costgcn.py:81-99, 190-211): small model with a stride-2 / channel-changing
     layer (weights and input stored) and the full PKU trunk (seeds + digest)."""
     from models.costgcn.costgcn import Model as RefCost
-    cfg = cost_config(num_classes=12, **SMALL)
+    # 64/128-channel models (the B200 path's tensor-core shapes): weights regenerated from the seed
+    cfg = cost_config(num_classes=12, in_ch=[64, 64, 128], out_ch=[64, 128, 128], stride=[1, 2, 1])
     sd = syn.synth_state_dict(RefCost(**cfg).state_dict(), 81)
     x = syn.synth_input((2, 3, 40, 25), 82)
-    save('costgcn_small', x=x, logits=run_ref_cost(cfg, sd, x), **sd_arrays(sd))
+    save('costgcn_small', logits=run_ref_cost(cfg, sd, x), seeds=np.array([81, 82]),
+         digest=np.array(syn.state_digest(sd)))
+    cfg = cost_config(num_classes=6, in_ch=[64, 64], out_ch=[64, 64], stride=[1, 1], residual=[0, 1],
+                      importance=False, graph='imu_fogit_ABCD', in_feat=6)
+    sd = syn.synth_state_dict(RefCost(**cfg).state_dict(), 85)
+    x = syn.synth_input((1, 6, 24, 7), 86)
+    save('costgcn_small_nores', logits=run_ref_cost(cfg, sd, x), seeds=np.array([85, 86]),
+         digest=np.array(syn.state_digest(sd)))
     cfg = cost_config()
     sd = syn.synth_state_dict(RefCost(**cfg).state_dict(), 83)
     x = syn.synth_input((2, 3, 48, 25), 84)
