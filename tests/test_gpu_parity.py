@@ -650,13 +650,13 @@ def test_stgcn_sliding_windows(pkg, syn, cuda):
 
 
 # ------------------------------------------------------------------ non-default graph-conv paths
-@pytest.mark.parametrize('switches', [{}, {'STGCN_GCNW': '0'}, {'STGCN_GCNW_FUSE': '0'}],
-                         ids=['default', 'frame-tile-kernel', 'two-kernel-stage'])
+@pytest.mark.parametrize('switches', [{}, {'STGCN_GCNW': '0'}, {'STGCN_GCNW_FUSE': '1'}],
+                         ids=['default', 'frame-tile-kernel', 'one-kernel-stage'])
 def test_stgcn_model_graphconv_paths_subprocess(cuda, switches):
-    """Model forwards default to the per-joint-weight GEMM with the LayerNorm stage running inside the same
-    persistent kernel (kernels_gcnw.cuh).  The other graph-conv forms stay covered at model level: the
-    frame-tile k_gcn_tc2 kernel (STGCN_GCNW=0; also what layer-level calls and dense adjacencies use) and
-    the two-kernel form of the stage (STGCN_GCNW_FUSE=0: GEMM -> z in HBM -> k_ln_stream) -- models of
+    """Model forwards default to the per-joint-weight GEMM + streaming LayerNorm (kernels_gcnw.cuh).  The other
+    graph-conv forms stay covered at model level: the frame-tile k_gcn_tc2 kernel (STGCN_GCNW=0; also what
+    layer-level calls and dense adjacencies use) and the opt-in one-kernel form of the stage
+    (STGCN_GCNW_FUSE=1: z through an L2-resident ring to LN warps of the same persistent kernel) -- models of
     growing depth incl. strided / channel-changing layers, both arithmetic modes, against the oracle.  The
     switches are read once per process, so tools/check_graphconv_paths.py runs in a child process."""
     import os
