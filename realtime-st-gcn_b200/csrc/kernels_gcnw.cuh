@@ -217,7 +217,7 @@ constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B 
 // and one weight stage both weight planes, so the MMA issuer waits on two barriers per twelve MMAs
 // instead of five per twelve, and the weight hi plane is loaded once instead of twice.
 template <int CO, bool MERGE, bool FUSE>
-__global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), 1)
+__global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), FUSE ? 1 : 2)
     k_gcnw(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GcnwParams p) {
   constexpr int kAPlane = 128 * 128;            // [128 frames][64 ch] bf16
   constexpr int kBPlane = CO * 128;             // [CO][64 ch] bf16
