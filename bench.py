@@ -7,9 +7,18 @@ Headline metric (BASELINE.json): ST-GCN forward skeleton-frames/s.  Workload = B
 (ST-GCN, 9 layers, PKU-MMD 25-joint graph, LayerNorm, N=256 synthetic trials x T=4000 per GPU,
 trial-sharded, no collective => weak scaling).  One step = one forward over the whole batch.
 `value` is timed with the input resident in HBM; `e2e` goes through the host-buffer C-ABI entry
-(pinned host input -> H2D -> forward -> D2H logits) every step.  Extra keys: `roofline`
-(dominant kernel class, timed live with CUDA events), `cpu_baseline` (oracle on host cores, N=1
-only), `rt` (RT-ST-GCN continual p50 step latency at 1 and 4096 streams, N=1 only), `clocks`.
+(pinned host input -> H2D -> forward -> D2H logits) every step.  Extra keys:
+  roofline      dominant kernel class, timed live with CUDA events
+  parity        logits of the timed run (first and last trial of the batch) against the CPU oracle
+  cpu_baseline  oracle on the host cores (N=1 only), on one trial of the workload
+  c1            BASELINE config 1 (N=1, T=300) on the GPU and on the host cores
+  rt            RT-ST-GCN continual p50 step latency at 1 and 4096 streams (configs 2 and 5), with the
+                oracle's continual loop timed beside it and the host-buffer (e2e) step; CoST-GCN step
+  long_trial    N=1: the T=262144 trial of config 4 on one GPU
+  tsplit        N>1: config 4, the T=262144 trial T-partitioned over the ranks (per-layer NCCL halo
+                exchange), checked against the oracle on rank 0
+  strong        N>1: config 3 strong-scaled (256 trials TOTAL over the ranks, no collective)
+  clocks        nvidia-smi clocks / throttle reasons sampled during the timed region
 """
 import argparse
 import ctypes
@@ -32,6 +41,8 @@ METRIC = "stgcn_fwd_skeleton_frames_per_s"
 UNIT = "frames/s"
 # algorithmic work per input frame for the PKU trunk (52 classes)
 FLOP_PER_FRAME = 54.87e6
+TOL = {'bf16x3': 1e-4, 'fp32': 1e-4, 'bf16': 2e-2}     # relative (max|diff| / max|ref|), tests/conftest.py rel_err
+LONG_T = 262144                                         # BASELINE config 4
 
 
 def parse():
@@ -50,6 +61,10 @@ def parse():
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--no-bf16-leg', action='store_true', help='skip the extra single-product bf16 measurement')
+    p.add_argument('--no-parity', action='store_true')
+    p.add_argument('--no-long', action='store_true', help='skip the config-4 legs (long_trial / tsplit / strong)')
+    p.add_argument('--allow-measurement-build', action='store_true',
+                   help='run although STGCN_DEBUG / STGCN_LIB select a measurement build (numbers are then not bench values)')
     return p.parse_args()
 
 
@@ -133,14 +148,17 @@ def trunk_flops(T, V=25, K=3, gamma=9, in_feat=3, classes=52):
 
 
 def ncu_traffic(kernel_class):
-    """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full`
-    capture (profiles/r01_ncu_top_kernel.json, written by tools/ncu_summary.py), or None."""
-    path = os.path.join(ROOT, 'profiles', 'r01_ncu_top_kernel.json')
-    try:
-        d = json.load(open(path))
-        return d.get(kernel_class, {}).get('dram_bytes_per_launch')
-    except (OSError, ValueError):
-        return None
+    """dram bytes (read + write) per launch of the dominant kernel class from the committed `ncu --set full`
+    capture (profiles/*_ncu_top_kernel.json, written by tools/ncu_summary.py), newest round first, or None."""
+    for name in ('r02_ncu_top_kernel.json', 'r01_ncu_top_kernel.json'):
+        try:
+            d = json.load(open(os.path.join(ROOT, 'profiles', name)))
+            v = d.get(kernel_class, {}).get('dram_bytes_per_launch')
+            if v:
+                return v
+        except (OSError, ValueError):
+            continue
+    return None
 
 
 def oracle_cfg(syn, norm):
@@ -153,8 +171,22 @@ def cpu_reference_step(x, sd, cfg):
         return O.stgcn_model(x, sd, cfg)
 
 
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def workload_config(args, N, T):
+    return {"workload": "ST-GCN fwd, 9 layers, PKU-MMD 25-joint graph, %s, N=%d trials x T=%d per GPU "
+                        "(BASELINE config 3), trial-sharded, no collective" % (args.norm, N, T),
+            "trials_per_gpu": N, "frames_per_trial": T, "math": args.math,
+            "l2": "inputs and activations (>= 0.3 GB per tensor) exceed the 126 MB L2"}
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU algorithm (oracle port: same ATen CPU ops) on the host cores."""
+    """Reference arm: the reference's CPU algorithm (oracle port: the same ATen CPU ops the reference's
+    nn.Modules dispatch, pinned to the reference's outputs by tests/golden) on all host cores.  One step =
+    one trial of the workload (a bounded sample of the 256-trial batch)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -173,25 +205,35 @@ def run_reference(args):
         cpu_reference_step(x, sd, ocfg)
     dt = (time.perf_counter() - t0) / args.steps
     value = args.frames / dt
+    cfgd = workload_config(args, args.trials, args.frames)
+    cfgd["math"] = "f32"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ST-GCN fwd, PKU-MMD graph, %s, T=%d V=25 (BASELINE config 3)" % (args.norm, args.frames),
-                   "trials_per_gpu": args.trials, "frames_per_trial": args.frames},
+        "config": cfgd,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "1 trial x T=%d per step (of %d trials), torch CPU fp32" % (args.frames, args.trials)},
+                         "sample": "1 trial x T=%d per step (of %d trials), torch CPU fp32, %d threads"
+                                   % (args.frames, args.trials, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def rt_latency(pkg, dev, streams, steps, graph_kw, math, hbm_gbs=None, cuda_graph=True):
-    """RT-ST-GCN continual step latency (one frame for every stream), CUDA-event timed per step."""
-    syn = pkg.synthetic
+# ----------------------------------------------------------------------------- continual legs
+def _p50(ms):
+    ms = sorted(ms)
+    return ms[len(ms) // 2], ms[int(len(ms) * 0.9)]
+
+
+def rt_latency(pkg, dev, streams, steps, graph_kw, math, hbm_gbs=None, cuda_graph=True, cpu_ref=False):
+    """RT-ST-GCN continual step latency (one frame for every stream), CUDA-event timed per step; optionally
+    the host-buffer step (pinned frame -> H2D -> step -> D2H logits) and the oracle's loop on the host cores."""
+    syn, lib = pkg.synthetic, pkg._lib.load()
     cfg = syn.arch_config('rt-st-gcn', **graph_kw)
+    sd = syn.synth_state_dict(pkg.RtStgcn(**cfg).state_dict(), 61)
     cfg['math'] = math
     m = pkg.RtStgcn(**cfg)
-    m.load_state_dict(syn.synth_state_dict(m.state_dict(), 61))
+    m.load_state_dict(sd)
     m = m.to(dev)
     m.prepare_benchmark({})
     m.enable_cuda_graph(cuda_graph)
@@ -206,21 +248,158 @@ def rt_latency(pkg, dev, streams, steps, graph_kw, math, hbm_gbs=None, cuda_grap
         m.step(frames[i % 8])
         ev[i][1].record()
     torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in ev)
-    p50 = ms[len(ms) // 2]
-    # state traffic per stream-frame = 4 * sum(C_out) * V * 4 B (read slot, write slot, read+write acc)
-    state_bytes = 4 * sum(cfg['rt-st-gcn']['out_ch']) * v * 4 * streams
-    out = {"streams": streams, "p50_ms": p50, "p90_ms": ms[int(len(ms) * 0.9)],
+    p50, p90 = _p50([a.elapsed_time(b) for a, b in ev])
+    desc, _ = m._descriptor()
+    # state traffic per stream-frame = read oldest FIFO slot, write it, read + write the accumulator
+    fifo16 = lib.rtstgcn_state_bytes(ctypes.byref(desc), streams) < 0.9 * streams * sum(
+        cfg['rt-st-gcn']['out_ch'][i] * v * 4 * (cfg['rt-st-gcn']['stride'][i] * 8 + 1 + cfg['rt-st-gcn']['stride'][i])
+        for i in range(len(cfg['rt-st-gcn']['out_ch'])))
+    per_elem = (2 + 2 + 4 + 4) if fifo16 else 16
+    state_bytes = per_elem * sum(cfg['rt-st-gcn']['out_ch']) * v * streams
+    out = {"streams": streams, "p50_ms": p50, "p90_ms": p90,
            "stream_frames_per_s": streams / (p50 * 1e-3), "cuda_graph": bool(cuda_graph),
+           "state_layout": "bf16 FIFO + fp32 accumulator" if fifo16 else "fp32 FIFO + fp32 accumulator",
            "state_gb_per_step": state_bytes / 1e9, "achieved_gbs": state_bytes / (p50 * 1e-3) / 1e9}
     if hbm_gbs:
         out["roofline"] = {"bound": "hbm", "achieved": out["achieved_gbs"], "peak": hbm_gbs, "unit": "GB/s",
                            "frac": out["achieved_gbs"] / hbm_gbs}
+    # ---- e2e: host-buffer C-ABI step (rtstgcn_step_host), every step H2D frame + D2H logits ----
+    x_host = torch.randn(streams, c, 1, v).pin_memory()
+    logits_host = torch.empty(streams, cfg['num_classes']).pin_memory()
+    state = m._ensure_state(streams, dev)
+    ws = torch.empty(max(lib.rtstgcn_step_workspace_bytes(ctypes.byref(desc), streams), 256), dtype=torch.uint8, device=dev)
+    io = torch.empty(x_host.numel() + logits_host.numel(), device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def step_host():
+        pkg._lib.check(lib.rtstgcn_step_host(ctypes.byref(desc), x_host.data_ptr(), state.data_ptr(),
+                                             logits_host.data_ptr(), streams, io.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             ctypes.c_void_p(stream)))
+    for _ in range(5):
+        step_host()
+    hs = []
+    for _ in range(min(steps, 100)):
+        t0 = time.perf_counter()
+        step_host()                                            # synchronises on return
+        hs.append((time.perf_counter() - t0) * 1e3)
+    out["e2e"] = {"p50_ms": _p50(hs)[0], "h2d_bytes_per_step": x_host.numel() * 4,
+                  "d2h_bytes_per_step": logits_host.numel() * 4,
+                  "note": "rtstgcn_step_host: pinned host frame -> H2D -> step -> D2H logits, wall clock per call"}
+    if cpu_ref:
+        from oracle import stgcn_oracle as O
+        oc = dict(layers=len(cfg['rt-st-gcn']['out_ch']), stride=cfg['rt-st-gcn']['stride'],
+                  residual=cfg['rt-st-gcn']['residual'], importance=True, kernel=cfg['rt-st-gcn']['kernel'],
+                  out_ch=cfg['rt-st-gcn']['out_ch'])
+        torch.set_num_threads(os.cpu_count() or 1)
+        st = O.rt_state_init(oc, sd, 1)
+        xs = torch.randn(350, 1, c, 1, v)
+        ts = []
+        with torch.no_grad():
+            for i in range(350):
+                t0 = time.perf_counter()
+                O.rt_model_step(xs[i], sd, oc, st)
+                ts.append((time.perf_counter() - t0) * 1e3)
+        out["cpu_reference"] = {"p50_ms": _p50(ts[50:])[0], "streams": 1, "frames": 300, "cores": os.cpu_count() or 1,
+                                "kind": "port", "note": "oracle continual loop (the reference's per-frame ATen op "
+                                "sequence), 50 warm-up + 300 timed frames, batch 1 as in the reference"}
+    del m
+    torch.cuda.empty_cache()
     return out
+
+
+def cost_latency(pkg, dev, streams, steps, math):
+    """CoST-GCN continual step (the reference README's comparator)."""
+    syn = pkg.synthetic
+    cfg = syn.arch_config('st-gcn')
+    cfg['st-gcn']['dilation'] = [1] * 9
+    cfg['math'] = math
+    m = pkg.CostGcn(**cfg)
+    m.load_state_dict(syn.synth_state_dict(m.state_dict(), 83))
+    m = m.to(dev).eval()
+    frames = torch.randn(8, streams, 3, 1, 25, device=dev)
+    for i in range(20):
+        m.step(frames[i % 8])
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        ev[i][0].record()
+        m.step(frames[i % 8])
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    p50, p90 = _p50([a.elapsed_time(b) for a, b in ev])
+    del m
+    torch.cuda.empty_cache()
+    return {"streams": streams, "p50_ms": p50, "p90_ms": p90, "stream_frames_per_s": streams / (p50 * 1e-3),
+            "cuda_graph": False, "math": math}
+
+
+# ----------------------------------------------------------------------------- config 4 / strong scaling
+def tsplit_leg(pkg, model, sd, args, dev, rank, world, dist, timed):
+    """BASELINE config 4: one T=262144 trial, T-partitioned over the ranks (one rank: the plain forward)."""
+    syn, ts, lib = pkg.synthetic, pkg.tsplit, pkg._lib.load()
+    x = syn.synth_input((1, 3, LONG_T, 25), 4242)              # the same trial on every rank (seeded)
+    res = {"workload": "ST-GCN fwd, single trial T=%d V=25 (BASELINE config 4), T-partitioned over %d GPU(s)"
+                       % (LONG_T, world), "n_gpus": world, "frames": LONG_T, "math": args.math}
+    out = None
+    if world == 1:
+        xd = x.to(dev)
+
+        def step():
+            nonlocal out
+            out = model(xd)
+        for _ in range(2):
+            step()
+        ms = timed(step, 3)
+    else:
+        desc, _ = model._descriptor()
+        ex = ts.DistExchange(rank, world, lib.stgcn_model_halo_bytes(ctypes.byref(desc), 1), dev)
+        s, e = ts.chunk_bounds(LONG_T, world, ts.total_stride(syn.TRUNK_STRIDE))[rank]
+        xl = x[:, :, s:e].contiguous().to(dev)
+
+        def step():
+            nonlocal out
+            out = model.forward_tsplit(xl, LONG_T, ex)
+        for _ in range(2):
+            step()
+        b0 = ex.bytes_sent
+        ms = timed(step, 3)
+        res.update(halo_bytes_sent_per_rank_per_step=(ex.bytes_sent - b0) // 3, exchanges_per_step=9,
+                   collective="per-layer ncclSend/ncclRecv with ring neighbours + one all-reduce of the pooled sums")
+    res.update(ms_per_step=ms, steps=3, frames_per_s=LONG_T / (ms * 1e-3))
+    if rank == 0 and not args.no_parity:
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        ref = cpu_reference_step(x, sd, oracle_cfg(syn, args.norm))
+        e = rel_err(out, ref)
+        res["parity"] = {"rel_err": e, "tol": TOL[args.math], "vs": "CPU oracle on the whole trial",
+                         "oracle_s": time.perf_counter() - t0}
+        assert e < TOL[args.math], "T-split result disagrees with the oracle: %.3e" % e
+    return res
+
+
+def strong_leg(model, pkg, args, dev, rank, world, timed, total=256):
+    """BASELINE config 3 strong-scaled: `total` trials over all ranks (32 per GPU at 8 GPUs), no collective."""
+    syn = pkg.synthetic
+    per = -(-total // world)
+    n = max(0, min(per, total - rank * per))
+    x = syn.synth_input((max(n, 1), 3, args.frames, 25), 7000 + rank).to(dev)
+
+    def step():
+        if n:
+            model(x[:n])
+    for _ in range(2):
+        step()
+    ms = timed(step, 3)
+    return {"workload": "ST-GCN fwd, %d trials x T=%d TOTAL over %d GPU(s), trial-sharded, no collective"
+                        % (total, args.frames, world), "n_gpus": world, "trials_total": total, "ms_per_step": ms,
+            "steps": 3, "frames_per_s": total * args.frames / (ms * 1e-3), "scaling": "strong"}
 
 
 def main():
     args = parse()
+    if (os.environ.get('STGCN_DEBUG') or os.environ.get('STGCN_LIB')) and not args.allow_measurement_build:
+        sys.exit("bench.py: STGCN_DEBUG / STGCN_LIB select a measurement build whose results are wrong on purpose; "
+                 "unset them (or pass --allow-measurement-build for a diagnostic run)")
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -282,6 +461,19 @@ def main():
     launches = lib.stgcn_launch_count() - l0
     value = world * frames_per_step / (ms * 1e-3)
 
+    # ---- parity at benchmark size: first and last trial of the timed batch against the CPU oracle ----
+    parity, cpu = None, None
+    ocfg = oracle_cfg(syn, args.norm)
+    if rank == 0 and not args.no_parity and args.norm == 'LayerNorm':
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        pick = sorted({0, N - 1})
+        ref = cpu_reference_step(x_host[pick], sd, ocfg)
+        e = rel_err(out[pick], ref)
+        parity = {"rel_err": e, "tol": TOL[args.math], "trials": pick,
+                  "vs": "CPU oracle (pinned to the reference's outputs by tests/golden) on the same inputs"}
+        assert e < TOL[args.math], "timed run disagrees with the oracle: rel_err %.3e" % e
+
     # ---- e2e: host-buffer C-ABI entry, H2D + forward + D2H every step ----
     e2e = None
     if not args.no_e2e:
@@ -328,12 +520,13 @@ def main():
                     "tensor_pipe_frac": (ach * mma_per_product / pk['bf16_tflops_sustained']) if mma_per_product else None,
                     "note": "achieved = algorithmic FLOPs (SURVEY 8d) of this kernel class / its CUDA-event time; "
                             "fp32-parity mode issues 3 bf16 MMAs per product, so the tensor pipe is busy "
-                            "tensor_pipe_frac of the measured peak",
+                            "tensor_pipe_frac of the measured peak; class_ms are per-class sums of event-bracketed launches",
                     "peak_source": pk['source'] + " bf16 sustained (kernel timed inside a long step)",
                     "launches": int(cls_n[i]), "avg_launch_ms": cls_ms[i] / max(cls_n[i], 1),
                     "share_of_step": cls_ms[i] / total if total else None,
                     "class_ms": {k: round(v, 3) for k, v in shares.items()},
-                    "whole_step_tflops": FLOP_PER_FRAME * frames_per_step / (ms * 1e-3) / 1e12}
+                    "whole_step_tflops": FLOP_PER_FRAME * frames_per_step / (ms * 1e-3) / 1e12,
+                    "whole_step_frac": FLOP_PER_FRAME * frames_per_step / (ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained']}
 
     # ---- the same workload in single-product bf16 mode (north_star: "a stated bf16 tolerance when that mode is
     # enabled"): reported next to the fp32-parity headline, never instead of it ----
@@ -355,29 +548,71 @@ def main():
         ms16 = timed(step16, 3)
         ref = out.float()
         bf16_leg = {"value": frames_per_step / (ms16 * 1e-3), "unit": UNIT, "ms_per_step": ms16, "steps": 3,
+                    "whole_step_frac": FLOP_PER_FRAME * frames_per_step / (ms16 * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
                     "max_rel_diff_vs_parity_mode": float((o16.float() - ref).abs().max() / ref.abs().max()),
-                    "stated_tolerance": "3e-2 relative on logits vs the fp32 reference (tests/test_gpu_parity.py BF16_TOL)"}
+                    "stated_tolerance": "2e-2 relative on logits and >= 98 % top-1 agreement vs the fp32 reference "
+                                        "(tests/test_gpu_parity.py BF16_TOL / BF16_TOP1)"}
         del m16, o16
+
+    del x
+    torch.cuda.empty_cache()
+
+    # ---- config 4 and strong-scaled config 3 (every rank takes part) ----
+    tsplit, strong = None, None
+    if not args.no_long and args.norm == 'LayerNorm' and args.math != 'fp32':
+        tsplit = tsplit_leg(pkg, model, sd, args, dev, rank, world, dist, timed)
+        if world > 1:
+            strong = strong_leg(model, pkg, args, dev, rank, world, timed)
+        torch.cuda.empty_cache()
+
+    # ---- config 1 (N=1, T=300) on the GPU and on the host cores ----
+    c1 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        x1h = syn.synth_input((1, 3, 300, V), 4321)
+        x1 = x1h.to(dev)
+        for _ in range(5):
+            model(x1)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+        for a, b in evs:
+            a.record()
+            o1 = model(x1)
+            b.record()
+        torch.cuda.synchronize()
+        g50 = _p50([a.elapsed_time(b) for a, b in evs])[0]
+        torch.set_num_threads(os.cpu_count() or 1)
+        r1 = cpu_reference_step(x1h, sd, ocfg)
+        cs = []
+        for _ in range(7):
+            t0 = time.perf_counter()
+            cpu_reference_step(x1h, sd, ocfg)
+            cs.append((time.perf_counter() - t0) * 1e3)
+        c50 = _p50(cs)[0]
+        c1 = {"workload": "ST-GCN fwd, N=1 C=3 T=300 V=25 (BASELINE config 1)", "gpu_p50_ms": g50,
+              "gpu_frames_per_s": 300 / (g50 * 1e-3), "cpu_p50_ms": c50, "cpu_frames_per_s": 300 / (c50 * 1e-3),
+              "cpu_cores": os.cpu_count() or 1, "cpu_kind": "port", "rel_err_vs_cpu": rel_err(o1, r1)}
 
     rt = None
     if rank == 0 and world == 1 and not args.no_rt:
-        del x
-        torch.cuda.empty_cache()
         imu = dict(graph='imu_fogit_ABCD', in_feat=6, num_classes=8)
-        rt = {"pku": [rt_latency(pkg, dev, b, args.rt_steps, {}, args.math, pk['hbm_gbs'])
+        want_cpu = not args.no_cpu_baseline
+        rt = {"pku": [rt_latency(pkg, dev, b, args.rt_steps, {}, args.math, pk['hbm_gbs'], cpu_ref=(want_cpu and b == 1))
                       for b in (1, args.rt_streams)],
-              "imu_bf16": [rt_latency(pkg, dev, b, args.rt_steps, imu, 'bf16', pk['hbm_gbs'])
-                           for b in (1, args.rt_streams)]}
-        rt["note"] = ("BASELINE configs 2 and 5: one continual step for all streams (LayerNorm, fp32 FIFO/accumulator "
-                      "state, CUDA-graph replay), p50 over %d steps after a 20-step FIFO fill; pku math=%s, imu "
-                      "math=bf16 (stated tolerance 3e-2 rel., tests/test_gpu_parity.py)" % (args.rt_steps, args.math))
+              "imu_bf16": [rt_latency(pkg, dev, b, args.rt_steps, imu, 'bf16', pk['hbm_gbs'],
+                                      cpu_ref=(want_cpu and b == 1))
+                           for b in (1, args.rt_streams)],
+              "costgcn_pku": [cost_latency(pkg, dev, b, min(args.rt_steps, 100), args.math if args.math != 'fp32' else 'bf16x3')
+                              for b in (1, args.rt_streams)]}
+        rt["note"] = ("BASELINE configs 2 and 5: one continual step for all streams (LayerNorm, CUDA-graph replay), p50 over "
+                      "%d steps after a 20-step FIFO fill; pku math=%s (fp32 FIFO + accumulator state), imu math=bf16 "
+                      "(bf16 FIFO + fp32 accumulator at 4096 streams; stated tolerance 2e-2 rel. / 98 %% top-1, "
+                      "tests/test_gpu_benchsize.py); roofline = state bytes of that layout / p50 vs the measured HBM copy "
+                      "peak; costgcn_pku: the CoST-GCN continual step (eager launches)" % (args.rt_steps, args.math))
 
-    cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         xs = x_host[:1].clone()
-        ocfg = oracle_cfg(syn, args.norm)
         cpu_reference_step(xs, sd, ocfg)
         reps, t0 = 0, time.perf_counter()
         while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 20):
@@ -389,19 +624,19 @@ def main():
                          % (reps, T, N)}
 
     if rank == 0:
-        print(json.dumps({
+        line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3(f32-parity)", "bf16": "bf16"}[args.math],
-            "data": "synthetic",
-            "config": {"workload": "ST-GCN fwd, 9 layers, PKU-MMD 25-joint graph, %s, N=%d trials x T=%d per GPU "
-                                   "(BASELINE config 3), trial-sharded, no collective" % (args.norm, N, T),
-                       "trials_per_gpu": N, "frames_per_trial": T, "math": args.math,
-                       "l2": "inputs and activations (>= 0.3 GB per tensor) exceed the 126 MB L2"},
-            "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "rt": rt,
-            "bf16_mode": bf16_leg,
-            "clocks": clocks.summary(),
-        }))
+            "data": "synthetic", "config": workload_config(args, N, T),
+            "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "parity": parity, "cpu_baseline": cpu,
+            "c1": c1, "rt": rt, "bf16_mode": bf16_leg, "clocks": clocks.summary(),
+        }
+        if world == 1:
+            line["long_trial"] = tsplit
+        else:
+            line["tsplit"], line["strong"] = tsplit, strong
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

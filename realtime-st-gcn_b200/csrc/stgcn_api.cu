@@ -275,41 +275,6 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
   return 0;
 }
 
-// ---- library-owned side stream (one per device) for the two-stream software pipeline of the graph-conv
-// stage; the caller's stream forks into it and joins again with events, so the calls stay ordinary
-// stream-ordered work for the caller (and capturable into a CUDA graph) --------------------------------
-struct SidePool {
-  cudaStream_t side = nullptr;
-  cudaEvent_t gemm_done[8], ln_done[8];
-};
-// one pool per host thread and device: two threads driving the same device (DataParallel-style replicas,
-// the emulated-rank tests) must not share the event ring
-SidePool *side_pool() {
-  static thread_local SidePool pools[16];
-  static thread_local bool ready[16] = {false};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  if (!ready[dev]) {
-    SidePool &p = pools[dev];
-    if (cudaStreamCreateWithFlags(&p.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    for (int i = 0; i < 8; ++i) {
-      if (cudaEventCreateWithFlags(&p.gemm_done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-      if (cudaEventCreateWithFlags(&p.ln_done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    }
-    ready[dev] = true;
-  }
-  return &pools[dev];
-}
-// STGCN_OVERLAP=0: run the graph-conv stage's two kernels back to back on the caller's stream
-inline bool overlap_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char *e = getenv("STGCN_OVERLAP");
-    on = e ? atoi(e) != 0 : 1;
-  }
-  return on != 0;
-}
-
 // ---- graph-conv stage with per-joint pre-scaled weights (kernels_gcnw.cuh) --------------------
 // z = GEMM(x planes) + bias, then LayerNorm(C,V) (+ ReLU) into l.out_*.  Fused form: one cooperative
 // persistent kernel, z through an L2-resident ring; two-kernel form: z in HBM + k_ln_stream.
@@ -338,73 +303,19 @@ int gcnw_stage(int c_out, const __nv_bfloat16 *xh, const __nv_bfloat16 *wsc, tc:
       STGCN_LAUNCH_OK();
     }
   } else {
-    // Two kernels per sub-chunk, software-pipelined over two streams: the GEMM of sub-chunk s+1 (tensor /
-    // latency bound, 1 CTA per SM at <= 88 registers) runs while the streaming LayerNorm of sub-chunk s
-    // (HBM / issue bound) fills the same SMs' spare warps.  z is double-buffered per sub-chunk.
-    int S = (int)(rows / 800000);
-    S = S < 1 ? 1 : (S > 8 ? 8 : S);
-    const bool by_trial = g.N >= S;
-    if (!by_trial && g.N != 1) S = 1;
-    if (!overlap_enabled()) S = 1;
-    // sub-chunk = `per` trials, or (single trial) `per` frames in multiples of 128
-    long long per = by_trial ? (g.N + S - 1) / S : (((long long)g.T + S - 1) / S + 127) / 128 * 128;
-    if (S == 1) per = by_trial ? g.N : g.T;
-    const long long sub_rows = (by_trial ? per * g.T : per) * V;
-    float *zb[2] = {ws.take<float>((size_t)sub_rows * c_out), S > 1 ? ws.take<float>((size_t)sub_rows * c_out) : nullptr};
+    float *zb = ws.take<float>((size_t)rows * c_out);
     if (!ws.measuring()) {
       STGCN_REQUIRE(!ws.overflow, "workspace too small (graph-conv stage)");
-      SidePool *sp = S > 1 ? side_pool() : nullptr;
-      STGCN_REQUIRE(S == 1 || sp, "graph-conv stage: cannot create the side stream");
-      const int Cin = g.Cin;
-      const long long total = by_trial ? g.N : g.T;
-      int k = 0;
-      for (long long at = 0; at < total; at += per, ++k) {
-        const long long cnt = total - at < per ? total - at : per;
-        tc::GcnwParams gs = g;
-        tc::LnStreamArgs ls = l;
-        const __nv_bfloat16 *xs = xh;
-        long long out_frame0;                         // first output frame (of the l.out_* buffers) of this sub-chunk
-        if (by_trial) {
-          gs.N = (int)cnt;
-          xs = xh + (size_t)at * T_full * V * Cin;
-          ls.frames = cnt * g.T;
-          out_frame0 = at * (l.out_T ? l.out_T : g.T);
-        } else {
-          gs.T = (int)cnt;
-          xs = xh + (size_t)at * fstride * V * Cin;
-          ls.frames = cnt;                            // single trial: frame t -> t + out_t0 of the same buffer
-          out_frame0 = at;
-        }
-        gs.out = zb[k & 1];
-        ls.z = zb[k & 1];
-        const size_t oo = (size_t)out_frame0 * V * c_out;
-        if (l.out_f32) ls.out_f32 = l.out_f32 + oo;
-        if (l.out_hi) ls.out_hi = l.out_hi + oo;
-        if (l.out_lo) ls.out_lo = l.out_lo + oo;
-        if (S > 1 && k >= 2) STGCN_CUDA_OK(cudaStreamWaitEvent(st, sp->ln_done[(k - 2) & 7], 0));   // z buffer free again
-        {
-          ProfScope ps(KC_GEMM_1X1, st);
-          if (tc::launch_gcnw(c_out, xs, wsc, gs, T_full, fstride, cap, plane_stride, st)) return 1;
-          STGCN_LAUNCH_OK();
-        }
-        cudaStream_t ln_st = st;
-        if (S > 1) {
-          STGCN_CUDA_OK(cudaEventRecord(sp->gemm_done[k & 7], st));
-          STGCN_CUDA_OK(cudaStreamWaitEvent(sp->side, sp->gemm_done[k & 7], 0));
-          ln_st = sp->side;
-        }
-        {
-          ProfScope ps(KC_FRAME, ln_st);
-          if (tc::launch_ln_stream(ls, ln_st)) return 1;
-          STGCN_LAUNCH_OK();
-        }
-        if (S > 1) STGCN_CUDA_OK(cudaEventRecord(sp->ln_done[k & 7], sp->side));
+      g.out = zb;
+      {
+        ProfScope ps(KC_GEMM_1X1, st);
+        if (tc::launch_gcnw(c_out, xh, wsc, g, T_full, fstride, cap, plane_stride, st)) return 1;
+        STGCN_LAUNCH_OK();
       }
-      if (S > 1) {
-        // join: everything the side stream did becomes a dependency of the caller's stream
-        STGCN_CUDA_OK(cudaStreamWaitEvent(st, sp->ln_done[(k - 1) & 7], 0));
-        if (k >= 2) STGCN_CUDA_OK(cudaStreamWaitEvent(st, sp->ln_done[(k - 2) & 7], 0));
-      }
+      l.z = zb;
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_ln_stream(l, st)) return 1;
+      STGCN_LAUNCH_OK();
     }
   }
   ws.release(mark);
