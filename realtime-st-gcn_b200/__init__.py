@@ -12,6 +12,8 @@ from . import synthetic       # noqa: F401
 from . import skeletons       # noqa: F401
 from . import tsplit          # noqa: F401
 from . import processor       # noqa: F401
+from . import segment         # noqa: F401
+from . import checkpoint      # noqa: F401
 from .models import MODELS, Stgcn, RtStgcn, CostGcn   # noqa: F401
 
-__all__ = ['MODELS', 'Stgcn', 'RtStgcn', 'CostGcn', 'synthetic', 'skeletons', 'tsplit', 'processor']
+__all__ = ['MODELS', 'Stgcn', 'RtStgcn', 'CostGcn', 'synthetic', 'skeletons', 'tsplit', 'processor', 'segment', 'checkpoint']

@@ -289,12 +289,86 @@ def gen_cost_models():
          digest=np.array(syn.state_digest(sd)))
 
 
+def gen_segments():
+    """BufferSegment / WindowSegment arithmetic of the reference (utils/segment_generator.py) on index ramps:
+    padding, chunk starts, label slices, which predictions survive mask_segment, and the fold of the
+    one-chunk-per-executor mode."""
+    from utils.segment_generator import BufferSegment as RefBuf, WindowSegment as RefWin
+    import torch.nn.functional as F
+    arrays = {}
+    base = dict(stages=1, num_classes=3, graph=dict(num_node=5), in_feat=2)
+    for L, S, G, W in ((100, 30, 9, 1), (101, 30, 9, 1), (250, 64, 9, 1), (90, 40, 9, 1)):
+        seg = RefBuf(rank='cpu', world_size=W, kernel=G, segment=S, **base)
+        ps, pe = seg.pad_sequence(L)
+        cap = torch.arange(L, dtype=torch.float32).view(1, 1, L, 1).expand(1, 2, L, 5).contiguous()
+        cap = F.pad(cap, (0, 0, ps, pe), value=-1.0)
+        labels = torch.arange(L).view(1, L)
+        starts, lab_lo, lab_hi, kept = [], [], [], []
+        for i, (x, y, n) in enumerate(seg.get_segment(cap, labels)):
+            starts.append(int(x[0, 0, 0, 0]))
+            lab_lo.append(int(y[0, 0]) if y.numel() else -1)
+            lab_hi.append(int(y[0, -1]) if y.numel() else -1)
+            pred = x[:, :1, :, 0].expand(1, 3, S)                  # "prediction" = the frame index itself
+            kept.append(seg.mask_segment(i, n, L, ps, pe, pred)[0, 0])
+        tag = 'buf|%d|%d|%d|%d|' % (L, S, G, W)
+        arrays[tag + 'pad'] = np.array([ps, pe, n])
+        arrays[tag + 'starts'] = np.array(starts)
+        arrays[tag + 'labels'] = np.array([lab_lo, lab_hi])
+        arrays[tag + 'kept'] = torch.cat(kept).numpy()
+    for L, G, W in ((64, 9, 2), (77, 9, 3), (50, 9, 1)):
+        seg = RefBuf(rank='cpu', world_size=W, kernel=G, **base)
+        ps, pe = seg.pad_sequence(L)
+        # the reference's get_segment returns (not yields) in this mode; rebuild its batch the way it would
+        cap = F.pad(torch.arange(L, dtype=torch.float32).view(1, 1, L, 1).expand(1, 2, L, 5).contiguous(), (0, 0, ps, pe), value=-1.0)
+        x = cap.unfold(2, seg.S, seg.S - G).permute(0, 2, 1, 4, 3).contiguous().view(W, 2, seg.S, 5)
+        pred = (x[:, :1, :, 0] + 1.0).expand(W, 3, seg.S).contiguous()
+        out = seg.mask_segment(0, 1, L, ps, pe, pred)
+        tag = 'fold|%d|%d|%d|' % (L, G, W)
+        arrays[tag + 'pad'] = np.array([ps, pe, seg.S])
+        arrays[tag + 'starts'] = x[:, 0, 0, 0].numpy()
+        arrays[tag + 'out'] = out.numpy()
+    for L, RF, S in ((40, 16, 10), (37, 8, 12)):
+        seg = RefWin(rank='cpu', world_size=1, receptive_field=RF, segment=S, **base)
+        ps, pe = seg.pad_sequence(L)
+        cap = F.pad(torch.arange(L, dtype=torch.float32).view(1, 1, L, 1).expand(1, 2, L, 5).contiguous(), (0, 0, ps, pe), value=-1.0)
+        labels = torch.arange(L).view(1, L)
+        first, last, nwin, lab = [], [], [], []
+        for x, y, n in seg.get_segment(cap, labels):
+            first.append(int(x[0, 0, -1, 0])); last.append(int(x[-1, 0, -1, 0])); nwin.append(x.shape[0])
+            lab.append([int(y[0, 0]), int(y[0, -1])])
+        tag = 'win|%d|%d|%d|' % (L, RF, S)
+        arrays[tag + 'pad'] = np.array([ps, pe, n])
+        arrays[tag + 'ends'] = np.array([first, last, nwin])
+        arrays[tag + 'labels'] = np.array(lab)
+    save('segments', **arrays)
+
+
+def gen_checkpoint():
+    """A checkpoint file exactly as the reference writes it (Processor._save_model, processor.py:325-334), from the
+    small LayerNorm ST-GCN model of `stgcn_model_small_ln` (so its logits are the expected output), plus the
+    DataParallel-style variant whose keys carry the `module.` prefix."""
+    cfg = syn.arch_config('st-gcn', normalization='LayerNorm', num_classes=12, **SMALL)
+    m = RefStgcn(**cfg)
+    m.load_state_dict(syn.synth_state_dict(m.state_dict(), 41))
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    torch.save({"epoch": 7, "model_state_dict": m.state_dict(), "optimizer_state_dict": opt.state_dict(), "loss": 0.25},
+               os.path.join(OUT, 'ckpt_stgcn_small.pt'))
+    torch.save({"epoch": 7, "model_state_dict": torch.nn.DataParallel(m).state_dict(),
+                "optimizer_state_dict": opt.state_dict(), "loss": 0.25}, os.path.join(OUT, 'ckpt_stgcn_small_dp.pt'))
+    for f in ('ckpt_stgcn_small.pt', 'ckpt_stgcn_small_dp.pt'):
+        print('%-32s %8.1f KB' % (f, os.path.getsize(os.path.join(OUT, f)) / 1024))
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'offline':
         gen_rt_offline()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'cost':
         gen_cost_models()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'host':
+        gen_segments()
+        gen_checkpoint()
         sys.exit(0)
     gen_graphs()
     gen_primitives()
@@ -303,3 +377,5 @@ if __name__ == '__main__':
     gen_rt_models()
     gen_rt_offline()
     gen_cost_models()
+    gen_segments()
+    gen_checkpoint()
