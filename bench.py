@@ -367,11 +367,23 @@ def tsplit_leg(pkg, model, sd, args, dev, rank, world, dist, timed):
                    collective="per-layer ncclSend/ncclRecv with ring neighbours + one all-reduce of the pooled sums")
     res.update(ms_per_step=ms, steps=3, frames_per_s=LONG_T / (ms * 1e-3))
     if rank == 0 and not args.no_parity:
+        # The reference pools with F.avg_pool2d in fp32; over the 65536 x 25 values per channel of this trial that
+        # kernel's own rounding error is 5.6e-4 on the pooled vector / 3.1e-4 on the logits (measured against an
+        # fp64 mean of the same fp32 trunk output) -- above the 1e-4 bound by itself.  Parity
+        # is therefore asserted against the oracle's trunk output pooled exactly (fp64), and the distance to the
+        # reference's own fp32 pooling is reported beside it.
+        from oracle import stgcn_oracle as O
         torch.set_num_threads(os.cpu_count() or 1)
         t0 = time.perf_counter()
-        ref = cpu_reference_step(x, sd, oracle_cfg(syn, args.norm))
-        e = rel_err(out, ref)
-        res["parity"] = {"rel_err": e, "tol": TOL[args.math], "vs": "CPU oracle on the whole trial",
+        with torch.no_grad():
+            ref, feats = O.stgcn_model(x, sd, oracle_cfg(syn, args.norm), return_features=True)
+        pooled = feats.double().mean(dim=(2, 3))
+        exact = (pooled @ sd['fcn_out.weight'].flatten(1).double().t() + sd['fcn_out.bias'].double()).unsqueeze(-1)
+        e, e_ref = rel_err(out, exact), rel_err(out, ref)
+        res["parity"] = {"rel_err": e, "tol": TOL[args.math],
+                         "vs": "CPU oracle trunk output of the whole trial, pooled in fp64",
+                         "rel_err_vs_reference_fp32_pooling": e_ref,
+                         "reference_pooling_own_error": rel_err(ref, exact),
                          "oracle_s": time.perf_counter() - t0}
         assert e < TOL[args.math], "T-split result disagrees with the oracle: %.3e" % e
     return res

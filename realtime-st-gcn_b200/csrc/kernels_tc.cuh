@@ -397,7 +397,7 @@ template <int C, int NH, bool kPR>
 __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr, int w,
                                            bool row_ok, long long row, long long row_o, float *s_part,
                                            int tile_parity, int h, uint8_t *patch, float shift, float s1, float s2,
-                                           bool add_bias, bool relu_mid, int bar_id = 1, const float *s_tabs = nullptr) {
+                                           bool add_bias, bool relu_mid, int bar_id = 1) {
   constexpr int CH = C / NH;
   const int c0 = h * CH;
   const int pstep = e.bias_sw ? V : 1;
@@ -419,9 +419,8 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
   }
   const float nmr = -mean * rstd;
   const long long tf1 = fdbg ? clock64() : 0;
-  // s_tabs: the two affine tables staged in shared memory by the kernel ([C/4][V][4] weight, then bias)
-  const float4 *nw4 = reinterpret_cast<const float4 *>(s_tabs ? s_tabs : e.n_wT) + (c0 >> 2) * V + w;
-  const float4 *nb4 = reinterpret_cast<const float4 *>(s_tabs ? s_tabs + C * V : e.n_bT) + (c0 >> 2) * V + w;
+  const float4 *nw4 = reinterpret_cast<const float4 *>(e.n_wT) + (c0 >> 2) * V + w;
+  const float4 *nb4 = reinterpret_cast<const float4 *>(e.n_bT) + (c0 >> 2) * V + w;
   const int lane = threadIdx.x & 31;
   const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
   const long long row0 = __shfl_sync(0xffffffffu, row, 0);        // rows of a warp are contiguous
@@ -507,8 +506,8 @@ __device__ __forceinline__ void epi_finish(const EpiParams &e, uint32_t taddr, i
           const int pi = (cb >> 2) + i;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (add_bias) b4 = __ldg(bias4 + pi * pstep);
-          const float4 g4 = s_tabs ? nw4[pi * V] : __ldg(nw4 + pi * V);
-          const float4 o4 = s_tabs ? nb4[pi * V] : __ldg(nb4 + pi * V);
+          const float4 g4 = __ldg(nw4 + pi * V);
+          const float4 o4 = __ldg(nb4 + pi * V);
           // ((v + b) - mean) * rstd * g + o as two FMAs on (v + b): x * rstd + (-mean * rstd), then * g + o
           v[4 * i] = fmaf(fmaf(v[4 * i] + b4.x, rstd, nmr), g4.x, o4.x);
           v[4 * i + 1] = fmaf(fmaf(v[4 * i + 1] + b4.y, rstd, nmr), g4.y, o4.y);
@@ -653,7 +652,7 @@ template <int C, int NH, bool kPR = false>
 __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t taddr, int r, int RT, int V, int fr,
                                                  int w, bool row_ok, long long row, long long row_o,
                                                  float *s_part, int tile_parity, int h, uint8_t *patch,
-                                                 int bar_id = 1, const float *s_tabs = nullptr) {
+                                                 int bar_id = 1) {
   if (e.debug & 1) return;
   constexpr int CH = C / NH;
   static_assert(CH % 32 == 0, "epilogue works in 32-column super-chunks");
@@ -683,7 +682,7 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiParams &e, uint32_t ta
   }
   if (pdbg) atomicAdd(&g_dbg[12], (unsigned long long)(clock64() - tp0));
   epi_finish<C, NH, kPR>(e, taddr, r, RT, V, fr, w, row_ok, row, row_o, s_part, tile_parity, h, patch, shift, s1, s2,
-                         true, false, bar_id, s_tabs);
+                         true, false, bar_id);
 }
 
 // RT-ST-GCN epilogue: the accumulator row holds z_t (graph-convolved frame, before bias).  Per
@@ -833,7 +832,6 @@ struct TcnTc2Params {
   int load_row[2];            // destination row in the stage
   int load_bytes[2];
   int tap_row[16];            // first stage row of tap j for tile 0
-  int tab_bytes;              // pair kernel: bytes reserved for the LayerNorm affine tables in shared memory (0: none)
   EpiParams epi;
 };
 
@@ -1630,15 +1628,6 @@ inline int tcn_sets_wanted() {
 // `halo`: the plane buffer holds `halo` extra frames before and after the T frames of every trial
 // (T-split: filled by the neighbouring ranks, or zeros at the sequence ends); output frame tau
 // still reads input frames stride*tau + j - pad of the T-frame sequence.
-inline bool tcn_tab_smem_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char *e = getenv("STGCN_TCN_TAB_SMEM");
-    on = e ? atoi(e) != 0 : 1;
-  }
-  return on != 0;
-}
-
 template <int C>
 int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Params p, int N, int T, int stride,
                      int halo, cudaStream_t st) {
@@ -1734,12 +1723,7 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
                                        : ((p.planes == 1 || p.epi.res_hi || (p.epi.out_hi && !p.epi.out_f32)) ? 2 : 1);
     int sets = (p.NT == 2 && want >= 2 &&
                 (kMaxSmem - 2 * p.a_stage_bytes - 2 * (kPartBytes + kPatchTotal) - 1536) / kBHalf >= 3) ? 2 : 1;
-    int fixed_p = sets * (kPartBytes + kPatchTotal) + 512 + 1024;
-    // LayerNorm affine tables (2 * C * V floats) in shared memory when at least four weight stages remain: the
-    // kernel leaves < 8 KB of L1, so the per-element table loads of the epilogue were missing L1 (hit rate 55 %)
-    const int tab = (2 * C * V * 4 + 127) & ~127;
-    p.tab_bytes = (!p.epi.raw && (kMaxSmem - 2 * p.a_stage_bytes - fixed_p - tab) / kBHalf >= 4 && tcn_tab_smem_enabled()) ? tab : 0;
-    fixed_p += p.tab_bytes;
+    const int fixed_p = sets * (kPartBytes + kPatchTotal) + 512 + 1024;
     int S = (kMaxSmem - 2 * p.a_stage_bytes - fixed_p) / kBHalf;
     if (S > 12) S = 12;
     if (S >= 2) {

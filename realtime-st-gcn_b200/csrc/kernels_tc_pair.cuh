@@ -121,8 +121,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * kEpiNH
   const uint32_t sB = sA + 2 * p.a_stage_bytes;
   const uint32_t sPart = sB + S * kBHalf;
   const uint32_t sPatch = sPart + SETS * kPartBytes;
-  const uint32_t sTabs = sPatch + SETS * kPatchTotal;               // LayerNorm affine tables (p.tab_bytes, may be 0)
-  const uint32_t sBar = sTabs + p.tab_bytes;
+  const uint32_t sBar = sPatch + SETS * kPatchTotal;
   const uint32_t bFullA = sBar, bEmptyA = sBar + 16, bPeerA = sBar + 32, bTmemFull = sBar + 48, bTmemEmpty = sBar + 64;
   const uint32_t bFullB = sBar + 80, bEmptyB = bFullB + 8 * S, bPeerB = bEmptyB + 8 * S;
   const uint32_t sTmemPtr = bPeerB + 8 * S;
@@ -158,16 +157,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * kEpiNH
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(sTmemPtr, kTmemCols);
-  const float *s_tabs = nullptr;
-  if (p.tab_bytes) {
-    float *s_tab = reinterpret_cast<float *>(gen_base + (sTabs - smem_base));
-    const int nt = C * p.V;
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-      s_tab[i] = __ldg(p.epi.n_wT + i);
-      s_tab[nt + i] = __ldg(p.epi.n_bT + i);
-    }
-    s_tabs = s_tab;
-  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                              // barriers of both CTAs initialised, TMEM allocated
@@ -321,7 +310,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * kEpiNH
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
         ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part_set, par, h, patch,
-                                          1 + set, s_tabs);
+                                          1 + set);
       }
       tc_fence_before();
       __syncwarp();
