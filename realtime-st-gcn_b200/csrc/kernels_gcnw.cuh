@@ -130,6 +130,11 @@ struct GcnwParams {
   // single joint are the taps, "source joint" of tap j = ring slot tap_src[j]; tab is not used
   int ntaps;
   int tap_src[16];
+  // temporal mode (tmode == 2: the Gamma x 1 convolution of an ST-GCN layer for ANY Gamma): the "edges" of every
+  // joint are the ntaps taps, source joint = the joint itself, tap j reads input frame stride*tau + j - tpad
+  // (frames outside the trial are zero-filled by TMA = the convolution's zero padding); stride 2 reads the
+  // even / odd frame sequences through two tensor maps
+  int tmode, tpad, tstride;
   // fused LayerNorm stage (k_gcnw<.., FUSE = true>)
   float *zring;                 // [R][128 frames][V][CO] fp32
   float2 *sring;                // [R][128][V][kEpiNH] (mean, M2) of every (frame, joint, column group)
@@ -218,7 +223,8 @@ constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B 
 // instead of five per twelve, and the weight hi plane is loaded once instead of twice.
 template <int CO, bool MERGE, bool FUSE>
 __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), FUSE ? 1 : 2)
-    k_gcnw(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GcnwParams p) {
+    k_gcnw(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x1,
+           const __grid_constant__ CUtensorMap tm_w, const GcnwParams p) {
   constexpr int kAPlane = 128 * 128;            // [128 frames][64 ch] bf16
   constexpr int kBPlane = CO * 128;             // [CO][64 ch] bf16
   constexpr int kABytes = MERGE ? 2 * kAPlane : kAPlane;
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.Cin / 64;
-  if (p.tab && __ldg(&p.tab->nedge) < 0) {
+  if (p.tmode == 0 && __ldg(&p.tab->nedge) < 0) {
     // the caller vouched for a sparse adjacency (stgcn_model_desc.reserved bit 1) that is not sparse:
     // fail loudly instead of computing with a truncated edge list
     if (threadIdx.x == 0 && blockIdx.x == 0)
@@ -255,6 +261,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_x1);
     tma_prefetch_desc(&tm_w);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bTmemFull + 8 * i, 1);
@@ -275,10 +282,10 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(sTmemPtr, 512);
-  if (p.ntaps > 0) {
+  if (p.tmode == 1) {
     if (threadIdx.x == 0) { s_ptr[0] = 0; s_ptr[1] = p.ntaps; }
     if (threadIdx.x < 16) s_src[threadIdx.x] = p.tap_src[threadIdx.x];
-  } else {
+  } else if (p.tmode == 0) {
     for (int i = threadIdx.x; i <= p.V; i += blockDim.x) s_ptr[i] = __ldg(&p.tab->ptr[i]);
     for (int i = threadIdx.x; i < kGwEdgeCap; i += blockDim.x) s_src[i] = __ldg(&p.tab->src[i]);
   }
@@ -292,29 +299,43 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
     // chunk and plane ----
     if (lane == 0) {
       int as = 0, a_ph = 0;
-      const bool tap = p.ntaps > 0;      // tap mode: tensor-map dimension 1 = rows, 2 = ring slots
+      const bool tap = p.tmode == 1;     // ring-tap mode: tensor-map dimension 1 = rows, 2 = ring slots
+      const bool tmp = p.tmode == 2;     // temporal mode: same joint, frame offset per tap, even / odd maps
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int w = item % p.V;
         const int tb = (item / p.V) % p.tblocks, n = item / (p.V * p.tblocks);
-        for (int e = s_ptr[w]; e < s_ptr[w + 1]; ++e)
+        const int e0 = tmp ? 0 : s_ptr[w], e1 = tmp ? p.ntaps : s_ptr[w + 1];
+        for (int e = e0; e < e1; ++e) {
+          // coordinates of the edge's / tap's activation box (dimension 1, dimension 2) and its tensor map
+          int c1 = tap ? tb * 128 : s_src[e], c2 = tap ? s_src[e] : tb * 128;
+          const CUtensorMap *tm = &tm_x;
+          if (tmp) {
+            const int d = e - p.tpad;
+            c1 = w;
+            if (p.tstride == 2) {
+              c2 = tb * 128 + (d >> 1);               // position in the even / odd frame sequence
+              tm = (d & 1) ? &tm_x1 : &tm_x;
+            } else {
+              c2 = tb * 128 + d;
+            }
+          }
           for (int kc = 0; kc < KC; ++kc) {
             if (MERGE) {
               mbar_wait(bEmptyA + 8 * as, a_ph ^ 1);
               mbar_expect_tx(bFullA + 8 * as, (uint32_t)(p.planes * kAPlane));
               for (int ap = 0; ap < p.planes; ++ap)
-                tma_load_5d(sA + as * kABytes + ap * kAPlane, &tm_x, bFullA + 8 * as, kc * 64, tap ? tb * 128 : s_src[e],
-                            tap ? s_src[e] : tb * 128, n, ap);
+                tma_load_5d(sA + as * kABytes + ap * kAPlane, tm, bFullA + 8 * as, kc * 64, c1, c2, n, ap);
               if (++as == SA) { as = 0; a_ph ^= 1; }
             } else {
               for (int ap = 0; ap < p.planes; ++ap) {
                 mbar_wait(bEmptyA + 8 * as, a_ph ^ 1);
                 mbar_expect_tx(bFullA + 8 * as, kAPlane);
-                tma_load_5d(sA + as * kABytes, &tm_x, bFullA + 8 * as, kc * 64, tap ? tb * 128 : s_src[e], tap ? s_src[e] : tb * 128,
-                            n, ap);
+                tma_load_5d(sA + as * kABytes, tm, bFullA + 8 * as, kc * 64, c1, c2, n, ap);
                 if (++as == SA) { as = 0; a_ph ^= 1; }
               }
             }
           }
+        }
       }
     }
   } else if (warp == 2) {
@@ -323,7 +344,8 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
       int bs = 0, b_ph = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int w = item % p.V;
-        for (int e = s_ptr[w]; e < s_ptr[w + 1]; ++e)
+        const int e0 = p.tmode == 2 ? 0 : s_ptr[w], e1 = p.tmode == 2 ? p.ntaps : s_ptr[w + 1];
+        for (int e = e0; e < e1; ++e)
           for (int kc = 0; kc < KC; ++kc) {
             if (MERGE) {
               mbar_wait(bEmptyB + 8 * bs, b_ph ^ 1);
@@ -355,7 +377,8 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * CO;
       uint32_t acc = 0;
-      for (int e = s_ptr[w]; e < s_ptr[w + 1]; ++e)
+      const int e0 = p.tmode == 2 ? 0 : s_ptr[w], e1 = p.tmode == 2 ? p.ntaps : s_ptr[w + 1];
+      for (int e = e0; e < e1; ++e)
         for (int kc = 0; kc < KC; ++kc) {
           if (MERGE) {
             mbar_wait(bFullA + 8 * a_s, a_ph);
@@ -428,7 +451,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
       const int w = item % p.V;
       const int grp = item / p.V;                                  // frame group (n, tb)
       const int tb = grp % p.tblocks, n = grp / p.tblocks;
-      const bool has_edges = s_ptr[w + 1] > s_ptr[w];
+      const bool has_edges = p.tmode == 2 || s_ptr[w + 1] > s_ptr[w];
       const int t = tb * 128 + q * 32 + lane;
       const bool row_ok = t < p.T;
       const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
@@ -859,6 +882,22 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
     xb[1] = 128; xb[2] = 1;
   }
   if (make_tmap_bf16(&tm_x, x, 5, xd, xs, xb)) return 1;
+  CUtensorMap tm_x1 = tm_x;
+  if (p.tmode == 2) {
+    // the view is the convolution INPUT: T_full frames per trial, read at stride p.tstride
+    if (p.tstride == 2) {
+      for (int q = 0; q < 2; ++q) {
+        xd[2] = q == 0 ? (uint64_t)(T_full + 1) / 2 : (uint64_t)T_full / 2;
+        xs[1] = (uint64_t)2 * V * p.Cin * 2;
+        if (make_tmap_bf16(q == 0 ? &tm_x : &tm_x1, x + (size_t)q * V * p.Cin, 5, xd, xs, xb)) return 1;
+      }
+    } else {
+      xd[2] = (uint64_t)T_full;
+      xs[1] = (uint64_t)V * p.Cin * 2;
+      if (make_tmap_bf16(&tm_x, x, 5, xd, xs, xb)) return 1;
+      tm_x1 = tm_x;
+    }
+  }
   const uint64_t wd[4] = {(uint64_t)p.Cin, (uint64_t)CO, (uint64_t)cap, 2};
   const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)cap * CO * p.Cin * 2};
   const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
@@ -867,11 +906,11 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
   STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcnw<CO, MERGE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   if (FUSE) {
     // producers wait for consumers in other CTAs: every CTA must be resident -> cooperative launch
-    void *args[3] = {&tm_x, &tm_w, &p};
+    void *args[4] = {&tm_x, &tm_x1, &tm_w, &p};
     STGCN_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_gcnw<CO, MERGE, FUSE>), dim3(grid),
                                               dim3(kGwThreads + 32 + kGwLnThreads), args, (size_t)smem, st));
   } else {
-    k_gcnw<CO, MERGE, FUSE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_w, p);
+    k_gcnw<CO, MERGE, FUSE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_x1, tm_w, p);
   }
   return 0;
 }

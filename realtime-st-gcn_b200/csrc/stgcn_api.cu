@@ -109,6 +109,17 @@ int launch_frame(const FrameArgs &a, cudaStream_t st) {
   return 0;
 }
 
+// STGCN_TAPS=0: layers the frame-tile temporal kernel does not cover (Gamma > 15) and BatchNorm layers use
+// the fp32 CUDA-core kernels instead of the all-taps tensor-core path
+inline bool taps_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_TAPS");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
+
 struct AdjCsr {
   int *ptr;
   int *yoff;
@@ -173,6 +184,9 @@ struct LayerPrep {
   tc::GcnwTables *gwtab = nullptr, *gwtabr = nullptr;
   __nv_bfloat16 *wsc = nullptr, *wscr = nullptr;
   float *n1V = nullptr, *nrV = nullptr;   // LayerNorm affine as [V][C] (LN warps of the fused stage): weight then bias
+  // "all taps" layer path (temporal convolution as a per-joint-tile GEMM over the taps, kernels_gcnw.cuh tmode 2):
+  // LayerNorm layers whose temporal kernel does not fit the frame-tile kernel (> 15 taps), and BatchNorm layers
+  bool taps = false;
 };
 
 LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws, bool sparse_adj = false) {
@@ -200,6 +214,19 @@ LayerPrep prep_take(const stgcn_layer_desc &d, int K, int V, Bump &ws, bool spar
   if (P.tcn) P.n2T = ws.take<float>((size_t)2 * d.c_out * V);
   P.gw = sparse_adj && P.gcn && tc::gcnw_enabled() && tc::gcnw_supported(d.c_in, d.c_out, V, K) &&
          (d.residual != STGCN_RES_CONV || P.res);
+  const bool bn = d.norm == STGCN_NORM_BATCHNORM;
+  const bool shapes_ok = !d.a_per_sample && d.rt == 0 && sparse_adj && tc::gcnw_enabled() &&
+                         tc::gcnw_supported(d.c_in, d.c_out, V, K) && tc::gcnw_supported(d.c_out, d.c_out, V, 1) &&
+                         d.kernel <= tc::kGwEdgeCap && taps_enabled();
+  P.taps = shapes_ok && ((ln && P.gw && !P.tcn) || bn);
+  if (P.taps) {
+    if (!P.wp16) P.wp16 = ws.take<__nv_bfloat16>((size_t)2 * d.c_out * d.c_out * d.kernel);
+    if (ln && !P.n2T) P.n2T = ws.take<float>((size_t)2 * d.c_out * V);
+    if (bn) {
+      P.bzT = ws.take<float>((size_t)d.c_out * V);
+      P.gw = true;                                   // edge tables + pre-scaled weights below
+    }
+  }
   P.gwr = P.gw && d.residual == STGCN_RES_CONV;
   if (P.gw) {
     const size_t cap = (size_t)tc::gcnw_edge_cap(V);
@@ -229,9 +256,14 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
     tc::k_split_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.gcn_w, P.wg16, nw);
     STGCN_LAUNCH_OK();
   }
-  if (P.tcn) {
+  if (P.tcn || P.taps) {
     const long long nw = (long long)d.c_out * d.c_out * d.kernel;
     tc::k_pack_tcn_w_bf16<<<cdiv(nw, 256), 256, 0, st>>>(d.tcn_w, P.wp16, d.c_out, d.c_out, d.kernel);
+    STGCN_LAUNCH_OK();
+  }
+  if (P.taps && !P.gcn) {                            // BatchNorm layers: the bias that flows through the adjacency
+    tc::k_bias_through_adj<<<cdiv((long long)d.c_out * V, 256), 256, 0, st>>>(d.a_eff, d.gcn_b, K, V, d.c_out,
+                                                                              P.bzT);
     STGCN_LAUNCH_OK();
   }
   if (P.res) {
@@ -248,15 +280,19 @@ int prep_run(const stgcn_layer_desc &d, int K, int V, const LayerPrep &P, cudaSt
     tc::k_gcnw_pack<<<cdiv(per * cap, 256), 256, 0, st>>>(d.gcn_w, P.gwtab, d.c_out, d.c_in, cap, P.wsc);
     STGCN_LAUNCH_OK();
     const int cvv = d.c_out * V;
+    if (d.norm == STGCN_NORM_LAYERNORM) {
     tc::k_transpose_cv<<<cdiv(cvv, 256), 256, 0, st>>>(d.n1_w, P.n1V, d.c_out, V);
     STGCN_LAUNCH_OK();
     tc::k_transpose_cv<<<cdiv(cvv, 256), 256, 0, st>>>(d.n1_b, P.n1V + cvv, d.c_out, V);
     STGCN_LAUNCH_OK();
+    }
     if (P.gwr) {
+      if (d.norm == STGCN_NORM_LAYERNORM) {
       tc::k_transpose_cv<<<cdiv(cvv, 256), 256, 0, st>>>(d.nr_w, P.nrV, d.c_out, V);
       STGCN_LAUNCH_OK();
       tc::k_transpose_cv<<<cdiv(cvv, 256), 256, 0, st>>>(d.nr_b, P.nrV + cvv, d.c_out, V);
       STGCN_LAUNCH_OK();
+      }
       tc::k_gcnw_tables<<<1, 32, 0, st>>>(nullptr, 1, V, 1, cap, P.gwtabr);
       STGCN_LAUNCH_OK();
       tc::k_gcnw_pack<<<cdiv(per * cap, 256), 256, 0, st>>>(d.res_w, P.gwtabr, d.c_out, d.c_in, cap, P.wscr);
@@ -322,6 +358,164 @@ int gcnw_stage(int c_out, const __nv_bfloat16 *xh, const __nv_bfloat16 *wsc, tc:
   return 0;
 }
 
+// ---- "all taps" ST-GCN layer: both stages as per-joint-tile GEMMs (kernels_gcnw.cuh) --------------------
+// The temporal convolution runs as the same GEMM as the graph convolution with the taps as edges (tmode 2),
+// which has no limit on Gamma (the frame-tile kernel k_tcn_tc2p stages a window of FT + Gamma - 1 frames and
+// stops at 15 taps) and writes its accumulators raw, which is what batch-statistics BatchNorm needs (moments
+// over the whole call first, then normalise).  LayerNorm: x planes -> [GEMM -> z -> LN1+ReLU] -> u planes ->
+// [tap GEMM -> q] -> LN2 + residual + ReLU (k_ln_stream).  BatchNorm: the same GEMMs, k_channel_stats +
+// k_bn_apply in between (fp32 rows; rows -> planes conversions before each GEMM).
+int gcnw_taps(int c, const __nv_bfloat16 *u, const __nv_bfloat16 *wp16, const float *bias, float *q, int N, int T,
+              int T_out, int V, int kernel, int stride, int planes, long long plane_stride, cudaStream_t st) {
+  STGCN_REQUIRE(stride == 1 || (stride == 2 && T >= 2), "temporal GEMM: stride must be 1 or 2 (got %d)", stride);
+  tc::GcnwParams g{};
+  g.T = T_out; g.V = V; g.Cin = c; g.planes = planes; g.N = N;
+  g.bias = bias; g.bias_sw = 0;
+  g.out = q;
+  g.tmode = 2; g.ntaps = kernel; g.tpad = (kernel - 1) / 2; g.tstride = stride;
+  ProfScope ps(KC_GEMM_TCN, st);
+  if (tc::launch_gcnw(c, u, wp16, g, T, stride, kernel, plane_stride, st)) return 1;
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+
+int layer_forward_taps(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out, int N, int T,
+                       Bump &ws, cudaStream_t st, const LayerPrep &P, bool x_planes, bool out_planes) {
+  const size_t mark = ws.mark();
+  const bool bn = d.norm == STGCN_NORM_BATCHNORM;
+  const int planes = math == STGCN_MATH_BF16X3 ? 2 : 1;
+  const int T_out = (T - 1) / d.stride + 1;
+  const long long rows = (long long)N * T * V, rows_out = (long long)N * T_out * V;
+  const int co = d.c_out, cap = tc::gcnw_edge_cap(V);
+  STGCN_REQUIRE(!bn || (!x_planes && !out_planes), "BatchNorm layers exchange fp32 rows");
+  // layer input as bf16 planes
+  const __nv_bfloat16 *xh = reinterpret_cast<const __nv_bfloat16 *>(x);
+  if (!x_planes) {
+    __nv_bfloat16 *sc = ws.take<__nv_bfloat16>((size_t)planes * rows * d.c_in);
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer input planes)");
+      const long long tot = rows * d.c_in;
+      ProfScope ps(KC_LAYOUT, st);
+      tc::k_rows_to_planes<<<cdiv(tot, 256), 256, 0, st>>>(x, sc, planes == 2 ? sc + tot : nullptr, tot);
+      STGCN_LAUNCH_OK();
+    }
+    xh = sc;
+  }
+  const __nv_bfloat16 *xl = planes == 2 ? xh + (size_t)rows * d.c_in : nullptr;
+  __nv_bfloat16 *u16 = ws.take<__nv_bfloat16>((size_t)planes * rows * co);
+  __nv_bfloat16 *u16_lo = (planes == 2 && u16) ? u16 + (size_t)rows * co : nullptr;
+  float *q = ws.take<float>((size_t)rows_out * co);
+  const bool res_conv = d.residual == STGCN_RES_CONV;
+  float *resb = res_conv ? ws.take<float>((size_t)rows_out * co) : nullptr;
+  if (!bn) {
+    // ---- LayerNorm ----
+    tc::LnStreamArgs l{};
+    l.frames = (long long)N * T; l.T = T; l.V = V; l.C = co;
+    l.n_wT = P.n1T; l.n_bT = P.n1T + (size_t)co * V;
+    l.relu = 1; l.eps = kEps;
+    l.out_hi = u16; l.out_lo = u16_lo;
+    tc::GcnwParams g{};
+    g.T = T; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
+    g.tab = P.gwtab;
+    g.bias = P.bzT; g.bias_sw = 1;
+    if (gcnw_stage(co, xh, P.wsc, g, l, P.n1V, T, 1, rows * d.c_in, ws, st)) return 1;
+    if (res_conv) {
+      tc::LnStreamArgs lr{};
+      lr.frames = (long long)N * T_out; lr.T = T_out; lr.V = V; lr.C = co;
+      lr.n_wT = P.nrT; lr.n_bT = P.nrT + (size_t)co * V;
+      lr.relu = 0; lr.eps = kEps;
+      lr.out_f32 = resb;
+      tc::GcnwParams gr{};
+      gr.T = T_out; gr.V = V; gr.Cin = d.c_in; gr.planes = planes; gr.N = N;
+      gr.tab = P.gwtabr;
+      gr.bias = d.res_b; gr.bias_sw = 0;
+      if (gcnw_stage(co, xh, P.wscr, gr, lr, P.nrV, T, d.stride, rows * d.c_in, ws, st)) return 1;
+    }
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "workspace too small (layer, all-taps path)");
+      if (gcnw_taps(co, u16, P.wp16, d.tcn_b, q, N, T, T_out, V, d.kernel, d.stride, planes, rows * co, st)) return 1;
+      tc::LnStreamArgs f{};
+      f.frames = (long long)N * T_out; f.T = T_out; f.V = V; f.C = co;
+      f.z = q;
+      f.n_wT = P.n2T; f.n_bT = P.n2T + (size_t)co * V;
+      f.relu = 1; f.eps = kEps;
+      if (d.residual == STGCN_RES_IDENTITY) { f.res_hi = xh; f.res_lo = xl; }
+      else if (res_conv) f.res_f32 = resb;
+      if (out_planes) {
+        f.out_hi = reinterpret_cast<__nv_bfloat16 *>(out);
+        f.out_lo = planes == 2 ? f.out_hi + (size_t)rows_out * co : nullptr;
+      } else {
+        f.out_f32 = out;
+      }
+      ProfScope ps(KC_FRAME, st);
+      if (tc::launch_ln_stream(f, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    ws.release(mark);
+    return 0;
+  }
+  // ---- BatchNorm (batch statistics over the whole call, stgcn.py:152,160,171) ----
+  float *z = ws.take<float>((size_t)rows * co);
+  float *uf = ws.take<float>((size_t)rows * co);
+  double *sums = ws.take<double>((size_t)4 * co);
+  if (!ws.measuring()) {
+    STGCN_REQUIRE(!ws.overflow, "workspace too small (layer, all-taps BatchNorm path)");
+    {
+      tc::GcnwParams g{};
+      g.T = T; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
+      g.tab = P.gwtab;
+      g.bias = P.bzT; g.bias_sw = 1;
+      g.out = z;
+      ProfScope ps(KC_GEMM_1X1, st);
+      if (tc::launch_gcnw(co, xh, P.wsc, g, T, 1, cap, rows * d.c_in, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    if (channel_stats(z, rows, co, sums, st)) return 1;
+    {
+      BnApplyArgs b{};
+      b.a = z; b.a_sum = sums; b.a_sumsq = sums + co; b.a_w = d.n1_w; b.a_b = d.n1_b;
+      b.relu_out = 1; b.rows = rows; b.C = co; b.inv_count = 1.0 / (double)rows; b.eps = kEps;
+      b.out = uf;
+      ProfScope ps(KC_BN, st);
+      k_bn_apply<<<148 * 8, 256, 0, st>>>(b);
+      STGCN_LAUNCH_OK();
+    }
+    {
+      const long long tot = rows * co;
+      ProfScope ps(KC_LAYOUT, st);
+      tc::k_rows_to_planes<<<cdiv(tot, 256), 256, 0, st>>>(uf, u16, u16_lo, tot);
+      STGCN_LAUNCH_OK();
+    }
+    if (res_conv) {
+      tc::GcnwParams g{};
+      g.T = T_out; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = N;
+      g.tab = P.gwtabr;
+      g.bias = d.res_b; g.bias_sw = 0;
+      g.out = resb;
+      ProfScope ps(KC_GEMM_1X1, st);
+      if (tc::launch_gcnw(co, xh, P.wscr, g, T, d.stride, cap, rows * d.c_in, st)) return 1;
+      STGCN_LAUNCH_OK();
+    }
+    if (gcnw_taps(co, u16, P.wp16, d.tcn_b, q, N, T, T_out, V, d.kernel, d.stride, planes, rows * co, st)) return 1;
+    if (channel_stats(q, rows_out, co, sums, st)) return 1;
+    BnApplyArgs b{};
+    b.a = q; b.a_sum = sums; b.a_sumsq = sums + co; b.a_w = d.n2_w; b.a_b = d.n2_b;
+    if (d.residual == STGCN_RES_IDENTITY) { b.b_mode = B_RAW; b.b = x; }
+    else if (res_conv) {
+      if (channel_stats(resb, rows_out, co, sums + 2 * co, st)) return 1;
+      b.b_mode = B_LN; b.b = resb; b.b_sum = sums + 2 * co; b.b_sumsq = sums + 3 * co;
+      b.b_w = d.nr_w; b.b_b = d.nr_b;
+    }
+    b.relu_out = 1; b.rows = rows_out; b.C = co; b.inv_count = 1.0 / (double)rows_out; b.eps = kEps;
+    b.out = out;
+    ProfScope ps(KC_BN, st);
+    k_bn_apply<<<148 * 8, 256, 0, st>>>(b);
+    STGCN_LAUNCH_OK();
+  }
+  ws.release(mark);
+  return 0;
+}
+
 // ---- ST-GCN layer on channels-last activations --------------------------------
 // x [N*T*V, c_in] -> out [N*T_out*V, c_out].  Scratch comes from `ws` (released on return).
 // `pp`: prepared operands (model path) or null (built here, per call).
@@ -346,6 +540,11 @@ int layer_forward_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       if (prep_run(d, K, V, local, st)) return 1;
     }
     pp = &local;
+  }
+  if (math != STGCN_MATH_FP32 && pp && pp->taps && !halo) {
+    const int r = layer_forward_taps(d, K, V, math, x, out, N, T, ws, st, *pp, x_planes, out_planes);
+    ws.release(mark);
+    return r;
   }
   // tensor-core temporal stage: LayerNorm, stride 1/2, C in {64,128,256}
   const bool tc_tcn = math != STGCN_MATH_FP32 && pp && pp->tcn &&
@@ -986,8 +1185,8 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     for (int i = 0; i < m.num_layers; ++i) {
       const stgcn_layer_desc &d = m.layers[i];
       const LayerPrep P = prep_take(d, K, V, pm, (m.reserved & 2) != 0);
-      pl[i] = m.math != STGCN_MATH_FP32 && P.gw && P.tcn &&
-              tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, tt);
+      pl[i] = m.math != STGCN_MATH_FP32 && d.norm == STGCN_NORM_LAYERNORM && P.gw &&
+              ((P.tcn && tc::tcn_tc2_supported(d.c_out, V, d.kernel, d.stride, tt)) || P.taps);
       tt = (tt - 1) / d.stride + 1;
     }
   }
@@ -1431,7 +1630,7 @@ int cost_step(const stgcn_model_desc &m, const float *x, void *state, long long 
       g.T = (int)rows; g.V = 1; g.Cin = d.c_out; g.planes = planes; g.N = 1;
       g.bias = d.tcn_b; g.bias_sw = 0;
       g.out = zq;
-      g.ntaps = d.kernel;
+      g.ntaps = d.kernel; g.tmode = 1;
       for (int j = 0; j < d.kernel; ++j) g.tap_src[j] = (int)((((t - (long long)j * d.stride) % F) + F) % F);
       tc::GcnwXView xv;
       xv.slots = F; xv.slot_stride = slot_n;

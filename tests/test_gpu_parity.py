@@ -691,3 +691,48 @@ def test_rt_fused_step_subprocess(cuda):
                          env=env, capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
     assert ' passed' in out.stdout and 'failed' not in out.stdout, out.stdout[-1000:]
+
+
+# ------------------------------------------------------------------ all-taps layer path (large Gamma, BatchNorm)
+@pytest.mark.parametrize('math,tol', [('bf16x3', TOL), ('bf16', BF16_TOL)])
+def test_stgcn_model_large_temporal_kernel(pkg, syn, cuda, math, tol):
+    """The reference's LayerNorm config uses a 69-tap temporal kernel (config/pku-mmd/ln/stgcn_local.json:26):
+    beyond the 15 taps of the frame-tile kernel, the temporal convolution runs as the per-joint-tile tcgen05 GEMM
+    over the taps (identity, strided / channel-changing and plain layers)."""
+    kw = dict(num_classes=12, kernel=69, in_ch=[64, 64, 128], out_ch=[64, 128, 128], stride=[1, 2, 1])
+    cfg = syn.arch_config('st-gcn', **kw)
+    sd = syn.synth_state_dict(pkg.Stgcn(**cfg).state_dict(), 101)
+    cfg['math'] = math
+    m = pkg.Stgcn(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    x = syn.synth_input((2, 3, 150, 25), 102)
+    l0 = pkg._lib.load().stgcn_launch_count()
+    logits, feats = m(x.to(cuda), return_features=True)
+    rl, rf = O.stgcn_model(x, sd, dict(layers=3, stride=kw['stride'], residual=[1] * 3, normalization='LayerNorm'),
+                           return_features=True)
+    e_l, e_f = rel_err(logits, rl), rel_err(feats, rf)
+    print("kernel 69 math=%s rel_err logits %.3e features %.3e" % (math, e_l, e_f))
+    assert e_l < tol and e_f < tol
+    assert pkg._lib.load().stgcn_launch_count() - l0 < 40       # tensor-core path: a few launches per layer
+
+
+@pytest.mark.parametrize('residual', [[1, 1, 1], [1, 0, 1]])
+def test_stgcn_model_batchnorm_tensor_core(pkg, syn, cuda, residual):
+    """BatchNorm mode (config/pku-mmd/as_is/stgcn_local.json) with the GEMMs on tcgen05: raw accumulators, batch
+    statistics over the whole call, then normalise (two-phase), vs the oracle (batch-statistics BatchNorm)."""
+    kw = dict(num_classes=12, normalization='BatchNorm', in_ch=[64, 64, 128], out_ch=[64, 128, 128], stride=[1, 2, 1],
+              residual=residual)
+    cfg = syn.arch_config('st-gcn', **kw)
+    sd = syn.synth_state_dict(pkg.Stgcn(**cfg).state_dict(), 103)
+    cfg['math'] = 'bf16x3'
+    m = pkg.Stgcn(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    x = syn.synth_input((3, 3, 44, 25), 104)
+    logits, feats = m(x.to(cuda), return_features=True)
+    rl, rf = O.stgcn_model(x, sd, dict(layers=3, stride=kw['stride'], residual=residual, normalization='BatchNorm'),
+                           return_features=True)
+    e_l, e_f = rel_err(logits, rl), rel_err(feats, rf)
+    print("BatchNorm tensor-core path rel_err logits %.3e features %.3e" % (e_l, e_f))
+    assert e_l < TOL and e_f < TOL
