@@ -832,6 +832,68 @@ __global__ void __launch_bounds__(256) k_bn_apply(BnApplyArgs p) {
   }
 }
 
+// Batch-statistics BatchNorm as a per-channel affine: coef[c] = (scale, shift) with scale = w / sqrt(var + eps),
+// shift = b - mean * scale (moments in double), then one float4 streaming pass (tensor-core BatchNorm path).
+__global__ void k_bn_coeffs(const double *__restrict__ sum, const double *__restrict__ sumsq,
+                            const float *__restrict__ w, const float *__restrict__ b, double inv_count, float eps,
+                            int C, float2 *__restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sum[c] * inv_count;
+  double var = sumsq[c] * inv_count - mean * mean;
+  if (var < 0) var = 0;
+  const double sc = (double)w[c] / sqrt(var + (double)eps);
+  coef[c] = make_float2((float)sc, (float)((double)b[c] - mean * sc));
+}
+
+struct BnApply4Args {
+  const float *a;
+  const float2 *a_coef;
+  int b_mode;                 // B_NONE / B_RAW / B_LN (here: BatchNorm of b with b_coef)
+  const float *b;
+  const float2 *b_coef;
+  int relu_out;
+  long long n4;               // rows * C / 4
+  int C;
+  float *out;                 // fp32 rows, and / or
+  __nv_bfloat16 *out_hi, *out_lo;   // bf16 hi / lo planes
+};
+
+__global__ void __launch_bounds__(256) k_bn_apply4(BnApply4Args p) {
+  const int C4 = p.C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const float4 a = *reinterpret_cast<const float4 *>(p.a + 4 * i);
+    const float4 k01 = *reinterpret_cast<const float4 *>(p.a_coef + c), k23 = *reinterpret_cast<const float4 *>(p.a_coef + c + 2);
+    float4 v = make_float4(fmaf(a.x, k01.x, k01.y), fmaf(a.y, k01.z, k01.w), fmaf(a.z, k23.x, k23.y), fmaf(a.w, k23.z, k23.w));
+    if (p.b_mode == B_RAW) {
+      const float4 r = *reinterpret_cast<const float4 *>(p.b + 4 * i);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    } else if (p.b_mode == B_LN) {
+      const float4 r = *reinterpret_cast<const float4 *>(p.b + 4 * i);
+      const float4 q01 = *reinterpret_cast<const float4 *>(p.b_coef + c), q23 = *reinterpret_cast<const float4 *>(p.b_coef + c + 2);
+      v.x += fmaf(r.x, q01.x, q01.y); v.y += fmaf(r.y, q01.z, q01.w);
+      v.z += fmaf(r.z, q23.x, q23.y); v.w += fmaf(r.w, q23.z, q23.w);
+    }
+    if (p.relu_out) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    if (p.out) *reinterpret_cast<float4 *>(p.out + 4 * i) = v;
+    if (p.out_hi) {
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+      *reinterpret_cast<uint2 *>(p.out_hi + 4 * i) =
+          make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+      if (p.out_lo) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+        *reinterpret_cast<uint2 *>(p.out_lo + 4 * i) =
+            make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+      }
+    }
+  }
+}
+
 // --------------------------------------------------------------------------- //
 // input stage: norm_in + fcn_in (stgcn.py:82-85).  x is [frames, V, C_in] (NTVC).
 //   LN mode: per-frame LayerNorm over (C_in, V), affine (C_in, V)

@@ -456,8 +456,8 @@ int layer_forward_taps(const stgcn_layer_desc &d, int K, int V, int math, const 
   }
   // ---- BatchNorm (batch statistics over the whole call, stgcn.py:152,160,171) ----
   float *z = ws.take<float>((size_t)rows * co);
-  float *uf = ws.take<float>((size_t)rows * co);
   double *sums = ws.take<double>((size_t)4 * co);
+  float2 *coef = ws.take<float2>((size_t)2 * co);
   if (!ws.measuring()) {
     STGCN_REQUIRE(!ws.overflow, "workspace too small (layer, all-taps BatchNorm path)");
     {
@@ -472,18 +472,13 @@ int layer_forward_taps(const stgcn_layer_desc &d, int K, int V, int math, const 
     }
     if (channel_stats(z, rows, co, sums, st)) return 1;
     {
-      BnApplyArgs b{};
-      b.a = z; b.a_sum = sums; b.a_sumsq = sums + co; b.a_w = d.n1_w; b.a_b = d.n1_b;
-      b.relu_out = 1; b.rows = rows; b.C = co; b.inv_count = 1.0 / (double)rows; b.eps = kEps;
-      b.out = uf;
       ProfScope ps(KC_BN, st);
-      k_bn_apply<<<148 * 8, 256, 0, st>>>(b);
+      k_bn_coeffs<<<cdiv(co, 128), 128, 0, st>>>(sums, sums + co, d.n1_w, d.n1_b, 1.0 / (double)rows, kEps, co, coef);
       STGCN_LAUNCH_OK();
-    }
-    {
-      const long long tot = rows * co;
-      ProfScope ps(KC_LAYOUT, st);
-      tc::k_rows_to_planes<<<cdiv(tot, 256), 256, 0, st>>>(uf, u16, u16_lo, tot);
+      BnApply4Args b{};
+      b.a = z; b.a_coef = coef; b.relu_out = 1; b.n4 = rows * co / 4; b.C = co;
+      b.out_hi = u16; b.out_lo = u16_lo;                     // relu(BN1(z)) straight into the temporal GEMM's operand planes
+      k_bn_apply4<<<148 * 8, 256, 0, st>>>(b);
       STGCN_LAUNCH_OK();
     }
     if (res_conv) {
@@ -498,18 +493,22 @@ int layer_forward_taps(const stgcn_layer_desc &d, int K, int V, int math, const 
     }
     if (gcnw_taps(co, u16, P.wp16, d.tcn_b, q, N, T, T_out, V, d.kernel, d.stride, planes, rows * co, st)) return 1;
     if (channel_stats(q, rows_out, co, sums, st)) return 1;
-    BnApplyArgs b{};
-    b.a = q; b.a_sum = sums; b.a_sumsq = sums + co; b.a_w = d.n2_w; b.a_b = d.n2_b;
+    if (res_conv && channel_stats(resb, rows_out, co, sums + 2 * co, st)) return 1;
+    ProfScope ps(KC_BN, st);
+    k_bn_coeffs<<<cdiv(co, 128), 128, 0, st>>>(sums, sums + co, d.n2_w, d.n2_b, 1.0 / (double)rows_out, kEps, co, coef);
+    STGCN_LAUNCH_OK();
+    BnApply4Args b{};
+    b.a = q; b.a_coef = coef;
     if (d.residual == STGCN_RES_IDENTITY) { b.b_mode = B_RAW; b.b = x; }
     else if (res_conv) {
-      if (channel_stats(resb, rows_out, co, sums + 2 * co, st)) return 1;
-      b.b_mode = B_LN; b.b = resb; b.b_sum = sums + 2 * co; b.b_sumsq = sums + 3 * co;
-      b.b_w = d.nr_w; b.b_b = d.nr_b;
+      k_bn_coeffs<<<cdiv(co, 128), 128, 0, st>>>(sums + 2 * co, sums + 3 * co, d.nr_w, d.nr_b, 1.0 / (double)rows_out,
+                                                kEps, co, coef + co);
+      STGCN_LAUNCH_OK();
+      b.b_mode = B_LN; b.b = resb; b.b_coef = coef + co;
     }
-    b.relu_out = 1; b.rows = rows_out; b.C = co; b.inv_count = 1.0 / (double)rows_out; b.eps = kEps;
+    b.relu_out = 1; b.n4 = rows_out * co / 4; b.C = co;
     b.out = out;
-    ProfScope ps(KC_BN, st);
-    k_bn_apply<<<148 * 8, 256, 0, st>>>(b);
+    k_bn_apply4<<<148 * 8, 256, 0, st>>>(b);
     STGCN_LAUNCH_OK();
   }
   ws.release(mark);
