@@ -125,6 +125,7 @@ struct GcnwParams {
   const float *bias;            // bias_sw = 1: [C/4][V][4] table, 0: [C] vector, null: none
   int bias_sw;
   float *out;                   // z fp32 rows [(n*T + t)*V + w][CO]
+  int tma_out;                  // rows leave through TMA stores (tm_z) instead of st.global from the patch
   int debug;
   // tap mode (CoST-GCN temporal convolution over a ring of frames, ntaps > 0): V == 1, the "edges" of the
   // single joint are the taps, "source joint" of tap j = ring slot tap_src[j]; tab is not used
@@ -165,6 +166,17 @@ __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
 }
 // L2 eviction priorities of the fused stage: the z ring must stay resident (written, read once ~10 us later,
 // overwritten in place a few hundred us later) while ~4x as many bytes stream through L2 once (x in, u out)
+// TMA store of a [32 rows][128 B] SWIZZLE_128B shared-memory box into a 4-D fp32 tensor (bulk async-group)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -224,7 +236,7 @@ constexpr int kGwThreads = 32 * (3 + 4 * kEpiNH);   // 0 A producer, 1 MMA, 2 B 
 template <int CO, bool MERGE, bool FUSE>
 __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), FUSE ? 1 : 2)
     k_gcnw(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x1,
-           const __grid_constant__ CUtensorMap tm_w, const GcnwParams p) {
+           const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_z, const GcnwParams p) {
   constexpr int kAPlane = 128 * 128;            // [128 frames][64 ch] bf16
   constexpr int kBPlane = CO * 128;             // [CO][64 ch] bf16
   constexpr int kABytes = MERGE ? 2 * kAPlane : kAPlane;
@@ -263,6 +275,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_x1);
     tma_prefetch_desc(&tm_w);
+    if (p.tma_out) tma_prefetch_desc(&tm_z);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bTmemFull + 8 * i, 1);
       mbar_init(bTmemEmpty + 8 * i, 4 * kEpiNH);
@@ -444,6 +457,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
     const int c0 = h * CH;
     uint8_t *patch = s_patch + (warp - 3) * kPatchBytes;
     uint8_t *mine = patch + lane * kPatchPitch;
+    uint8_t *tpatch = s_patch + (warp - 3) * 4096;           // TMA-store form: [32 rows][128 B], 1024-B aligned
     int buf = 0, t_ph = 0, tile_k = 0;
     const uint64_t pol_keep = FUSE ? l2_policy_evict_last() : 0ull;
     float v[16];
@@ -496,8 +510,24 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
               s1 += (d0 + d1) + (d2 + d3);
               s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
             }
-            *reinterpret_cast<float4 *>(mine + half * 64 + i * 16) = o;
+            if (!FUSE && p.tma_out)      // SWIZZLE_128B box row: 16-B chunk j of row r sits at chunk j ^ (r & 7)
+              *reinterpret_cast<float4 *>(tpatch + lane * 128 + (((half * 4 + i) ^ (lane & 7)) << 4)) = o;
+            else
+              *reinterpret_cast<float4 *>(mine + half * 64 + i * 16) = o;
           }
+        }
+        if (!FUSE && p.tma_out) {
+          // the box [32 frames][32 channels] of this joint goes out as ONE TMA store (rows past the end of the
+          // trial are clipped by the tensor map); the patch is reused once the store has read it
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tm_z, smem_u32(tpatch), c0 + sb, w, tb * 128 + q * 32, n);
+            bulk_commit();
+            bulk_wait_read0();
+          }
+          __syncwarp();
+          continue;
         }
         __syncwarp();
 #pragma unroll
@@ -534,6 +564,7 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
       buf ^= 1;
       if (buf == 0) t_ph ^= 1;
     }
+    if (!FUSE && p.tma_out && lane == 0) bulk_wait0();        // all stores of this warp have left shared memory and landed
   } else if (FUSE && warp == 3 + 4 * kEpiNH) {
     // ---- publisher: tiles whose eight epilogue warps have arrived become visible to the other CTAs ----
     // (bar.sync-style cumulativity: the epilogue's stores happen-before its CTA-scope arrive, the fence
@@ -814,6 +845,15 @@ inline bool gcnw_enabled() {
 // The one-kernel form of the stage is opt-in (STGCN_GCNW_FUSE=1): it removes z's HBM round trip (measured:
 // 1.64 GB instead of 3.2 GB of DRAM traffic per C = 64 launch pair) but the cross-CTA ring couples the
 // progress of all CTAs, and on B200 it runs 1.7x slower than GEMM + k_ln_stream
+// STGCN_GCNW_TMA_OUT=0: the GEMM's rows leave with st.global from the warp's patch instead of TMA stores
+inline bool gcnw_tma_out_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_GCNW_TMA_OUT");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
 inline bool gcnw_fuse_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -902,15 +942,23 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
   const uint64_t wst[3] = {(uint64_t)p.Cin * 2, (uint64_t)CO * p.Cin * 2, (uint64_t)cap * CO * p.Cin * 2};
   const uint32_t wb[4] = {64, (uint32_t)CO, 1, 1};
   if (make_tmap_bf16(&tm_w, wsc, 4, wd, wst, wb)) return 1;
+  CUtensorMap tm_z = tm_w;
+  p.tma_out = (!FUSE && gcnw_tma_out_enabled()) ? 1 : 0;
+  if (p.tma_out) {
+    const uint64_t zd[4] = {(uint64_t)CO, (uint64_t)V, (uint64_t)p.T, (uint64_t)p.N};
+    const uint64_t zs[3] = {(uint64_t)CO * 4, (uint64_t)V * CO * 4, (uint64_t)p.T * V * CO * 4};
+    const uint32_t zb[4] = {32, 1, 32, 1};
+    if (make_tmap(&tm_z, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, p.out, 4, zd, zs, zb)) return 1;
+  }
   const int grid = p.items < num_sms() ? p.items : num_sms();
   STGCN_CUDA_OK(cudaFuncSetAttribute(k_gcnw<CO, MERGE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   if (FUSE) {
     // producers wait for consumers in other CTAs: every CTA must be resident -> cooperative launch
-    void *args[4] = {&tm_x, &tm_x1, &tm_w, &p};
+    void *args[5] = {&tm_x, &tm_x1, &tm_w, &tm_z, &p};
     STGCN_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_gcnw<CO, MERGE, FUSE>), dim3(grid),
                                               dim3(kGwThreads + 32 + kGwLnThreads), args, (size_t)smem, st));
   } else {
-    k_gcnw<CO, MERGE, FUSE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_x1, tm_w, p);
+    k_gcnw<CO, MERGE, FUSE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_x1, tm_w, tm_z, p);
   }
   return 0;
 }
