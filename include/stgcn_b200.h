@@ -208,6 +208,11 @@ size_t rtstgcn_step_workspace_bytes(const stgcn_model_desc *m, int B);
 /* One frame for every stream: x (B,in_feat,1,V) -> logits (B,num_classes). */
 int rtstgcn_step(const stgcn_model_desc *m, const float *x, void *state, float *logits, int B,
                  void *workspace, size_t workspace_bytes, void *stream);
+/* The same step, and top5 (B, 5) int32 = indices of the five largest logits of every stream, best
+ * first: what the reference's Statistics computes with torch.topk(predictions, 5, dim=1)
+ * (utils/statistics.py:4-16), produced by the kernel that produces the logits. */
+int rtstgcn_step_top5(const stgcn_model_desc *m, const float *x, void *state, float *logits, int32_t *top5,
+                      int B, void *workspace, size_t workspace_bytes, void *stream);
 /* One OnlineLayer.forward on x (B,c_in,1,V) -> y (B,c_out,1,V); layer_state is the
  * slice for this layer laid out as rtstgcn_layer_state_bytes describes. */
 size_t rtstgcn_layer_state_bytes(const stgcn_layer_desc *d, int V, int B);

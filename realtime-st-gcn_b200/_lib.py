@@ -75,6 +75,8 @@ SYMBOLS = {
     'rtstgcn_state_reset': (c_int, [_P_MODEL, c_void_p, c_int, c_int, c_int, c_void_p]),
     'rtstgcn_step_workspace_bytes': (c_size_t, [_P_MODEL, c_int]),
     'rtstgcn_step': (c_int, [_P_MODEL, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    'rtstgcn_step_top5': (c_int, [_P_MODEL, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                          c_void_p]),
     'rtstgcn_layer_state_bytes': (c_size_t, [_P_LAYER, c_int, c_int]),
     'rtstgcn_layer_workspace_bytes': (c_size_t, [_P_LAYER, c_int, c_int, c_int]),
     'rtstgcn_layer_step': (c_int, [_P_LAYER, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -692,10 +692,14 @@ inline bool rt_update_supported(int V, int C) { return C % 4 == 0 && (V * C / 4 
 // x [B*V, C] fp32 rows -> logits [B, classes]
 // --------------------------------------------------------------------------- //
 constexpr int kRtHeadStreams = 8;
+// top5 (optional, [B][5] int32): indices of the five largest logits of every stream, best first -- the
+// reference's Statistics (utils/statistics.py:4-16: torch.topk(predictions, 5, dim=1)) computed where the
+// logits are produced, so an evaluation loop needs only 20 bytes per stream-frame from the device
 __global__ void __launch_bounds__(256)
     k_rt_head(const float *__restrict__ x, int B, int V, int C, const float *__restrict__ W,
-              const float *__restrict__ bias, int classes, float *__restrict__ logits) {
-  extern __shared__ float s_pool[];                       // [kRtHeadStreams][C]
+              const float *__restrict__ bias, int classes, float *__restrict__ logits, int *__restrict__ top5) {
+  extern __shared__ float s_pool[];                       // [kRtHeadStreams][C] (+ [kRtHeadStreams][classes] with top5)
+  float *s_log = s_pool + kRtHeadStreams * C;
   const int b0 = blockIdx.x * kRtHeadStreams;
   const int nb = B - b0 < kRtHeadStreams ? B - b0 : kRtHeadStreams;
   const float inv_v = 1.f / (float)V;
@@ -737,7 +741,63 @@ __global__ void __launch_bounds__(256)
     for (int c = lane; c < C; c += 32) a = fmaf(__ldg(W + (long long)m * C + c), s_pool[s * C + c], a);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) logits[(long long)(b0 + s) * classes + m] = a + __ldg(bias + m);
+    if (lane == 0) {
+      a += __ldg(bias + m);
+      logits[(long long)(b0 + s) * classes + m] = a;
+      if (top5) s_log[s * classes + m] = a;
+    }
+  }
+  if (!top5) return;
+  __syncthreads();
+  // one warp per stream: five rounds of warp arg-max over the classes
+  for (int s = warp; s < nb; s += 8) {
+    float *row = s_log + s * classes;
+    for (int r = 0; r < 5; ++r) {
+      float best = -3.402823466e38f;
+      int bi = 0x7fffffff;
+      for (int m = lane; m < classes; m += 32) {
+        const float v = row[m];
+        if (v > best || (v == best && m < bi)) { best = v; bi = m; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        top5[(long long)(b0 + s) * 5 + r] = r < classes ? bi : -1;
+        if (bi < classes) row[bi] = -3.402823466e38f;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// indices of the five largest of `classes` logits per row (one warp per row; best first, ties to the lower index)
+__global__ void __launch_bounds__(256) k_topk5(const float *__restrict__ logits, int rows, int classes, int *__restrict__ top5) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float *lp = logits + (long long)row * classes;
+  int taken[5] = {-1, -1, -1, -1, -1};
+  for (int r = 0; r < 5; ++r) {
+    float best = -3.402823466e38f;
+    int bi = 0x7fffffff;
+    for (int m = lane; m < classes; m += 32) {
+      bool used = false;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) used |= (taken[j] == m);
+      const float v = lp[m];
+      if (!used && (v > best || (v == best && m < bi))) { best = v; bi = m; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    taken[r] = bi;
+    if (lane == 0) top5[(long long)row * 5 + r] = bi < classes ? bi : -1;
   }
 }
 

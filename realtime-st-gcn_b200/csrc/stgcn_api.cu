@@ -1342,7 +1342,7 @@ bool rt_fifo_bf16(const stgcn_model_desc &m, int B) {
 }
 
 int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logits, int B, Bump &ws,
-            cudaStream_t st) {
+            cudaStream_t st, int *top5 = nullptr) {
   const int V = m.num_joints, K = m.partitions;
   STGCN_REQUIRE(m.norm == STGCN_NORM_LAYERNORM,
                 "continual inference needs LayerNorm (reference raises at models/utils/batchnorm.py:20)");
@@ -1457,8 +1457,8 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
   const int c_last = m.layers[m.num_layers - 1].c_out;
   if (!ws.measuring()) {
     ProfScope ps(KC_POOL, st);
-    k_rt_head<<<cdiv(B, kRtHeadStreams), 256, sizeof(float) * kRtHeadStreams * c_last, st>>>(
-        buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits);
+    k_rt_head<<<cdiv(B, kRtHeadStreams), 256, sizeof(float) * kRtHeadStreams * (c_last + m.num_classes), st>>>(
+        buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, top5);
     STGCN_LAUNCH_OK();
   }
   if (!ws.measuring()) {
@@ -1663,8 +1663,8 @@ int cost_step(const stgcn_model_desc &m, const float *x, void *state, long long 
   }
   const int c_last = m.layers[m.num_layers - 1].c_out;
   ProfScope ps(KC_POOL, st);
-  k_rt_head<<<cdiv(B, kRtHeadStreams), 256, sizeof(float) * kRtHeadStreams * c_last, st>>>(
-      last, B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits);
+  k_rt_head<<<cdiv(B, kRtHeadStreams), 256, sizeof(float) * kRtHeadStreams * (c_last + m.num_classes), st>>>(
+      last, B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, nullptr);
   STGCN_LAUNCH_OK();
   return 0;
 }
@@ -2019,6 +2019,22 @@ int rtstgcn_step(const stgcn_model_desc *m, const float *x, void *state, float *
   STGCN_REQUIRE(state && workspace && B > 0, "rtstgcn_step: null state/workspace or empty batch");
   Bump ws(workspace, workspace_bytes);
   return rt_step(*m, x, state, logits, B, ws, as_stream(stream));
+}
+
+int rtstgcn_step_top5(const stgcn_model_desc *m, const float *x, void *state, float *logits, int32_t *top5, int B,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+  if (check_model(m)) return 1;
+  STGCN_REQUIRE(state && workspace && top5 && B > 0, "rtstgcn_step_top5: null state/workspace/top5 or empty batch");
+  STGCN_REQUIRE(m->num_classes <= 4096, "rtstgcn_step_top5: too many classes");
+  Bump ws(workspace, workspace_bytes);
+  if (rt_small_supported(*m, B)) {
+    // the one-cluster-kernel latency path writes logits only: rank them with the same routine afterwards
+    if (rt_step(*m, x, state, logits, B, ws, as_stream(stream))) return 1;
+    k_topk5<<<cdiv(B, 8), 256, 0, as_stream(stream)>>>(logits, B, m->num_classes, top5);
+    STGCN_LAUNCH_OK();
+    return 0;
+  }
+  return rt_step(*m, x, state, logits, B, ws, as_stream(stream), top5);
 }
 
 size_t rtstgcn_layer_state_bytes(const stgcn_layer_desc *d, int V, int B) {

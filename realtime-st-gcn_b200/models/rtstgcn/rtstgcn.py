@@ -153,13 +153,31 @@ class Model(nn.Module):
             ctypes.byref(m), _lib.ptr(self._state), self._state_streams, first, count,
             _lib.stream_ptr(self._state.device)))
 
-    def _launch_step(self, frame, logits, b, dev):
+    def _launch_step(self, frame, logits, b, dev, top5=None):
         lib = _lib.load()
         m, _ = self._descriptor()
         state = self._ensure_state(b, dev)
         ws = self._ws.get(lib.rtstgcn_step_workspace_bytes(ctypes.byref(m), b), dev)
+        if top5 is not None:
+            _lib.check(lib.rtstgcn_step_top5(ctypes.byref(m), _lib.ptr(frame), _lib.ptr(state), _lib.ptr(logits),
+                                             _lib.ptr(top5), b, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+            return
         _lib.check(lib.rtstgcn_step(ctypes.byref(m), _lib.ptr(frame), _lib.ptr(state), _lib.ptr(logits), b,
                                     _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+
+    @torch.no_grad()
+    def step_top5(self, frame):
+        """One continual step that also ranks the classes on the device: returns ``(logits (B, classes, 1),
+        top5 (B, 5) int32)`` -- ``Statistics`` (utils/statistics.py:4-16) without a separate top-k pass."""
+        b, c, l, v = frame.shape
+        if l != 1:
+            raise RuntimeError("step_top5() takes exactly one frame per stream")
+        frame = frame.contiguous()
+        dev = _lib.require_cuda(frame, self.A, self.fcn_in.weight)
+        logits = torch.empty((b, self.num_classes), device=dev, dtype=torch.float32)
+        top5 = torch.empty((b, 5), device=dev, dtype=torch.int32)
+        self._launch_step(frame, logits, b, dev, top5)
+        return logits.unsqueeze(-1), top5
 
     @torch.no_grad()
     def step(self, frame):

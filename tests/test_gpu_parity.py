@@ -734,3 +734,15 @@ def test_stgcn_model_batchnorm_tensor_core(pkg, syn, cuda, residual):
     e_l, e_f = rel_err(logits, rl), rel_err(feats, rf)
     print("BatchNorm tensor-core path rel_err logits %.3e features %.3e" % (e_l, e_f))
     assert e_l < TOL and e_f < TOL
+
+
+def test_rt_step_top5_matches_topk(pkg, syn, cuda):
+    """Top-5 ranked in the logits kernel (batched path) / right after the cluster kernel (latency path) equals
+    torch.topk of the logits -- the reference's Statistics (utils/statistics.py:4-16)."""
+    for b in (3, 40):
+        m, x, _ = _rt_case(pkg, syn, cuda, 'pku', 'bf16x3')
+        frames = torch.randn(6, b, 3, 1, 25, device=cuda)
+        for t in range(6):
+            logits, top5 = m.step_top5(frames[t])
+        ref = torch.topk(logits.squeeze(-1), 5, dim=1).indices
+        assert torch.equal(top5.long(), ref)
