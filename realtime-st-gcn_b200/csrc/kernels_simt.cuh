@@ -692,16 +692,19 @@ inline bool rt_update_supported(int V, int C) { return C % 4 == 0 && (V * C / 4 
 // x [B*V, C] fp32 rows -> logits [B, classes]
 // --------------------------------------------------------------------------- //
 constexpr int kRtHeadStreams = 8;
+// streams per block: enough blocks to fill the GPU at small batches, W reuse at large ones
+inline int rt_head_streams(int B) { return B >= 2048 ? kRtHeadStreams : (B >= 512 ? 4 : (B >= 128 ? 2 : 1)); }
 // top5 (optional, [B][5] int32): indices of the five largest logits of every stream, best first -- the
 // reference's Statistics (utils/statistics.py:4-16: torch.topk(predictions, 5, dim=1)) computed where the
 // logits are produced, so an evaluation loop needs only 20 bytes per stream-frame from the device
 __global__ void __launch_bounds__(256)
     k_rt_head(const float *__restrict__ x, int B, int V, int C, const float *__restrict__ W,
-              const float *__restrict__ bias, int classes, float *__restrict__ logits, int *__restrict__ top5) {
-  extern __shared__ float s_pool[];                       // [kRtHeadStreams][C] (+ [kRtHeadStreams][classes] with top5)
-  float *s_log = s_pool + kRtHeadStreams * C;
-  const int b0 = blockIdx.x * kRtHeadStreams;
-  const int nb = B - b0 < kRtHeadStreams ? B - b0 : kRtHeadStreams;
+              const float *__restrict__ bias, int classes, float *__restrict__ logits, int *__restrict__ top5,
+              int spb) {
+  extern __shared__ float s_pool[];                       // [spb][C] + [spb][classes]; spb streams per block
+  float *s_log = s_pool + spb * C;
+  const int b0 = blockIdx.x * spb;
+  const int nb = B - b0 < spb ? B - b0 : spb;
   const float inv_v = 1.f / (float)V;
   // pooling: float4 lanes over the channels, 256 / (C/4) streams in parallel, all V loads of a stream in flight
   const int C4 = C >> 2;

@@ -1457,8 +1457,9 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
   const int c_last = m.layers[m.num_layers - 1].c_out;
   if (!ws.measuring()) {
     ProfScope ps(KC_POOL, st);
-    k_rt_head<<<cdiv(B, kRtHeadStreams), 256, sizeof(float) * kRtHeadStreams * (c_last + m.num_classes), st>>>(
-        buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, top5);
+    const int spb = rt_head_streams(B);
+    k_rt_head<<<cdiv(B, spb), 256, sizeof(float) * spb * (c_last + m.num_classes), st>>>(
+        buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, top5, spb);
     STGCN_LAUNCH_OK();
   }
   if (!ws.measuring()) {
@@ -1663,8 +1664,9 @@ int cost_step(const stgcn_model_desc &m, const float *x, void *state, long long 
   }
   const int c_last = m.layers[m.num_layers - 1].c_out;
   ProfScope ps(KC_POOL, st);
-  k_rt_head<<<cdiv(B, kRtHeadStreams), 256, sizeof(float) * kRtHeadStreams * (c_last + m.num_classes), st>>>(
-      last, B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, nullptr);
+  const int spb = rt_head_streams(B);
+  k_rt_head<<<cdiv(B, spb), 256, sizeof(float) * spb * (c_last + m.num_classes), st>>>(
+      last, B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, nullptr, spb);
   STGCN_LAUNCH_OK();
   return 0;
 }
