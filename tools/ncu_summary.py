@@ -28,7 +28,11 @@ SCALE = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 
 
 
 def rows_of(rep):
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the `ncu -i rep --page raw --csv` dump of one (written on the GPU box when the report itself is too large to bring back)
+    if rep.endswith('.csv'):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     res = []
