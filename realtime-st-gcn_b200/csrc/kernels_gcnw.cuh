@@ -21,9 +21,11 @@
 // to HBM and back, and the HBM-bound normalisation overlaps the MMA-bound GEMM on the same SMs.
 // Producers only ever wait for consumers of EARLIER groups and consumers never wait for producers of
 // later ones, so the schedule cannot deadlock as long as all CTAs are resident (cooperative launch).
-// Measured on B200 (32 trials x T = 4000, parity mode): 17.0 ms for the stage against 9.9 ms for the two
-// kernels -- z does stay in L2 (with the L2 eviction-priority hints below), but the ring couples the
-// progress of all CTAs (throughput = ring slots / loop latency, ~55 us measured) -- so it is not the default.
+// Measured on B200 (32 trials x T = 4000, parity mode): 12.3 ms for the stage (64 MB ring, 4-step LN items;
+// 17-48 ms with smaller rings / larger items) against 9.9 ms for the two kernels -- z does stay in L2 (with
+// the L2 eviction-priority hints below: 1.64 GB of DRAM traffic per C = 64 launch instead of 3.2 GB), but
+// the ring couples the progress of all CTAs (throughput = ring slots / loop latency, ~55 us measured with
+// statically assigned tiles) -- so it is not the default.
 // Tree-structured adjacency only: the weight buffer holds 6*V edges.
 #pragma once
 #include "kernels_tc.cuh"
@@ -224,7 +226,7 @@ __device__ __forceinline__ void wait_flag(const unsigned *p, unsigned target, un
 constexpr int kGwLnThreads = 256;     // LN warps of the fused stage
 constexpr int kGwLnFrames = 8;        // frames per LN work item (one warp)
 constexpr int kGwLnBlocks = 128 / kGwLnFrames;  // frame blocks per group; x npc position chunks = LN items per group
-constexpr int kGwLnIters = 7;         // at most this many 32-position steps per item (bounds an item's latency, and
+constexpr int kGwLnIters = 4;         // at most this many 32-position steps per item (bounds an item's latency, and
                                       // with it the number of groups the ring must hold)
 constexpr int kGwPubRing = 4;         // tiles the epilogue may run ahead of the publisher warp
 
@@ -984,14 +986,14 @@ inline bool gcnw_fuse_enabled() {
   return on != 0;
 }
 // ring geometry of the fused stage: slots of [128 frames][V][CO] fp32.  The ring must hold the groups
-// the GEMM side produces during one LN item's latency (~15 us: up to ~45 groups for C = 64, ~10 for
-// C = 256) and stay L2-resident: ~48 MB, 8..64 slots
+// the GEMM side produces during one trip round the produce -> normalise -> release loop and still stay
+// L2-resident (eviction-priority hints): 64 MB / 6..64 slots measured best (sweep in profiles/)
 inline int gcnw_env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e && atoi(e) > 0 ? atoi(e) : dflt;
 }
 inline int gcnw_ring_slots(int V, int CO) {
-  static const int mb = gcnw_env_int("STGCN_GCNW_RING_MB", 24);       // tuning aid
+  static const int mb = gcnw_env_int("STGCN_GCNW_RING_MB", 64);       // tuning aid
   const size_t slot = (size_t)128 * V * CO * sizeof(float);
   int R = (int)((size_t)mb * 1024 * 1024 / slot);
   return R > 64 ? 64 : (R < 6 ? 6 : R);

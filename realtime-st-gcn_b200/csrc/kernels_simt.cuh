@@ -738,16 +738,30 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int pair = warp; pair < nb * classes; pair += 8) {
-    const int m = pair / nb, s = pair - m * nb;             // the warps of a block share a W row (L1 hit)
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(W + (long long)m * C + c), s_pool[s * C + c], a);
+  // a warp takes a class: its W row is read once (C/32 values per lane, C <= 512 in registers) and applied to
+  // every stream of the block
+  for (int m = warp; m < classes; m += 8) {
+    float wr[16];
+    const bool in_regs = C <= 512;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
-      a += __ldg(bias + m);
-      logits[(long long)(b0 + s) * classes + m] = a;
-      if (top5) s_log[s * classes + m] = a;
+    for (int j = 0; j < 16; ++j) wr[j] = (in_regs && lane + 32 * j < C) ? __ldg(W + (long long)m * C + lane + 32 * j) : 0.f;
+    const float bm = __ldg(bias + m);
+    for (int s = 0; s < nb; ++s) {
+      float a = 0.f;
+      if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (lane + 32 * j < C) a = fmaf(wr[j], s_pool[s * C + lane + 32 * j], a);
+      } else {
+        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(W + (long long)m * C + c), s_pool[s * C + c], a);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) {
+        a += bm;
+        logits[(long long)(b0 + s) * classes + m] = a;
+        if (top5) s_log[s * classes + m] = a;
+      }
     }
   }
   if (!top5) return;
