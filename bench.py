@@ -12,6 +12,7 @@ trial-sharded, no collective => weak scaling).  One step = one forward over the 
   parity        logits of the timed run (first and last trial of the batch) against the CPU oracle
   cpu_baseline  oracle on the host cores (N=1 only), on one trial of the workload
   c1            BASELINE config 1 (N=1, T=300) on the GPU and on the host cores
+  windows       sliding-window inference of one 4000-frame trial (receptive_field 50)
   rt            RT-ST-GCN continual p50 step latency at 1 and 4096 streams (configs 2 and 5), with the
                 oracle's continual loop timed beside it and the host-buffer (e2e) step; CoST-GCN step
   long_trial    N=1: the T=262144 trial of config 4 on one GPU
@@ -606,6 +607,25 @@ def main():
               "gpu_frames_per_s": 300 / (g50 * 1e-3), "cpu_p50_ms": c50, "cpu_frames_per_s": 300 / (c50 * 1e-3),
               "cpu_cores": os.cpu_count() or 1, "cpu_kind": "port", "rel_err_vs_cpu": rel_err(o1, r1)}
 
+    # ---- sliding-window inference of one trial (W = the reference configs' receptive_field) ----
+    windows = None
+    if rank == 0 and world == 1 and not args.no_long and args.norm == 'LayerNorm' and args.math != 'fp32':
+        Lw, Ww = 4000, 50
+        capw = syn.synth_input((1, 3, Lw, V), 4322).to(dev)
+        for _ in range(2):
+            model.forward_windows(capw, Ww)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in evs:
+            a.record()
+            model.forward_windows(capw, Ww)
+            b.record()
+        torch.cuda.synchronize()
+        w50 = _p50([a.elapsed_time(b) for a, b in evs])[0]
+        windows = {"workload": "ST-GCN sliding windows, one trial L=%d, receptive_field=%d (config/pku-mmd/ln/stgcn_local.json), "
+                               "windows read in place, first layer's per-frame work shared" % (Lw, Ww),
+                   "p50_ms": w50, "windows_per_s": Lw / (w50 * 1e-3), "window_frames_per_s": Lw * Ww / (w50 * 1e-3)}
+
     rt = None
     if rank == 0 and world == 1 and not args.no_rt:
         imu = dict(graph='imu_fogit_ABCD', in_feat=6, num_classes=8)
@@ -644,7 +664,7 @@ def main():
             "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3(f32-parity)", "bf16": "bf16"}[args.math],
             "data": "synthetic", "config": workload_config(args, N, T),
             "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "parity": parity, "cpu_baseline": cpu,
-            "c1": c1, "rt": rt, "bf16_mode": bf16_leg, "clocks": clocks.summary(),
+            "c1": c1, "windows": windows, "rt": rt, "bf16_mode": bf16_leg, "clocks": clocks.summary(),
         }
         if world == 1:
             line["long_trial"] = tsplit

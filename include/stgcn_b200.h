@@ -99,12 +99,15 @@ int stgcn_abi_version(void);
 const char *stgcn_last_error(void);
 /* 0 if `device` is an sm_100 GPU this build can run on. */
 int stgcn_device_check(int device);
-/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+/* Number of kernels this library has launched in this process, all devices and threads
+ * (bench.py's gpu_launches). */
 long long stgcn_launch_count(void);
 /* Measurement aid: between begin/end every kernel launch is bracketed by CUDA events on its
  * stream; end() synchronises and returns summed milliseconds and launch counts per kernel class:
  * 0 layout, 1 gemm_1x1, 2 gemm_tcn, 3 frame(adjacency/norm/residual), 4 batchnorm, 5 embed,
- * 6 pool+classifier, 7 misc.  Not re-entrant; single device. */
+ * 6 pool+classifier, 7 misc.  State is per DEVICE (the calling thread's current device): a process that
+ * runs one replica thread per GPU profiles each device independently; launches from several threads onto
+ * one device are collected under a lock. */
 #define STGCN_KERNEL_CLASSES 8
 int stgcn_profile_begin(void);
 int stgcn_profile_end(float *ms_per_class_host, long long *launches_per_class_host, int n_classes);
@@ -234,7 +237,10 @@ int stgcn_mean_joints_forward(const float *x, float *y, long long rows, int V, v
 
 /* ---- host-buffer entry points (processor.py:367,380 / :418 equivalents) ----- */
 /* x_host/logits_host are HOST buffers (pinned for async copies); device_io must
- * hold N*in_feat*T*V + N*num_classes floats.  H2D, forward, D2H on `stream`. */
+ * hold N*in_feat*T*V + N*num_classes floats.  The model forward stages the input chunk by chunk
+ * (the same trial chunks the forward computes in) on an internal per-device copy stream, so the H2D
+ * copy of chunk i+1 runs under the kernels of chunk i; kernels and the D2H of the logits run on
+ * `stream`, which is synchronised before returning. */
 int stgcn_model_forward_host(const stgcn_model_desc *m, const float *x_host, float *logits_host,
                              int N, int T, void *device_io, void *workspace,
                              size_t workspace_bytes, void *stream);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -43,9 +44,13 @@ enum KernelClass {
   KC_COUNT
 };
 
+// One profiler per device: replicas run one host thread per GPU, each thread brackets and reads
+// the launches of its own device; slots are handed out under the profiler's mutex, so several threads may
+// also drive one device.
 struct Profiler {
   std::atomic<long long> launches{0};
-  bool on = false;
+  std::atomic<bool> on{false};
+  std::mutex mu;
   static constexpr int kMax = 4096;
   cudaEvent_t ev[kMax][2];
   int cls[kMax];
@@ -54,28 +59,41 @@ struct Profiler {
   float ms[KC_COUNT] = {0};
   long long count[KC_COUNT] = {0};
 };
-inline Profiler &prof() {
-  static Profiler p;
+constexpr int kMaxDevices = 32;
+inline Profiler *prof_table() {
+  static Profiler p[kMaxDevices];
   return p;
+}
+inline Profiler &prof() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return prof_table()[dev >= 0 && dev < kMaxDevices ? dev : 0];
 }
 // RAII: brackets one kernel launch with events when profiling is on.
 struct ProfScope {
   cudaStream_t st;
-  int slot = -1;
+  cudaEvent_t stop = nullptr;
   ProfScope(int cls, cudaStream_t s) : st(s) {
     Profiler &p = prof();
-    if (!p.on || p.n >= Profiler::kMax) return;
-    slot = p.n++;
-    if (slot >= p.created) {
-      cudaEventCreate(&p.ev[slot][0]);
-      cudaEventCreate(&p.ev[slot][1]);
-      p.created = slot + 1;
+    if (!p.on.load(std::memory_order_relaxed)) return;
+    cudaEvent_t start;
+    {
+      std::lock_guard<std::mutex> g(p.mu);
+      if (p.n >= Profiler::kMax) return;
+      const int slot = p.n++;
+      if (slot >= p.created) {
+        cudaEventCreate(&p.ev[slot][0]);
+        cudaEventCreate(&p.ev[slot][1]);
+        p.created = slot + 1;
+      }
+      p.cls[slot] = cls;
+      start = p.ev[slot][0];
+      stop = p.ev[slot][1];
     }
-    p.cls[slot] = cls;
-    cudaEventRecord(p.ev[slot][0], st);
+    cudaEventRecord(start, st);
   }
   ~ProfScope() {
-    if (slot >= 0) cudaEventRecord(prof().ev[slot][1], st);
+    if (stop) cudaEventRecord(stop, st);
   }
 };
 

@@ -832,6 +832,8 @@ struct TcnTc2Params {
   int load_row[2];            // destination row in the stage
   int load_bytes[2];
   int tap_row[16];            // first stage row of tap j for tile 0
+  long long res_trial_rows;   // rows between consecutive trials of the residual (set by the launcher: T_out*V;
+                              // V when the trials are overlapping windows of one shared frame sequence)
   EpiParams epi;
 };
 
@@ -995,8 +997,8 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
         for (int m = 0; m < p.NT; ++m) {
           const int t = f0 + m * p.FT + fr;
           if (t < p.T_out) {
-            const char *rp = reinterpret_cast<const char *>(p.epi.res + (((long long)n * p.T_out + t) * p.V + w) * C +
-                                                            h * (C / kEpiNH));
+            const char *rp = reinterpret_cast<const char *>(
+                p.epi.res + (n * p.res_trial_rows + (long long)t * p.V + w) * C + h * (C / kEpiNH));
 #pragma unroll
             for (int o = 0; o < (C / kEpiNH) * 4; o += 128) prefetch_l2(rp + o);
           }
@@ -1011,7 +1013,8 @@ __global__ void __launch_bounds__(kTcn2Threads, 1)
         const bool row_ok = (r < RT) && (t < p.T_out);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part, par, h,
+        const long long row_res = n * p.res_trial_rows + (long long)t * p.V + w;
+        ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row_res, row, s_part, par, h,
                                           s_patch + (warp - 3) * kPatchBytes);
       }
       // accumulator buffer drained: hand it back to the MMA issuer
@@ -1628,10 +1631,15 @@ inline int tcn_sets_wanted() {
 // `halo`: the plane buffer holds `halo` extra frames before and after the T frames of every trial
 // (T-split: filled by the neighbouring ranks, or zeros at the sequence ends); output frame tau
 // still reads input frames stride*tau + j - pad of the T-frame sequence.
+// `trial_frames` / `buf_frames` (stride 1 only): trial n starts `trial_frames` frames after trial n-1 in a plane
+// of `buf_frames` frames -- overlapping windows of one shared frame sequence (sliding-window inference); the
+// residual is then addressed with the same trial pitch.  0 = dense (N, T) trials.
 template <int C>
 int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Params p, int N, int T, int stride,
-                     int halo, cudaStream_t st) {
+                     int halo, cudaStream_t st, int trial_frames = 0, long long buf_frames = 0) {
   const int V = p.V, pad = (p.G - 1) / 2;
+  if (trial_frames && (stride != 1 || halo)) return fail("tcn tensor-core kernel: windowed trials need stride 1, no halo");
+  p.res_trial_rows = trial_frames ? (long long)trial_frames * V : (long long)p.T_out * V;
   const int kMaxSmem = 232448;
   // frames per tile: as many whole frames as fit 128 rows; shrink for the big stride-2 case
   int FT = 128 / V;
@@ -1689,10 +1697,11 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
     T += 2 * halo;                                   // frames per trial in the buffer
     for (int q = 0; q < p.n_loads; ++q) p.load_f0[q] += halo / stride;
   }
-  const uint64_t plane_stride = (uint64_t)N * T * V * C * 2;
+  const uint64_t plane_stride = (uint64_t)(trial_frames ? buf_frames : (long long)N * T) * V * C * 2;
   if (stride == 1) {
     const uint64_t ud[5] = {(uint64_t)C, (uint64_t)V, (uint64_t)T, (uint64_t)N, (uint64_t)p.planes};
-    const uint64_t us[4] = {(uint64_t)C * 2, (uint64_t)V * C * 2, (uint64_t)T * V * C * 2, plane_stride};
+    const uint64_t us[4] = {(uint64_t)C * 2, (uint64_t)V * C * 2,
+                            (uint64_t)(trial_frames ? trial_frames : T) * V * C * 2, plane_stride};
     const uint32_t ub[5] = {64, (uint32_t)V, (uint32_t)(p.load_bytes[0] / (V * 128)), 1, 1};
     if (make_tmap_bf16(&tm_u0, u, 5, ud, us, ub)) return 1;
     tm_u1 = tm_u0;
@@ -1744,11 +1753,12 @@ int launch_tcn_tc2_c(const __nv_bfloat16 *u, const __nv_bfloat16 *wp, TcnTc2Para
 }
 
 inline int launch_tcn_tc2(int C, const __nv_bfloat16 *u, const __nv_bfloat16 *wp, const TcnTc2Params &p, int N,
-                          int T, int stride, int halo, cudaStream_t st) {
+                          int T, int stride, int halo, cudaStream_t st, int trial_frames = 0,
+                          long long buf_frames = 0) {
   switch (C) {
-    case 64: return launch_tcn_tc2_c<64>(u, wp, p, N, T, stride, halo, st);
-    case 128: return launch_tcn_tc2_c<128>(u, wp, p, N, T, stride, halo, st);
-    case 256: return launch_tcn_tc2_c<256>(u, wp, p, N, T, stride, halo, st);
+    case 64: return launch_tcn_tc2_c<64>(u, wp, p, N, T, stride, halo, st, trial_frames, buf_frames);
+    case 128: return launch_tcn_tc2_c<128>(u, wp, p, N, T, stride, halo, st, trial_frames, buf_frames);
+    case 256: return launch_tcn_tc2_c<256>(u, wp, p, N, T, stride, halo, st, trial_frames, buf_frames);
   }
   return fail("tcn tensor-core kernel: unsupported channel count %d", C);
 }

@@ -280,8 +280,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * kEpiNH
         for (int m = m_first; m < m_last; ++m) {
           const int t = f0 + m * p.FT + fr;
           if (t < p.T_out) {
-            const char *rp = reinterpret_cast<const char *>(p.epi.res + (((long long)n * p.T_out + t) * p.V + w) * C +
-                                                            h * (C / kEpiNH));
+            const char *rp = reinterpret_cast<const char *>(
+                p.epi.res + (n * p.res_trial_rows + (long long)t * p.V + w) * C + h * (C / kEpiNH));
 #pragma unroll
             for (int o = 0; o < (C / kEpiNH) * 4; o += 128) prefetch_l2(rp + o);
           }
@@ -290,7 +290,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * kEpiNH
         for (int m = m_first; m < m_last; ++m) {
           const int t = f0 + m * p.FT + fr;
           if (t < p.T_out) {
-            const long long ro = (((long long)n * p.T_out + t) * p.V + w) * C + h * (C / kEpiNH);
+            const long long ro = (n * p.res_trial_rows + (long long)t * p.V + w) * C + h * (C / kEpiNH);
             const char *rh = reinterpret_cast<const char *>(p.epi.res_hi + ro);
             const char *rl = reinterpret_cast<const char *>(p.epi.res_lo ? p.epi.res_lo + ro : p.epi.res_hi + ro);
 #pragma unroll
@@ -309,8 +309,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (3 + 4 * kEpiNH
         const bool row_ok = valid && (r < RT) && (t < p.T_out);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols + m * C);
         const long long row = ((long long)n * p.T_out + t) * p.V + w;
-        ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row, row, s_part_set, par, h, patch,
-                                          1 + set);
+        const long long row_res = n * p.res_trial_rows + (long long)t * p.V + w;
+        ln_epilogue_tile<C, kEpiNH, true>(p.epi, taddr, r, RT, p.V, fr, w, row_ok, row_res, row, s_part_set, par, h,
+                                          patch, 1 + set);
       }
       tc_fence_before();
       __syncwarp();

@@ -3,6 +3,7 @@
 
 #include <cstdlib>
 
+#include <vector>
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
@@ -1158,6 +1159,78 @@ size_t model_prepare_layout(const stgcn_model_desc &m, void *base, size_t cap, L
   return pb.peak;
 }
 
+// ---- sliding windows: the per-frame work of the first layer is done once per FRAME, not once per window ------
+// Window n of a chunk covers frames [n, n + W) of the chunk's Tc = n_win + W - 1 frames.  Everything before the
+// first temporal convolution is a per-frame function (input norm, fcn_in, graph convolution, LayerNorm, ReLU), so
+// it is evaluated on the Tc shared frames; the temporal kernel then reads its windows out of that one sequence
+// through a tensor map whose trial pitch is one frame (the rows outside a window are zero-filled by TMA exactly as
+// the convolution's padding), and an identity residual is addressed the same way.  STGCN_WINDOWS_SHARE=0 keeps the
+// per-window evaluation (A/B and the parity test).
+inline bool windows_share_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_WINDOWS_SHARE");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
+inline bool windows_share_supported(const stgcn_model_desc &m, const LayerPrep &P, int W) {
+  const stgcn_layer_desc &d = m.layers[0];
+  return windows_share_enabled() && m.math != STGCN_MATH_FP32 && d.norm == STGCN_NORM_LAYERNORM && embed_warp_path(m) &&
+         P.gw && P.tcn && !P.taps && d.stride == 1 && d.residual != STGCN_RES_CONV &&
+         tc::tcn_tc2_supported(d.c_out, m.num_joints, d.kernel, 1, W);
+}
+// x: strided view of the padded capture at the chunk's first frame; out: [n_win][W][V][c_out] (fp32 rows or planes)
+int layer0_windows_shared(const stgcn_model_desc &m, const LayerPrep &P, const float *x, float *out, int n_win, int W,
+                          const long long *xs, bool out_planes, Bump &ws, cudaStream_t st) {
+  const stgcn_layer_desc &d = m.layers[0];
+  const int V = m.num_joints, planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
+  const int Tc = n_win + W - 1;
+  const long long rows_c = (long long)Tc * V, rows_out = (long long)n_win * W * V;
+  const size_t mark = ws.mark();
+  __nv_bfloat16 *h0 = ws.take<__nv_bfloat16>((size_t)planes * rows_c * d.c_in);
+  __nv_bfloat16 *u16 = ws.take<__nv_bfloat16>((size_t)planes * rows_c * d.c_out);
+  const long long one_trial[3] = {0, xs[1], xs[2]};
+  if (embed(m, x, reinterpret_cast<float *>(h0), 1, Tc, ws, st, one_trial, planes)) return 1;
+  tc::LnStreamArgs l{};
+  l.frames = Tc; l.T = Tc; l.V = V; l.C = d.c_out;
+  l.n_wT = P.n1T; l.n_bT = P.n1T + (size_t)d.c_out * V;
+  l.relu = 1; l.eps = kEps;
+  l.out_hi = u16; l.out_lo = planes == 2 && u16 ? u16 + (size_t)rows_c * d.c_out : nullptr;
+  tc::GcnwParams g{};
+  g.T = Tc; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = 1;
+  g.tab = P.gwtab;
+  g.bias = P.bzT; g.bias_sw = 1;
+  g.debug = debug_mode();
+  if (gcnw_stage(d.c_out, h0, P.wsc, g, l, P.n1V, Tc, 1, rows_c * d.c_in, ws, st)) return 1;
+  if (!ws.measuring()) {
+    STGCN_REQUIRE(!ws.overflow, "workspace too small (shared window frames)");
+    tc::TcnTc2Params p{};
+    p.T_out = W; p.V = V; p.G = d.kernel;
+    p.planes = planes;
+    p.epi.bias = d.tcn_b; p.epi.bias_sw = 0;
+    p.epi.n_wT = P.n2T; p.epi.n_bT = P.n2T + (size_t)d.c_out * V;
+    if (d.residual == STGCN_RES_IDENTITY) {
+      p.epi.res_hi = h0;
+      p.epi.res_lo = planes == 2 ? h0 + (size_t)rows_c * d.c_in : nullptr;
+    }
+    if (out_planes) {
+      p.epi.out_hi = reinterpret_cast<__nv_bfloat16 *>(out);
+      p.epi.out_lo = planes == 2 ? p.epi.out_hi + (size_t)rows_out * d.c_out : nullptr;
+    } else {
+      p.epi.out_f32 = out;
+    }
+    p.epi.relu = 1;
+    p.epi.eps = kEps;
+    p.epi.debug = debug_mode();
+    ProfScope ps(KC_GEMM_TCN, st);
+    if (tc::launch_tcn_tc2(d.c_out, u16, P.wp16, p, n_win, W, 1, 0, st, 1, Tc)) return 1;
+    STGCN_LAUNCH_OK();
+  }
+  ws.release(mark);
+  return 0;
+}
+
 // ST-GCN model on `n` trials (one chunk).  logits [n, classes]; features optional (NCTV).
 int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float *features, int n, int T,
                 Bump &ws, cudaStream_t st, const stgcn_halo_desc *halo = nullptr, float *pooled_sums = nullptr,
@@ -1190,7 +1263,15 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     }
   }
   const bool in0_planes = pl[0] && embed_warp_path(m);
-  if (embed(m, x, buf[0], n, T, ws, st, xs, in0_planes ? planes : 0)) return 1;
+  // sliding windows (xs with a one-frame trial pitch): first layer on the shared frames
+  bool shared0 = false;
+  if (xs && xs[0] == xs[2] && have && !halo && pl[0]) {
+    Bump p0(const_cast<void *>(m.prepared), m.prepared_bytes);
+    const LayerPrep P0 = prep_take(m.layers[0], K, V, p0, (m.reserved & 2) != 0);
+    shared0 = windows_share_supported(m, P0, T);
+    if (shared0 && layer0_windows_shared(m, P0, x, buf[1], n, T, xs, pl[0] && pl[1], ws, st)) return 1;
+  }
+  if (!shared0 && embed(m, x, buf[0], n, T, ws, st, xs, in0_planes ? planes : 0)) return 1;
   int cur = 0;
   t = T;
   Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
@@ -1202,6 +1283,11 @@ int model_chunk(const stgcn_model_desc &m, const float *x, float *logits, float 
     LayerPrep P;
     if (have) P = prep_take(d, K, V, pb, (m.reserved & 2) != 0);
     const bool out_planes = pl[i] && pl[i + 1];
+    if (i == 0 && shared0) {
+      x_planes = out_planes;
+      cur ^= 1;
+      continue;
+    }
     if (layer_forward_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], n, t, ws, st, have ? &P : nullptr, halo, i,
                            x_planes, out_planes, (m.reserved & 2) != 0))
       return 1;
@@ -1680,10 +1766,15 @@ extern "C" {
 int stgcn_abi_version(void) { return STGCN_ABI_VERSION; }
 const char *stgcn_last_error(void) { return err_buf(); }
 
-long long stgcn_launch_count(void) { return prof().launches.load(); }
+long long stgcn_launch_count(void) {
+  long long total = 0;
+  for (int d = 0; d < kMaxDevices; ++d) total += prof_table()[d].launches.load();
+  return total;
+}
 
 int stgcn_profile_begin(void) {
   Profiler &p = prof();
+  std::lock_guard<std::mutex> g(p.mu);
   p.n = 0;
   for (int i = 0; i < KC_COUNT; ++i) {
     p.ms[i] = 0.f;
@@ -1697,6 +1788,7 @@ int stgcn_profile_end(float *ms_per_class, long long *launches_per_class, int n_
   Profiler &p = prof();
   p.on = false;
   STGCN_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> g(p.mu);
   for (int i = 0; i < p.n; ++i) {
     float ms = 0.f;
     STGCN_CUDA_OK(cudaEventElapsedTime(&ms, p.ev[i][0], p.ev[i][1]));
@@ -1894,11 +1986,13 @@ size_t stgcn_model_workspace_bytes(const stgcn_model_desc *m, int N, int T) {
   return model_chunk_bytes(*m, default_chunk(*m, N, T), T);
 }
 
-int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits, float *features, int N,
-                        int T, void *workspace, size_t workspace_bytes, void *stream) {
-  if (check_model(m)) return 1;
+// Shared body of stgcn_model_forward / stgcn_model_forward_host.  With `x_host` the trial chunks are fed
+// from host memory on `copy` (all copies are queued up front, one event per chunk) so that the copy of chunk
+// i+1 runs under the compute of chunk i; `x` is then the device staging buffer the chunks land in.
+static int model_forward_chunks(const stgcn_model_desc *m, const float *x, float *logits, float *features, int N,
+                                int T, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                                const float *x_host, cudaStream_t copy) {
   STGCN_REQUIRE(N > 0 && T > 0, "model: empty input");
-  cudaStream_t st = as_stream(stream);
   // largest trial chunk the caller's workspace can hold (LayerNorm: trials are independent)
   int nc = default_chunk(*m, N, T);
   while (nc > 1 && model_chunk_bytes(*m, nc, T) > workspace_bytes) nc = (nc + 1) / 2;
@@ -1911,14 +2005,44 @@ int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits
   int t_final = T;
   for (int i = 0; i < m->num_layers; ++i) t_final = (t_final - 1) / m->layers[i].stride + 1;
   const int c_last = m->layers[m->num_layers - 1].c_out;
-  for (int n0 = 0; n0 < N; n0 += nc) {
-    int n = N - n0 < nc ? N - n0 : nc;
-    Bump ws(workspace, workspace_bytes);
-    if (model_chunk(*m, x + (size_t)n0 * m->in_feat * T * V, logits + (size_t)n0 * m->num_classes,
-                    features ? features + (size_t)n0 * c_last * t_final * V : nullptr, n, T, ws, st))
-      return 1;
+  const size_t per_trial = (size_t)m->in_feat * T * V;
+  const int n_chunks = (N + nc - 1) / nc;
+  std::vector<cudaEvent_t> fed;
+  int rc = 0;
+  if (x_host) {
+    fed.resize(n_chunks, nullptr);
+    cudaEvent_t start;                                     // the staging buffer is free once `st` got here
+    STGCN_CUDA_OK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    cudaEventRecord(start, st);
+    cudaStreamWaitEvent(copy, start, 0);
+    cudaEventDestroy(start);
+    for (int c = 0; c < n_chunks && !rc; ++c) {
+      const int n0 = c * nc, n = N - n0 < nc ? N - n0 : nc;
+      float *dst = const_cast<float *>(x) + (size_t)n0 * per_trial;
+      if (cudaEventCreateWithFlags(&fed[c], cudaEventDisableTiming) != cudaSuccess ||
+          cudaMemcpyAsync(dst, x_host + (size_t)n0 * per_trial, (size_t)n * per_trial * sizeof(float),
+                          cudaMemcpyHostToDevice, copy) != cudaSuccess ||
+          cudaEventRecord(fed[c], copy) != cudaSuccess)
+        rc = fail("forward_host: staging copy of chunk %d failed: %s", c, cudaGetErrorString(cudaGetLastError()));
+    }
   }
-  return 0;
+  for (int c = 0; c < n_chunks && !rc; ++c) {
+    const int n0 = c * nc, n = N - n0 < nc ? N - n0 : nc;
+    if (x_host) cudaStreamWaitEvent(st, fed[c], 0);
+    Bump ws(workspace, workspace_bytes);
+    rc = model_chunk(*m, x + (size_t)n0 * per_trial, logits + (size_t)n0 * m->num_classes,
+                     features ? features + (size_t)n0 * c_last * t_final * V : nullptr, n, T, ws, st);
+  }
+  for (cudaEvent_t e : fed)
+    if (e) cudaEventDestroy(e);
+  return rc;
+}
+
+int stgcn_model_forward(const stgcn_model_desc *m, const float *x, float *logits, float *features, int N,
+                        int T, void *workspace, size_t workspace_bytes, void *stream) {
+  if (check_model(m)) return 1;
+  return model_forward_chunks(m, x, logits, features, N, T, workspace, workspace_bytes, as_stream(stream), nullptr,
+                              nullptr);
 }
 
 // ---- sliding-window inference (utils/segment_generator.py:109-154, processor.py:374-380) ------------
@@ -2206,8 +2330,23 @@ int stgcn_model_forward_host(const stgcn_model_desc *m, const float *x_host, flo
   const size_t nx = (size_t)N * m->in_feat * T * m->num_joints, nl = (size_t)N * m->num_classes;
   float *dx = static_cast<float *>(device_io);
   float *dl = dx + nx;
-  STGCN_CUDA_OK(cudaMemcpyAsync(dx, x_host, nx * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (stgcn_model_forward(m, dx, dl, nullptr, N, T, workspace, workspace_bytes, stream)) return 1;
+  // per-device staging stream (created once): chunk copies overlap the previous chunk's kernels
+  static std::mutex mu;
+  static cudaStream_t copy_streams[kMaxDevices] = {nullptr};
+  int dev = 0;
+  STGCN_CUDA_OK(cudaGetDevice(&dev));
+  STGCN_REQUIRE(dev >= 0 && dev < kMaxDevices, "forward_host: device index %d out of range", dev);
+  cudaStream_t copy;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (!copy_streams[dev]) STGCN_CUDA_OK(cudaStreamCreateWithFlags(&copy_streams[dev], cudaStreamNonBlocking));
+    copy = copy_streams[dev];
+  }
+  if (model_forward_chunks(m, dx, dl, nullptr, N, T, workspace, workspace_bytes, st, x_host, copy)) {
+    cudaStreamSynchronize(copy);
+    cudaStreamSynchronize(st);
+    return 1;
+  }
   STGCN_CUDA_OK(cudaMemcpyAsync(logits_host, dl, nl * sizeof(float), cudaMemcpyDeviceToHost, st));
   STGCN_CUDA_OK(cudaStreamSynchronize(st));
   return 0;

@@ -649,6 +649,33 @@ def test_stgcn_sliding_windows(pkg, syn, cuda):
     assert rel_err(out[0, :, pick].t().unsqueeze(-1), ref) < TOL
 
 
+def test_stgcn_sliding_windows_shared_first_layer_subprocess(cuda, tmp_path):
+    """Sliding windows share their frames: everything before the first temporal convolution is evaluated once per
+    frame and the temporal kernel reads its windows out of that one sequence (tensor map with a one-frame trial
+    pitch).  The result must equal the per-window evaluation (STGCN_WINDOWS_SHARE=0) bit for bit -- with and
+    without a first-layer residual, both arithmetic modes, several window chunks per call -- and both must match
+    the oracle.  The switches are read once per process, hence child processes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = {}
+    for share in ('1', '0'):
+        path = str(tmp_path / ('win%s.pt' % share))
+        env = dict(os.environ, STGCN_WINDOWS_SHARE=share, STGCN_CHUNK_ROWS='200000')
+        out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'check_windows_paths.py'), path], env=env,
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [l for l in out.stdout.splitlines() if ' err ' in l]
+        assert len(lines) == 3, out.stdout[-2000:]
+        for l in lines:
+            assert float(l.split(' err ')[1]) < (TOL if l.startswith('bf16x3') else BF16_TOL), l
+        got[share] = torch.load(path)
+    assert set(got['1']) == set(got['0']) and len(got['1']) == 3
+    for k in got['1']:
+        assert torch.equal(got['1'][k], got['0'][k]), k
+
+
 # ------------------------------------------------------------------ non-default graph-conv paths
 @pytest.mark.parametrize('switches', [{}, {'STGCN_GCNW': '0'}, {'STGCN_GCNW_FUSE': '1'}],
                          ids=['default', 'frame-tile-kernel', 'one-kernel-stage'])
