@@ -321,6 +321,16 @@ int gcnw_stage(int c_out, const __nv_bfloat16 *xh, const __nv_bfloat16 *wsc, tc:
   const size_t mark = ws.mark();
   const int V = g.V, cap = tc::gcnw_edge_cap(V);
   const long long rows = (long long)g.N * g.T * V;
+  // The stage is a per-frame function: when the trials are dense in memory (no halo frames, frame stride 1, or
+  // stride 2 over an even number of frames) they form ONE frame sequence, so a 128-frame tile may span trials --
+  // short trials (sliding windows, T = 50 .. 300; the deep layers at T/4) no longer leave tiles part empty.
+  if (g.N > 1 && l.out_T == 0 && g.tmode == 0 && (long long)g.N * T_full < (1ll << 30) &&
+      ((fstride == 1 && T_full == g.T) || (fstride == 2 && T_full == 2 * g.T))) {
+    T_full *= g.N;
+    g.T *= g.N;
+    l.T = g.T;
+    g.N = 1;
+  }
   if (tc::gcnw_fuse_enabled()) {
     const int groups = g.N * ((g.T + 127) / 128);
     g.zring = ws.take<float>(tc::gcnw_ring_floats(V, c_out));
