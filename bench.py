@@ -57,7 +57,7 @@ def parse():
     p.add_argument('--math', default=os.environ.get('STGCN_MATH', 'bf16x3'), choices=['fp32', 'bf16x3', 'bf16'])
     p.add_argument('--norm', default='LayerNorm', choices=['LayerNorm', 'BatchNorm'])
     p.add_argument('--rt-streams', type=int, default=4096)
-    p.add_argument('--rt-steps', type=int, default=200)
+    p.add_argument('--rt-steps', type=int, default=1000)
     p.add_argument('--no-rt', action='store_true')
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
@@ -215,7 +215,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfgd,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "port",
                          "sample": "1 trial x T=%d per step (of %d trials), torch CPU fp32, %d threads"
                                    % (args.frames, args.trials, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -223,6 +223,18 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- continual legs
+def cpu_model():
+    """Model name of the host CPU (report it beside every CPU timing)."""
+    try:
+        with open('/proc/cpuinfo') as f:
+            for l in f:
+                if l.lower().startswith('model name'):
+                    return l.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
 def _p50(ms):
     ms = sorted(ms)
     return ms[len(ms) // 2], ms[int(len(ms) * 0.9)]
@@ -302,7 +314,7 @@ def rt_latency(pkg, dev, streams, steps, graph_kw, math, hbm_gbs=None, cuda_grap
                 t0 = time.perf_counter()
                 O.rt_model_step(xs[i], sd, oc, st)
                 ts.append((time.perf_counter() - t0) * 1e3)
-        out["cpu_reference"] = {"p50_ms": _p50(ts[50:])[0], "streams": 1, "frames": 300, "cores": os.cpu_count() or 1,
+        out["cpu_reference"] = {"p50_ms": _p50(ts[50:])[0], "streams": 1, "frames": 300, "cores": os.cpu_count() or 1, "cpu_model": cpu_model(),
                                 "kind": "port", "note": "oracle continual loop (the reference's per-frame ATen op "
                                 "sequence), 50 warm-up + 300 timed frames, batch 1 as in the reference"}
     del m
@@ -605,7 +617,7 @@ def main():
         c50 = _p50(cs)[0]
         c1 = {"workload": "ST-GCN fwd, N=1 C=3 T=300 V=25 (BASELINE config 1)", "gpu_p50_ms": g50,
               "gpu_frames_per_s": 300 / (g50 * 1e-3), "cpu_p50_ms": c50, "cpu_frames_per_s": 300 / (c50 * 1e-3),
-              "cpu_cores": os.cpu_count() or 1, "cpu_kind": "port", "rel_err_vs_cpu": rel_err(o1, r1)}
+              "cpu_cores": os.cpu_count() or 1, "cpu_model": cpu_model(), "cpu_kind": "port", "rel_err_vs_cpu": rel_err(o1, r1)}
 
     # ---- sliding-window inference of one trial (W = the reference configs' receptive_field) ----
     windows = None
@@ -653,7 +665,7 @@ def main():
             cpu_reference_step(xs, sd, ocfg)
             reps += 1
         dt = (time.perf_counter() - t0) / reps
-        cpu = {"value": T / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": T / dt, "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "port",
                "sample": "%d x (1 trial, T=%d) of the %d-trial workload; oracle = same ATen CPU ops as the reference"
                          % (reps, T, N)}
 
