@@ -764,8 +764,11 @@ __global__ void __launch_bounds__(256, 2) k_ln_stream(LnStreamArgs p) {
   }
   const float rstd = 1.f / sqrtf(block_sum(q, s_red) * inv_nm1 + p.eps);
   const float nmr = -mean * rstd;
-  const long long n = f / p.T;
-  const long long fo = p.out_T ? n * p.out_T + (f - n * p.T) + p.out_t0 : f;
+  long long fo = f;
+  if (p.out_T) {                                             // halo layout only: keeps the division off the main path
+    const int n = (int)f / p.T;                              // frames < 2^31 (checked by the launcher)
+    fo = (long long)n * p.out_T + ((int)f - n * p.T) + p.out_t0;
+  }
   const long long ob = fo * (long long)p.V * p.C;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
@@ -869,8 +872,11 @@ __global__ void __launch_bounds__(256) k_ln_warp(LnStreamArgs p) {
   }
   const float rstd = 1.f / sqrtf(m2 / (float)(p.V * p.C - 1) + p.eps);
   const float nmr = -mean * rstd;
-  const long long n = f / p.T;
-  const long long fo = p.out_T ? n * p.out_T + (f - n * p.T) + p.out_t0 : f;
+  long long fo = f;
+  if (p.out_T) {                                             // halo layout only: keeps the division off the main path
+    const int n = (int)f / p.T;                              // frames < 2^31 (checked by the launcher)
+    fo = (long long)n * p.out_T + ((int)f - n * p.T) + p.out_t0;
+  }
   const long long ob = fo * (long long)p.V * p.C;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {

@@ -715,6 +715,16 @@ __global__ void __launch_bounds__(256)
         const float4 *xp = reinterpret_cast<const float4 *>(x + ((long long)(b0 + s) * V) * C) + c4;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
         int v = 0;
+        for (; v + 6 <= V; v += 6) {                       // six independent 16-byte loads in flight per thread
+          float4 u[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) u[i] = __ldg(xp + (long long)(v + i) * C4);
+#pragma unroll
+          for (int i = 0; i < 6; i += 2) {
+            a0.x += u[i].x; a0.y += u[i].y; a0.z += u[i].z; a0.w += u[i].w;
+            a1.x += u[i + 1].x; a1.y += u[i + 1].y; a1.z += u[i + 1].z; a1.w += u[i + 1].w;
+          }
+        }
         for (; v + 1 < V; v += 2) {
           const float4 u0 = __ldg(xp + (long long)v * C4), u1 = __ldg(xp + (long long)(v + 1) * C4);
           a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
