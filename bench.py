@@ -607,6 +607,18 @@ def main():
             b.record()
         torch.cuda.synchronize()
         g50 = _p50([a.elapsed_time(b) for a, b in evs])[0]
+        model.enable_cuda_graph(True)                        # the same forward replayed from a CUDA graph
+        for _ in range(3):
+            og = model(x1)
+        torch.cuda.synchronize()
+        for a, b in evs:
+            a.record()
+            og = model(x1)
+            b.record()
+        torch.cuda.synchronize()
+        gg50 = _p50([a.elapsed_time(b) for a, b in evs])[0]
+        model.enable_cuda_graph(False)
+        assert torch.equal(og, o1), "CUDA-graph replay differs from the eager forward"
         torch.set_num_threads(os.cpu_count() or 1)
         r1 = cpu_reference_step(x1h, sd, ocfg)
         cs = []
@@ -616,7 +628,7 @@ def main():
             cs.append((time.perf_counter() - t0) * 1e3)
         c50 = _p50(cs)[0]
         c1 = {"workload": "ST-GCN fwd, N=1 C=3 T=300 V=25 (BASELINE config 1)", "gpu_p50_ms": g50,
-              "gpu_frames_per_s": 300 / (g50 * 1e-3), "cpu_p50_ms": c50, "cpu_frames_per_s": 300 / (c50 * 1e-3),
+              "gpu_frames_per_s": 300 / (g50 * 1e-3), "gpu_graph_p50_ms": gg50, "gpu_graph_frames_per_s": 300 / (gg50 * 1e-3), "cpu_p50_ms": c50, "cpu_frames_per_s": 300 / (c50 * 1e-3),
               "cpu_cores": os.cpu_count() or 1, "cpu_model": cpu_model(), "cpu_kind": "port", "rel_err_vs_cpu": rel_err(o1, r1)}
 
     # ---- sliding-window inference of one trial (W = the reference configs' receptive_field) ----

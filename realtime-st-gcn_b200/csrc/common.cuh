@@ -46,9 +46,9 @@ enum KernelClass {
 
 // One profiler per device: replicas run one host thread per GPU, each thread brackets and reads
 // the launches of its own device; slots are handed out under the profiler's mutex, so several threads may
-// also drive one device.
+// also drive one device.  The launch counter and the "any profiler on" flag are process-wide atomics, so a
+// launch with profiling off costs one relaxed load and one add (no cudaGetDevice on the launch path).
 struct Profiler {
-  std::atomic<long long> launches{0};
   std::atomic<bool> on{false};
   std::mutex mu;
   static constexpr int kMax = 4096;
@@ -59,6 +59,14 @@ struct Profiler {
   float ms[KC_COUNT] = {0};
   long long count[KC_COUNT] = {0};
 };
+struct ProfGlobal {
+  std::atomic<long long> launches{0};
+  std::atomic<int> active{0};      // devices with profiling on
+};
+inline ProfGlobal &prof_global() {
+  static ProfGlobal g;
+  return g;
+}
 constexpr int kMaxDevices = 32;
 inline Profiler *prof_table() {
   static Profiler p[kMaxDevices];
@@ -74,6 +82,7 @@ struct ProfScope {
   cudaStream_t st;
   cudaEvent_t stop = nullptr;
   ProfScope(int cls, cudaStream_t s) : st(s) {
+    if (prof_global().active.load(std::memory_order_relaxed) == 0) return;
     Profiler &p = prof();
     if (!p.on.load(std::memory_order_relaxed)) return;
     cudaEvent_t start;
@@ -99,7 +108,7 @@ struct ProfScope {
 
 #define STGCN_LAUNCH_OK()                                                                 \
   do {                                                                                    \
-    ::stgcn::prof().launches.fetch_add(1, std::memory_order_relaxed);                     \
+    ::stgcn::prof_global().launches.fetch_add(1, std::memory_order_relaxed);              \
     cudaError_t e_ = cudaGetLastError();                                                  \
     if (e_ != cudaSuccess)                                                                \
       return ::stgcn::fail("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \

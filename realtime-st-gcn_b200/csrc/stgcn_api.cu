@@ -1776,11 +1776,7 @@ extern "C" {
 int stgcn_abi_version(void) { return STGCN_ABI_VERSION; }
 const char *stgcn_last_error(void) { return err_buf(); }
 
-long long stgcn_launch_count(void) {
-  long long total = 0;
-  for (int d = 0; d < kMaxDevices; ++d) total += prof_table()[d].launches.load();
-  return total;
-}
+long long stgcn_launch_count(void) { return prof_global().launches.load(); }
 
 int stgcn_profile_begin(void) {
   Profiler &p = prof();
@@ -1790,13 +1786,13 @@ int stgcn_profile_begin(void) {
     p.ms[i] = 0.f;
     p.count[i] = 0;
   }
-  p.on = true;
+  if (!p.on.exchange(true)) prof_global().active.fetch_add(1);
   return 0;
 }
 
 int stgcn_profile_end(float *ms_per_class, long long *launches_per_class, int n_classes) {
   Profiler &p = prof();
-  p.on = false;
+  if (p.on.exchange(false)) prof_global().active.fetch_sub(1);
   STGCN_CUDA_OK(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> g(p.mu);
   for (int i = 0; i < p.n; ++i) {

@@ -625,6 +625,23 @@ def test_stgcn_layer_tensor_core_other_graphs(pkg, cuda, graph, c, kernel, strid
     assert rel_err(y3, ref) < TOL, rel_err(y3, ref)
 
 
+def test_stgcn_cuda_graph_replay(pkg, syn, cuda):
+    """Stgcn.enable_cuda_graph: config-1-sized forwards are launch-bound, so the module can replay the captured
+    kernel sequence; replays equal the eager forward bit for bit, for new inputs and after a shape change."""
+    cfg = syn.arch_config('st-gcn', num_classes=12, in_ch=[64, 64, 128], out_ch=[64, 128, 128], stride=[1, 2, 1])
+    m = pkg.Stgcn(**cfg)
+    m.load_state_dict(syn.synth_state_dict(m.state_dict(), 71))
+    m = m.to(cuda).eval()
+    xs = [syn.synth_input((1, 3, 60, 25), 72), syn.synth_input((1, 3, 60, 25), 73), syn.synth_input((2, 3, 37, 25), 74)]
+    eager = [m(x.to(cuda)).clone() for x in xs]
+    m.enable_cuda_graph(True)
+    for x, ref in zip(xs + xs[:1], eager + eager[:1]):
+        out = m(x.to(cuda))
+        assert torch.equal(out, ref)
+    m.enable_cuda_graph(False)
+    assert torch.equal(m(xs[1].to(cuda)), eager[1])
+
+
 # ------------------------------------------------------------------ sliding-window inference (SURVEY 8f rank 1)
 def test_stgcn_sliding_windows(pkg, syn, cuda):
     """WindowSegment semantics (utils/segment_generator.py:109-154): frame i classified from the W
