@@ -29,11 +29,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.
+// Default (.release.cta) semantics on purpose: what the epilogue hands back is a TMEM accumulator buffer, ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not generic-proxy memory.  The .release.cluster form
+// compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive, i.e. every epilogue warp waited once per
+// item for its own output stores to become visible GPU-wide (ncu: 0.9 "membar" stall cycles per issued instruction
+// in k_tcn_tc2p<64>).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t cta) {
   uint32_t remote;
