@@ -138,6 +138,8 @@ struct GcnwParams {
   // (frames outside the trial are zero-filled by TMA = the convolution's zero padding); stride 2 reads the
   // even / odd frame sequences through two tensor maps
   int tmode, tpad, tstride;
+  int smem_cap;               // 0 = all shared memory; else the launcher sizes its stage rings to this many bytes
+                              // (a CTA that leaves room for another kernel's CTAs on the same SM)
   // fused LayerNorm stage (k_gcnw<.., FUSE = true>)
   float *zring;                 // [R][128 frames][V][CO] fp32
   float2 *sring;                // [R][128][V][kEpiNH] (mean, M2) of every (frame, joint, column group)
@@ -1024,7 +1026,7 @@ struct GcnwXView {
 template <int CO, bool FUSE>
 int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p, int T_full, int fstride, int cap,
                   long long plane_stride, cudaStream_t st, const GcnwXView &xv) {
-  const int V = p.V, kMaxSmem = 232448;
+  const int V = p.V;
   p.tblocks = (p.T + 127) / 128;
   p.items = p.N * p.tblocks * V;
   const int fixed = kPatchTotal + 1024 + 1024 + 512 + 1024;
@@ -1032,6 +1034,12 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
   constexpr int kA = MERGE ? 2 * 128 * 128 : 128 * 128, kB = MERGE ? 2 * CO * 128 : CO * 128;
   // weight stages first (they are the long-latency stream for C >= 128), then activation stages
   int SB = MERGE ? (CO >= 128 ? 2 : 3) : 3;
+  int kMaxSmem = 232448;
+  if (p.smem_cap > 0 && p.smem_cap < kMaxSmem) {           // shared-SM mode: smallest rings that still pipeline
+    if (!MERGE) SB = 2;
+    const int need = fixed + SB * kB + 2 * kA;
+    kMaxSmem = p.smem_cap > need ? p.smem_cap : need;
+  }
   int SA = (kMaxSmem - fixed - SB * kB) / kA;
   if (SA > (MERGE ? 4 : 8)) SA = MERGE ? 4 : 8;
   if (SA < 2) return fail("gcnw: shared memory does not fit");

@@ -848,8 +848,12 @@ int launch_rt_state(const RtUpdateArgs &u, cudaStream_t st) {
 int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const float *x, float *out,
                        float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st,
                        const LayerPrep *pp = nullptr, bool use_gw = false, bool x_planes = false,
-                       bool out_planes = false, bool fifo_bf16 = false) {
+                       bool out_planes = false, bool fifo_bf16 = false, long long slot_rows = 0,
+                       int gw_smem_cap = 0, cudaEvent_t gemm_wait = nullptr, cudaEvent_t gemm_done = nullptr) {
+  // slot_rows: rows (streams * V) between consecutive FIFO / accumulator slots when the call covers only a range
+  // of the streams the state was laid out for (0 = the B of this call); gw_smem_cap: see GcnwParams::smem_cap
   if (check_layer(d)) return 1;
+  STGCN_REQUIRE(!slot_rows || use_gw, "rt layer: stream ranges need the per-joint-weight GEMM path");
   STGCN_REQUIRE(!fifo_bf16 || use_gw, "rt layer: the bf16 FIFO layout needs the per-joint-weight GEMM path");
   STGCN_REQUIRE(d.norm == STGCN_NORM_LAYERNORM,
                 "continual inference needs LayerNorm: batch statistics of a single frame are undefined "
@@ -881,11 +885,15 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       const __nv_bfloat16 *xh = reinterpret_cast<const __nv_bfloat16 *>(x);
       const __nv_bfloat16 *xl = planes == 2 ? xh + (size_t)rows * d.c_in : nullptr;
       const int cap = tc::gcnw_edge_cap(V);
+      // two-half step: this half's GEMMs start when the other half's GEMMs of the same phase are done, so that a
+      // GEMM always shares the SMs with the other half's state kernel
+      if (gemm_wait) STGCN_CUDA_OK(cudaStreamWaitEvent(st, gemm_wait, 0));
       if (qr) {
         tc::GcnwParams g{};
         g.T = B; g.V = V; g.Cin = d.c_in; g.planes = planes; g.N = 1;
         g.tab = pp->gwtabr;
         g.out = qr;                            // no bias (rtstgcn.py:503)
+        g.smem_cap = gw_smem_cap;
         ProfScope ps(KC_GEMM_1X1, st);
         if (tc::launch_gcnw(d.c_out, xh, pp->wscr, g, B, 1, cap, rows * d.c_in, st)) return 1;
         STGCN_LAUNCH_OK();
@@ -896,10 +904,12 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
         g.tab = pp->gwtab;
         g.bias = pp->bzT; g.bias_sw = 1;
         g.out = zb;
+        g.smem_cap = gw_smem_cap;
         ProfScope ps(KC_GEMM_1X1, st);
         if (tc::launch_gcnw(d.c_out, xh, pp->wsc, g, B, 1, cap, rows * d.c_in, st)) return 1;
         STGCN_LAUNCH_OK();
       }
+      if (gemm_done) STGCN_CUDA_OK(cudaEventRecord(gemm_done, st));
       RtUpdateArgs u{};
       u.B = B; u.V = V; u.C = d.c_out;
       u.z = zb;
@@ -909,7 +919,7 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       u.fifo_bf16 = fifo_bf16 ? 1 : 0;
       u.F = d.stride * (d.kernel - 1) + 1;
       u.S = d.stride;
-      u.slot = rows * d.c_out;
+      u.slot = (slot_rows ? slot_rows : rows) * d.c_out;
       u.n_wT = pp->n1T; u.n_bT = pp->n1T + (size_t)d.c_out * V;
       if (d.residual == STGCN_RES_IDENTITY) { u.res_mode = 1; u.res_hi = xh; u.res_lo = xl; }
       else if (d.residual == STGCN_RES_CONV) {
@@ -1437,6 +1447,130 @@ bool rt_fifo_bf16(const stgcn_model_desc &m, int B) {
   return true;
 }
 
+// STGCN_RT_OVERLAP: smallest stream count that is stepped as two overlapping halves (0 = never)
+inline int rt_overlap_min_streams() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("STGCN_RT_OVERLAP");
+    v = e ? atoi(e) : 1024;
+    if (v <= 0) v = 0x7fffffff;
+  }
+  return v;
+}
+inline int rt_overlap_smem_cap() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("STGCN_RT_OVERLAP_SMEM");      // 0 = the GEMM CTAs keep all shared memory (measured best)
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+// per-device side stream + fork / join events of the two-half step (created once; usable under stream capture)
+// The caller holds the returned per-device lock while it enqueues fork .. join: the events are shared by every
+// model instance of the device, and a record / wait pair of another host thread must not land between them.
+constexpr int kRtSideEvents = 2 + 2 * 64;      // fork, join, and one "GEMMs done" event per layer and half
+int rt_side_stream(cudaStream_t *side, cudaEvent_t **ev, std::unique_lock<std::mutex> &hold) {
+  static std::mutex mu[kMaxDevices];
+  static cudaStream_t streams[kMaxDevices] = {nullptr};
+  static cudaEvent_t events[kMaxDevices][kRtSideEvents] = {{nullptr}};
+  int dev = 0;
+  STGCN_CUDA_OK(cudaGetDevice(&dev));
+  STGCN_REQUIRE(dev >= 0 && dev < kMaxDevices, "rt step: device index %d out of range", dev);
+  hold = std::unique_lock<std::mutex>(mu[dev]);
+  if (!streams[dev]) {
+    STGCN_CUDA_OK(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    for (int i = 0; i < kRtSideEvents; ++i)
+      STGCN_CUDA_OK(cudaEventCreateWithFlags(&events[dev][i], cudaEventDisableTiming));
+  }
+  *side = streams[dev];
+  *ev = events[dev];
+  return 0;
+}
+// STGCN_RT_OVERLAP_MODE: 0 (default) = the halves run free, 1 = the second half starts one GEMM phase late,
+// 2 = GEMM phases of the two halves alternate strictly.  Measured at 2048 / 4096 streams (PKU trunk, ms):
+// one batch 0.838 / 1.489; mode 0 0.786 / 1.473; mode 1 0.830 / 1.508; mode 2 0.964 / 1.571 -- a GEMM and a
+// state kernel that share the SMs slow each other by what the overlap gains, so only the free-running form
+// (which mostly fills the tails of the half-sized launches) is kept.
+inline int rt_overlap_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("STGCN_RT_OVERLAP_MODE");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+// One continual step for streams [b0, b0 + nb) of a state laid out for B streams (the many-streams path), in
+// three parts so that two ranges can be enqueued layer by layer on two CUDA streams.
+struct RtRangeCursor {
+  float *buf[2] = {nullptr, nullptr};
+  int cur = 0, b0 = 0, nb = 0;
+  size_t prep_off = 0;            // walk through the prepared operands
+};
+int rt_step_range_begin(const stgcn_model_desc &m, const RtLayout &L, const float *x, int B, int b0, int nb,
+                        bool all_gw, Bump &ws, cudaStream_t st, RtRangeCursor &c) {
+  const int V = m.num_joints;
+  STGCN_REQUIRE(all_gw || (b0 == 0 && nb == B), "rt step: stream ranges need the per-joint-weight GEMM path");
+  size_t max_act = (size_t)nb * V * m.layers[0].c_in;
+  for (int i = 0; i < m.num_layers; ++i) {
+    size_t a = (size_t)nb * V * m.layers[i].c_out;
+    if (a > max_act) max_act = a;
+  }
+  c.buf[0] = ws.take<float>(max_act);
+  c.buf[1] = ws.take<float>(max_act);
+  c.cur = 0; c.b0 = b0; c.nb = nb; c.prep_off = 0;
+  const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
+  STGCN_REQUIRE(ws.measuring() || !ws.overflow, "rtstgcn_step: workspace too small (%zu B given)", ws.cap);
+  return embed(m, x ? x + (size_t)b0 * m.in_feat * V : nullptr, c.buf[0], nb, 1, ws, st, nullptr, all_gw ? planes : 0);
+}
+int rt_step_range_layer(const stgcn_model_desc &m, const RtLayout &L, void *state, int B, bool all_gw, bool fifo16,
+                        Bump &ws, cudaStream_t st, int gw_smem_cap, RtRangeCursor &c, int i,
+                        cudaEvent_t gemm_wait, cudaEvent_t gemm_done) {
+  const int V = m.num_joints, K = m.partitions;
+  const bool have = use_prepared(m), sparse = (m.reserved & 2) != 0;
+  const stgcn_layer_desc &d = m.layers[i];
+  STGCN_REQUIRE(d.rt == 1, "rtstgcn_step needs online layers (rt == 1)");
+  char *sb = static_cast<char *>(state);
+  int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters) + c.b0;
+  const size_t first = (size_t)c.b0 * V * d.c_out;           // elements before this range inside one slot
+  float *fifo = ws.measuring() ? nullptr
+                               : reinterpret_cast<float *>(sb + L.fifo[i] + first * (fifo16 && all_gw ? 2 : 4));
+  float *acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]) + first;
+  LayerPrep P;
+  if (have) {
+    Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
+    pb.off = c.prep_off;
+    P = prep_take(d, K, V, pb, sparse);
+    c.prep_off = pb.off;
+  }
+  const bool last = i + 1 == m.num_layers;
+  if (rt_layer_step_ntvc(d, K, V, m.math, c.buf[c.cur], c.buf[c.cur ^ 1], fifo, acc, counter, c.nb, ws, st,
+                         have ? &P : nullptr, all_gw, all_gw, all_gw && !last, fifo16 && all_gw,
+                         c.nb == B ? 0 : (long long)B * V, gw_smem_cap, gemm_wait, gemm_done))
+    return 1;
+  c.cur ^= 1;
+  return 0;
+}
+int rt_step_range_end(const stgcn_model_desc &m, float *logits, int *top5, cudaStream_t st, RtRangeCursor &c) {
+  const int V = m.num_joints, c_last = m.layers[m.num_layers - 1].c_out;
+  ProfScope ps(KC_POOL, st);
+  const int spb = rt_head_streams(c.nb);
+  k_rt_head<<<cdiv(c.nb, spb), 256, sizeof(float) * spb * (c_last + m.num_classes), st>>>(
+      c.buf[c.cur], c.nb, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits + (size_t)c.b0 * m.num_classes,
+      top5 ? top5 + (size_t)c.b0 * 5 : nullptr, spb);
+  STGCN_LAUNCH_OK();
+  return 0;
+}
+int rt_step_range(const stgcn_model_desc &m, const RtLayout &L, const float *x, void *state, float *logits, int *top5,
+                  int B, int b0, int nb, bool all_gw, bool fifo16, Bump &ws, cudaStream_t st, int gw_smem_cap) {
+  RtRangeCursor c;
+  if (rt_step_range_begin(m, L, x, B, b0, nb, all_gw, ws, st, c)) return 1;
+  for (int i = 0; i < m.num_layers; ++i)
+    if (rt_step_range_layer(m, L, state, B, all_gw, fifo16, ws, st, gw_smem_cap, c, i, nullptr, nullptr)) return 1;
+  if (!ws.measuring() && rt_step_range_end(m, logits, top5, st, c)) return 1;
+  return 0;
+}
+
 int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logits, int B, Bump &ws,
             cudaStream_t st, int *top5 = nullptr) {
   const int V = m.num_joints, K = m.partitions;
@@ -1508,12 +1642,6 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     ws.release(mark);
     return 0;
   }
-  size_t max_act = (size_t)B * V * m.layers[0].c_in;
-  for (int i = 0; i < m.num_layers; ++i) {
-    size_t a = (size_t)B * V * m.layers[i].c_out;
-    if (a > max_act) max_act = a;
-  }
-  float *buf[2] = {ws.take<float>(max_act), ws.take<float>(max_act)};
   const bool have = use_prepared(m);
   const bool sparse = (m.reserved & 2) != 0;
   // per-joint-weight GEMM path: all layers or none (the activations then travel as bf16 planes)
@@ -1526,37 +1654,67 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
       all_gw = Q.gw && (d.residual != STGCN_RES_CONV || Q.res) && rt_update_supported(V, d.c_out);
     }
   }
-  const int planes = m.math == STGCN_MATH_BF16X3 ? 2 : 1;
   const bool fifo16 = rt_fifo_bf16(m, B);
   STGCN_REQUIRE(!fifo16 || all_gw || ws.measuring(),
                 "rtstgcn_step: bf16 continual mode stores the FIFO as bf16 and needs prepared operands "
                 "(stgcn_model_prepare)");
-  STGCN_REQUIRE(ws.measuring() || !ws.overflow, "rtstgcn_step: workspace too small (%zu B given)", ws.cap);
-  if (embed(m, x, buf[0], B, 1, ws, st, nullptr, all_gw ? planes : 0)) return 1;
-  char *sb = static_cast<char *>(state);
-  int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(sb + L.counters);
-  int cur = 0;
-  Bump pb(const_cast<void *>(m.prepared), m.prepared_bytes);
-  for (int i = 0; i < m.num_layers; ++i) {
-    const stgcn_layer_desc &d = m.layers[i];
-    STGCN_REQUIRE(d.rt == 1, "rtstgcn_step needs online layers (rt == 1)");
-    float *fifo = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.fifo[i]);
-    float *acc = ws.measuring() ? nullptr : reinterpret_cast<float *>(sb + L.acc[i]);
-    LayerPrep P;
-    if (have) P = prep_take(d, K, V, pb, sparse);
-    const bool last = i + 1 == m.num_layers;
-    if (rt_layer_step_ntvc(d, K, V, m.math, buf[cur], buf[cur ^ 1], fifo, acc, counter, B, ws, st,
-                           have ? &P : nullptr, all_gw, all_gw, all_gw && !last, fifo16 && all_gw))
-      return 1;
-    cur ^= 1;
-  }
-  const int c_last = m.layers[m.num_layers - 1].c_out;
-  if (!ws.measuring()) {
-    ProfScope ps(KC_POOL, st);
-    const int spb = rt_head_streams(B);
-    k_rt_head<<<cdiv(B, spb), 256, sizeof(float) * spb * (c_last + m.num_classes), st>>>(
-        buf[cur], B, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits, top5, spb);
-    STGCN_LAUNCH_OK();
+  int *counter = ws.measuring() ? nullptr : reinterpret_cast<int *>(static_cast<char *>(state) + L.counters);
+  const int halves = (all_gw && B >= rt_overlap_min_streams()) ? 2 : 1;
+  if (halves == 1) {
+    if (rt_step_range(m, L, x, state, logits, top5, B, 0, B, all_gw, fifo16, ws, st, 0)) return 1;
+  } else {
+    // Two halves of the streams as two independent pipelines on two CUDA streams: the launches of one half fill
+    // the tails of the other's (-5 % at 1024 streams, -6 % at 2048, -1 % at 4096).  Pairing one half's GEMM with
+    // the other half's state kernel on purpose (STGCN_RT_OVERLAP_MODE, STGCN_RT_OVERLAP_SMEM) does not pay.
+    const int nb0 = ((B / 2 + 127) / 128) * 128 < B ? ((B / 2 + 127) / 128) * 128 : B / 2;
+    cudaStream_t side = nullptr;
+    cudaEvent_t *ev = nullptr;
+    std::unique_lock<std::mutex> hold;
+    if (!ws.measuring() && rt_side_stream(&side, &ev, hold)) return 1;
+    size_t part[2];
+    for (int h = 0; h < 2; ++h) {
+      Bump wm(nullptr, 0);
+      if (rt_step_range(m, L, nullptr, nullptr, nullptr, nullptr, B, h ? nb0 : 0, h ? B - nb0 : nb0, all_gw, fifo16, wm,
+                        nullptr, 0))
+        return 1;
+      part[h] = (wm.peak + 255) & ~size_t(255);
+    }
+    char *w0 = ws.take<char>(part[0]), *w1 = ws.take<char>(part[1]);
+    if (!ws.measuring()) {
+      STGCN_REQUIRE(!ws.overflow, "rtstgcn_step: workspace too small (%zu B given)", ws.cap);
+      cudaEvent_t fork = ev[0], join = ev[1];
+      STGCN_CUDA_OK(cudaEventRecord(fork, st));
+      STGCN_CUDA_OK(cudaStreamWaitEvent(side, fork, 0));
+      Bump b0(w0, part[0]), b1(w1, part[1]);
+      const int cap = rt_overlap_smem_cap(), mode = rt_overlap_mode(), NL = m.num_layers;
+      // half 0, layer i: waits for half 1's GEMMs of layer i-1 (mode 2), records doneA[i];
+      // half 1, layer i: waits for doneA[i] (mode 2; mode 1: layer 0 only), records doneB[i] (mode 2).
+      // The two halves are ENQUEUED one after the other, so half 0 can only wait on events of half 1 that were
+      // recorded earlier in host order: enqueue layer by layer, alternating the halves.
+      cudaEvent_t *doneA = ev + 2, *doneB = ev + 2 + 64;
+      int rc = 0;
+      if (mode == 0) {
+        rc = rt_step_range(m, L, x, state, logits, top5, B, 0, nb0, all_gw, fifo16, b0, st, cap);
+        rc = rc || rt_step_range(m, L, x, state, logits, top5, B, nb0, B - nb0, all_gw, fifo16, b1, side, cap);
+      } else {
+        cudaEvent_t waitA[64] = {nullptr}, recA[64] = {nullptr}, waitB[64] = {nullptr}, recB[64] = {nullptr};
+        for (int i = 0; i < NL; ++i) {
+          if (mode == 2 || i == 0) { recA[i] = doneA[i]; waitB[i] = doneA[i]; }
+          if (mode == 2 && i + 1 < NL) { recB[i] = doneB[i]; waitA[i + 1] = doneB[i]; }
+        }
+        RtRangeCursor ca, cb;
+        rc = rt_step_range_begin(m, L, x, B, 0, nb0, all_gw, b0, st, ca) ||
+             rt_step_range_begin(m, L, x, B, nb0, B - nb0, all_gw, b1, side, cb);
+        for (int i = 0; i < NL && !rc; ++i) {
+          rc = rt_step_range_layer(m, L, state, B, all_gw, fifo16, b0, st, cap, ca, i, waitA[i], recA[i]) ||
+               rt_step_range_layer(m, L, state, B, all_gw, fifo16, b1, side, cap, cb, i, waitB[i], recB[i]);
+        }
+        rc = rc || rt_step_range_end(m, logits, top5, st, ca) || rt_step_range_end(m, logits, top5, side, cb);
+      }
+      cudaEventRecord(join, side);                           // always rejoin (also after an error, also under capture)
+      cudaStreamWaitEvent(st, join, 0);
+      if (rc) return 1;
+    }
   }
   if (!ws.measuring()) {
     k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(counter, 0, B, rt_counter_period(m));
