@@ -208,7 +208,11 @@ size_t rtstgcn_state_bytes(const stgcn_model_desc *m, int B);
 int rtstgcn_state_reset(const stgcn_model_desc *m, void *state, int B, int first, int count,
                         void *stream);
 size_t rtstgcn_step_workspace_bytes(const stgcn_model_desc *m, int B);
-/* One frame for every stream: x (B,in_feat,1,V) -> logits (B,num_classes). */
+/* One frame for every stream: x (B,in_feat,1,V) -> logits (B,num_classes).
+ * From 1024 streams on (STGCN_RT_OVERLAP) the streams are stepped as two halves, the second on an internal
+ * per-device stream forked from and joined back into `stream` with events; the call may be captured into a CUDA
+ * graph, but the first call on a device creates that stream, so make one un-captured call first (a warm-up
+ * launch is needed anyway for the kernels' function attributes). */
 int rtstgcn_step(const stgcn_model_desc *m, const float *x, void *state, float *logits, int B,
                  void *workspace, size_t workspace_bytes, void *stream);
 /* The same step, and top5 (B, 5) int32 = indices of the five largest logits of every stream, best
