@@ -106,6 +106,36 @@ def test_rt_4096_streams(pkg, syn, cuda, tag, math):
         assert err < TOL, err
 
 
+def test_rt_two_half_step_ragged_split(pkg, syn, cuda):
+    """From 1024 streams on the continual step runs as two halves of the streams on two CUDA streams.  1100
+    streams split 640 + 460 (ragged last 128-row tiles in both halves): streams on both sides of the split, the
+    per-stream reset of one stream in each half, and the fused top-5, against the oracle's continual loop."""
+    m, sd, ocfg, cfg = _rt(pkg, syn, cuda, 'bf16x3', {})
+    B, L, c, v = 1100, 22, cfg['in_feat'], cfg['graph']['num_node']
+    pick = [0, 639, 640, 641, 1099]
+    g = torch.Generator().manual_seed(7)
+    xs = torch.randn(len(pick), c, L, v, generator=g)
+    outs, tops = [], []
+    for t in range(L):
+        frame = torch.randn(B, c, 1, v, generator=g)
+        frame[pick] = xs[:, :, t:t + 1]
+        logits, top5 = m.step_top5(frame.to(cuda))
+        outs.append(logits[pick].cpu())
+        tops.append(top5[pick].cpu())
+    out = torch.cat(outs, dim=2)
+    ref = O.rt_model_run(xs, sd, ocfg)
+    assert rel_err(out, ref) < TOL, rel_err(out, ref)
+    assert torch.equal(torch.stack(tops, dim=2)[:, 0].long(), out.argmax(1))
+    # restart streams 639 and 640 only: they replay the trial from frame 0, the others continue
+    m.reset_streams(639, 2)
+    outs = []
+    for t in range(6):
+        frame = torch.randn(B, c, 1, v, generator=g)
+        frame[[639, 640]] = xs[1:3, :, t:t + 1]
+        outs.append(m.step(frame.to(cuda))[[639, 640]].cpu())
+    assert rel_err(torch.cat(outs, dim=2), ref[1:3, :, :6]) < TOL
+
+
 @pytest.mark.parametrize('tag,math', [('pku', 'bf16x3'), ('imu', 'bf16')])
 def test_rt_long_horizon_1000_frames(pkg, syn, cuda, tag, math):
     """the online layer keeps a running sum, acc += z_t - z_{t-F}; 1000 frames (the frame
