@@ -4,6 +4,8 @@
 #include <atomic>
 #include <mutex>
 #include <cstdarg>
+#include <cstdlib>
+#include <utility>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -118,6 +120,40 @@ struct ProfScope {
   do {                                                                                    \
     if (!(cond)) return ::stgcn::fail(__VA_ARGS__);                                       \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// A kernel launched with launch_pdl may be scheduled while the previous kernel of the stream is still running: its
+// CTAs become resident and run their prologue (barrier init, TMEM allocation, static tables, weight prefetch), and
+// block in griddep_wait() until the previous kernel has completed and its writes are visible.  Rules kept by every
+// kernel that is launched this way: (1) no global access to data another kernel of the chain writes before
+// griddep_wait(); (2) griddep_launch() only AFTER griddep_wait(), so at most two kernels of a chain are in flight
+// and code before a wait can only race with the immediate predecessor.  Launched without the attribute (or with
+// STGCN_PDL=0) both instructions are no-ops.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_PDL");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Bump allocator over a caller-owned workspace.  With base == nullptr it only
 // measures, so *_workspace_bytes() and the forward share one code path.

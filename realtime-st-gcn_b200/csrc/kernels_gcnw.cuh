@@ -315,6 +315,10 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
     // ---- A producer: for every edge of the item's joint, the source joint's 128 frames, per 64-channel
     // chunk and plane ----
     if (lane == 0) {
+      // the activations are the only operand another kernel of the chain writes (weights, tables and bias are
+      // prepared once): everything else of this CTA -- weight stages included -- is already in flight
+      griddep_wait();
+      griddep_launch();
       int as = 0, a_ph = 0;
       const bool tap = p.tmode == 1;     // ring-tap mode: tensor-map dimension 1 = rows, 2 = ring slots
       const bool tmp = p.tmode == 2;     // temporal mode: same joint, frame offset per tap, even / odd maps
@@ -1095,7 +1099,8 @@ int launch_gcnw_c(const __nv_bfloat16 *x, const __nv_bfloat16 *wsc, GcnwParams p
     STGCN_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_gcnw<CO, MERGE, FUSE>), dim3(grid),
                                               dim3(kGwThreads + 32 + kGwLnThreads), args, (size_t)smem, st));
   } else {
-    k_gcnw<CO, MERGE, FUSE><<<grid, kGwThreads, smem, st>>>(tm_x, tm_x1, tm_w, tm_z, p);
+    STGCN_CUDA_OK(launch_pdl(k_gcnw<CO, MERGE, FUSE>, dim3(grid), dim3(kGwThreads), (size_t)smem, st, tm_x, tm_x1, tm_w,
+                             tm_z, p));
   }
   return 0;
 }

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) 
     tc::fence_barrier_init();
   }
   __syncthreads();
+  griddep_wait();                       // z, state and counters come from earlier kernels of the chain
+  if (tid == 0) griddep_launch();
 
   if (tid >= TH) {
     // ---- producer warp: one lane streams the chunks of this CTA's streams into the stage ring ----
@@ -255,7 +257,7 @@ int launch_rt_stream_t(const RtUpdateArgs &a, cudaStream_t st) {
   long long grid = (long long)tc::num_sms() * per_sm;
   if (grid > a.B) grid = a.B;
   STGCN_CUDA_OK(cudaFuncSetAttribute(k_rt_stream<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_rt_stream<TH><<<(unsigned)grid, TH + 32, smem, st>>>(a);
+  STGCN_CUDA_OK(launch_pdl(k_rt_stream<TH>, dim3((unsigned)grid), dim3(TH + 32), (size_t)smem, st, a));
   return 0;
 }
 

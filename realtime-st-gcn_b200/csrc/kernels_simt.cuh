@@ -703,6 +703,8 @@ __global__ void __launch_bounds__(256)
               int spb) {
   extern __shared__ float s_pool[];                       // [spb][C] + [spb][classes]; spb streams per block
   float *s_log = s_pool + spb * C;
+  griddep_wait();
+  griddep_launch();
   const int b0 = blockIdx.x * spb;
   const int nb = B - b0 < spb ? B - b0 : spb;
   const float inv_v = 1.f / (float)V;
@@ -832,6 +834,8 @@ __global__ void __launch_bounds__(256) k_topk5(const float *__restrict__ logits,
 // (the kernels only use cnt % F and cnt % S), so they never overflow on a long-running stream;
 // period == 0: plain increment
 __global__ void k_advance_counters(int *counter, int first, int count, int period) {
+  griddep_wait();
+  griddep_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) {
     int c = counter[first + i] + 1;
@@ -1079,6 +1083,8 @@ __global__ void __launch_bounds__(256) k_embed_warp(EmbedWarpArgs p) {
   for (int i = threadIdx.x; i < p.C0 * p.C_in; i += blockDim.x) sw[i] = p.W[i];
   for (int i = threadIdx.x; i < p.C0; i += blockDim.x) sb[i] = p.bias[i];
   __syncthreads();
+  griddep_wait();                                 // the input frames (and the output buffer's previous readers)
+  griddep_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // C_in == 3 and 32 % (C0/4) == 0 (the shipped trunks: 3 -> 64): a lane always produces the same four
   // output channels, so its weights live in registers and the inner product needs no shared-memory reads

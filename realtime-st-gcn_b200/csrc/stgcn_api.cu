@@ -1123,7 +1123,7 @@ int embed(const stgcn_model_desc &m, const float *x, float *h0, int N, int T, Bu
     long long blocks = (frames + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     ProfScope ps(KC_EMBED, st);
-    k_embed_warp<<<(unsigned)blocks, 256, smem, st>>>(e);
+    STGCN_CUDA_OK(launch_pdl(k_embed_warp, dim3((unsigned)blocks), dim3(256), smem, st, e));
     STGCN_LAUNCH_OK();
     return 0;
   }
@@ -1555,9 +1555,10 @@ int rt_step_range_end(const stgcn_model_desc &m, float *logits, int *top5, cudaS
   const int V = m.num_joints, c_last = m.layers[m.num_layers - 1].c_out;
   ProfScope ps(KC_POOL, st);
   const int spb = rt_head_streams(c.nb);
-  k_rt_head<<<cdiv(c.nb, spb), 256, sizeof(float) * spb * (c_last + m.num_classes), st>>>(
-      c.buf[c.cur], c.nb, V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits + (size_t)c.b0 * m.num_classes,
-      top5 ? top5 + (size_t)c.b0 * 5 : nullptr, spb);
+  STGCN_CUDA_OK(launch_pdl(k_rt_head, dim3(cdiv(c.nb, spb)), dim3(256),
+                           sizeof(float) * spb * (c_last + m.num_classes), st, (const float *)c.buf[c.cur], c.nb, V,
+                           c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits + (size_t)c.b0 * m.num_classes,
+                           top5 ? top5 + (size_t)c.b0 * 5 : (int *)nullptr, spb));
   STGCN_LAUNCH_OK();
   return 0;
 }
@@ -1717,7 +1718,8 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     }
   }
   if (!ws.measuring()) {
-    k_advance_counters<<<cdiv(B, 256), 256, 0, st>>>(counter, 0, B, rt_counter_period(m));
+    STGCN_CUDA_OK(launch_pdl(k_advance_counters, dim3(cdiv(B, 256)), dim3(256), (size_t)0, st, counter, 0, B,
+                             rt_counter_period(m)));
     STGCN_LAUNCH_OK();
   }
   return 0;
