@@ -318,7 +318,6 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
       // the activations are the only operand another kernel of the chain writes (weights, tables and bias are
       // prepared once): everything else of this CTA -- weight stages included -- is already in flight
       griddep_wait();
-      griddep_launch();
       int as = 0, a_ph = 0;
       const bool tap = p.tmode == 1;     // ring-tap mode: tensor-map dimension 1 = rows, 2 = ring slots
       const bool tmp = p.tmode == 2;     // temporal mode: same joint, frame offset per tap, even / odd maps
@@ -358,6 +357,10 @@ __global__ void __launch_bounds__(kGwThreads + (FUSE ? 32 + kGwLnThreads : 0), F
           }
         }
       }
+      // this CTA's last activation loads are issued: what remains is the tail of the pipeline, under which the
+      // next kernel's CTAs may become resident (triggering at the start keeps them resident -- and, measured,
+      // slowing this kernel -- for its whole duration)
+      griddep_launch();
     }
   } else if (warp == 2) {
     // ---- B producer: the edge's pre-scaled weight tiles (hi, lo for an A hi stage; hi for an A lo stage) ----
@@ -741,6 +744,8 @@ struct LnStreamArgs {
 template <int NV>
 __global__ void __launch_bounds__(256, 2) k_ln_stream(LnStreamArgs p) {
   __shared__ float s_red[32];
+  griddep_wait();                                            // z comes from the GEMM launched just before
+  griddep_launch();
   const long long f = blockIdx.x;
   const int VC4 = (p.V * p.C) >> 2, C4 = p.C >> 2;
   const bool c4_pow2 = (C4 & (C4 - 1)) == 0;
@@ -836,6 +841,8 @@ __global__ void __launch_bounds__(256, 2) k_ln_stream(LnStreamArgs p) {
 template <int NV>
 __global__ void __launch_bounds__(256) k_ln_warp(LnStreamArgs p) {
   const int lane = threadIdx.x & 31;
+  griddep_wait();
+  griddep_launch();
   const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (f >= p.frames) return;
   const int VC4 = (p.V * p.C) >> 2, C4 = p.C >> 2;
@@ -954,12 +961,13 @@ inline int launch_ln_stream(const LnStreamArgs &a, cudaStream_t st) {
   const int vc4 = a.V * a.C / 4, c4 = a.C / 4;
   if ((c4 & (c4 - 1)) == 0 && vc4 <= ln_warp_limit()) {
     const unsigned blocks = (unsigned)((a.frames + 7) / 8);
-    if (vc4 <= 32 * 13) { k_ln_warp<13><<<blocks, 256, 0, st>>>(a); return 0; }
-    if (vc4 <= 32 * 25) { k_ln_warp<25><<<blocks, 256, 0, st>>>(a); return 0; }
+    if (vc4 <= 32 * 13) { STGCN_CUDA_OK(launch_pdl(k_ln_warp<13>, dim3(blocks), dim3(256), (size_t)0, st, a)); return 0; }
+    if (vc4 <= 32 * 25) { STGCN_CUDA_OK(launch_pdl(k_ln_warp<25>, dim3(blocks), dim3(256), (size_t)0, st, a)); return 0; }
   }
-  if (nv <= 2) k_ln_stream<2><<<(unsigned)a.frames, 256, 0, st>>>(a);
-  else if (nv <= 4) k_ln_stream<4><<<(unsigned)a.frames, 256, 0, st>>>(a);
-  else if (nv <= 7) k_ln_stream<7><<<(unsigned)a.frames, 256, 0, st>>>(a);
+  const dim3 grid((unsigned)a.frames), block(256);
+  if (nv <= 2) STGCN_CUDA_OK(launch_pdl(k_ln_stream<2>, grid, block, (size_t)0, st, a));
+  else if (nv <= 4) STGCN_CUDA_OK(launch_pdl(k_ln_stream<4>, grid, block, (size_t)0, st, a));
+  else if (nv <= 7) STGCN_CUDA_OK(launch_pdl(k_ln_stream<7>, grid, block, (size_t)0, st, a));
   else return fail("ln stream: V*C = %d too large", a.V * a.C);
   return 0;
 }

@@ -87,7 +87,6 @@ __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) 
   }
   __syncthreads();
   griddep_wait();                       // z, state and counters come from earlier kernels of the chain
-  if (tid == 0) griddep_launch();
 
   if (tid >= TH) {
     // ---- producer warp: one lane streams the chunks of this CTA's streams into the stage ring ----
@@ -123,6 +122,7 @@ __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) 
           if (++s == kRtStages) { s = 0; ph ^= 1u; }
         }
       }
+      griddep_launch();                 // last copies issued: the next kernel may move in under this CTA's tail
     }
     return;
   }
