@@ -264,6 +264,19 @@ def rt_latency(pkg, dev, streams, steps, graph_kw, math, hbm_gbs=None, cuda_grap
         ev[i][1].record()
     torch.cuda.synchronize()
     p50, p90 = _p50([a.elapsed_time(b) for a, b in ev])
+    # the same captured step replayed back to back (no Python / copy / clone between the steps): what the device
+    # needs per step -- at one stream the per-call figure above is mostly the host issuing three operations
+    device_ms = None
+    g = getattr(m, '_graph', None)
+    if cuda_graph and g is not None:
+        reps = 200
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g['graph'].replay()
+        b.record()
+        torch.cuda.synchronize()
+        device_ms = a.elapsed_time(b) / reps
     desc, _ = m._descriptor()
     # state traffic per stream-frame = read oldest FIFO slot, write it, read + write the accumulator
     fifo16 = lib.rtstgcn_state_bytes(ctypes.byref(desc), streams) < 0.9 * streams * sum(
@@ -271,7 +284,7 @@ def rt_latency(pkg, dev, streams, steps, graph_kw, math, hbm_gbs=None, cuda_grap
         for i in range(len(cfg['rt-st-gcn']['out_ch'])))
     per_elem = (2 + 2 + 4 + 4) if fifo16 else 16
     state_bytes = per_elem * sum(cfg['rt-st-gcn']['out_ch']) * v * streams
-    out = {"streams": streams, "p50_ms": p50, "p90_ms": p90,
+    out = {"streams": streams, "p50_ms": p50, "p90_ms": p90, "device_ms_back_to_back": device_ms,
            "stream_frames_per_s": streams / (p50 * 1e-3), "cuda_graph": bool(cuda_graph),
            "state_layout": "bf16 FIFO + fp32 accumulator" if fifo16 else "fp32 FIFO + fp32 accumulator",
            "state_gb_per_step": state_bytes / 1e9, "achieved_gbs": state_bytes / (p50 * 1e-3) / 1e9}

@@ -29,7 +29,10 @@ constexpr int kMaxLayers = 16;
 constexpr int kRowsPerWarp = 4;   // output rows a warp accumulates at once (register tile)
 constexpr int kChunk = 32;        // input channels per staged weight chunk
 constexpr int kWPitch = kChunk + 4;  // floats per staged weight row (+4: conflict-free fragment loads)
-constexpr int kStages = 3;        // weight-chunk ring depth (cp.async, two chunks in flight)
+#ifndef STGCN_RTS_STAGES
+#define STGCN_RTS_STAGES 3   // 3 / 5 / 8 measured: 0.150 / 0.150 / 0.148 ms per 1-stream step (not the bound)
+#endif
+constexpr int kStages = STGCN_RTS_STAGES;   // weight-chunk ring depth (cp.async, kStages - 1 chunks in flight)
 constexpr int kCsrPtrMax = 128;   // K*V + 1 row pointers staged in shared memory
 constexpr int kCsrNnzMax = 256;   // adjacency non-zeros staged in shared memory (tree graphs: ~3V)
 
@@ -49,6 +52,7 @@ __device__ unsigned long long g_dbg[8];
 struct Params {
   int num_layers, V, K, in_feat, num_classes, B, c_max, debug;
   int period;                                 // frame counters wrap at this value (0: never)
+  int single_pass;                            // math = bf16: one TF32 product instead of the 3xTF32 split
   float eps;
   const float *x;                             // (B, in_feat, 1, V)
   float *logits;                              // (B, num_classes)
@@ -65,6 +69,11 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
   const float r = x - __uint_as_float(hi);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -91,8 +100,9 @@ inline size_t smem_floats(int c_max, int V, int K) {
   const size_t cv = (size_t)c_max * V;
   const size_t ys = (size_t)(K + 1) * (c_max / kNC) * V;
   const size_t wr = (size_t)kStages * (K + 1) * (c_max / kNC) * kWPitch;  // weight-chunk ring
+  const size_t stage = 2 * (size_t)(c_max / kNC) * V;      // this CTA's normalised slice, per layer parity
   return 2 * cv /* x ping-pong */ + ys + wr + 2 * kNC * 4 /* stats */ + 64 +
-         kCsrPtrMax + 2 * kCsrNnzMax;
+         kCsrPtrMax + 2 * kCsrNnzMax + stage + 4 /* mbarrier */;
 }
 
 __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_small(const __grid_constant__ Params p) {
@@ -111,6 +121,12 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
   float *red = stats + 2 * kNC * 4;
   int *s_ptr = reinterpret_cast<int *>(red + 64);                // [kCsrPtrMax]
   int2 *s_va = reinterpret_cast<int2 *>(s_ptr + kCsrPtrMax);      // [kCsrNnzMax]
+  float *xstage = reinterpret_cast<float *>(s_va + kCsrNnzMax);   // [2][c_max/kNC][V]: slice on its way to the peers
+  const uint32_t xbar = tc::smem_u32(xstage + 2 * (size_t)(p.c_max / kNC) * V);   // "next layer's input complete"
+  if (tid == 0) {
+    tc::mbar_init(xbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   const int cnt = p.counter[b];
   const bool dbg = (p.debug & 4) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
@@ -155,8 +171,8 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
     asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty) group keeps the count uniform
     ++issued;
   };
-  issue_next();
-  issue_next();
+#pragma unroll
+  for (int i = 0; i < kStages - 1; ++i) issue_next();
   int consumed = 0;
 
   // ---- input stage (every CTA, redundantly): LayerNorm over (in_feat, V), then fcn_in ----
@@ -233,6 +249,7 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
     const int g = lane >> 2, tq = lane & 3;
     const int jr = warp * 16;
     const bool active = jr < rows;
+    const int NT = (V + 7) >> 3;
     float dacc[4][4];
     {
       float bias0 = 0.f, bias1 = 0.f;
@@ -246,29 +263,52 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
     }
     lap(1);
     for (int ch = 0; ch < L.c_in / kChunk; ++ch) {
-      issue_next();                                             // chunk consumed + 2
+      issue_next();                                             // chunk consumed + kStages - 1
       lap(6);
-      asm volatile("cp.async.wait_group 2;" ::: "memory");      // chunk `consumed` has landed (this thread's part)
+      asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");   // chunk `consumed` has landed (this thread's part)
       __syncthreads();                                          // ... and everybody else's
       lap(7);
       if (active) {
         const float *wst = wring + (size_t)(consumed % kStages) * stage_floats + (jr + g) * kWPitch + tq;
         const float *xc = x + (size_t)(ch * kChunk + tq) * V + g;
+        if (p.single_pass) {
+          // math = bf16: one TF32 product (2^-11 operands, inside the mode's stated 2e-2 tolerance)
 #pragma unroll
-        for (int k0 = 0; k0 < kChunk; k0 += 8) {
-          uint32_t ah[4], al[4];
-          split_tf32(wst[k0], ah[0], al[0]);
-          split_tf32(wst[8 * kWPitch + k0], ah[1], al[1]);
-          split_tf32(wst[k0 + 4], ah[2], al[2]);
-          split_tf32(wst[8 * kWPitch + k0 + 4], ah[3], al[3]);
+          for (int k0 = 0; k0 < kChunk; k0 += 8) {
+            uint32_t ah[4];
+            ah[0] = to_tf32(wst[k0]);
+            ah[1] = to_tf32(wst[8 * kWPitch + k0]);
+            ah[2] = to_tf32(wst[k0 + 4]);
+            ah[3] = to_tf32(wst[8 * kWPitch + k0 + 4]);
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            uint32_t bh[2], bl[2];
-            split_tf32(xc[k0 * V + nt * 8], bh[0], bl[0]);
-            split_tf32(xc[(k0 + 4) * V + nt * 8], bh[1], bl[1]);
-            mma_tf32(dacc[nt], al, bh);
-            mma_tf32(dacc[nt], ah, bl);
-            mma_tf32(dacc[nt], ah, bh);
+            for (int nt = 0; nt < 4; ++nt) {
+              if (nt < NT) {
+                uint32_t bh[2];
+                bh[0] = to_tf32(xc[k0 * V + nt * 8]);
+                bh[1] = to_tf32(xc[(k0 + 4) * V + nt * 8]);
+                mma_tf32(dacc[nt], ah, bh);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k0 = 0; k0 < kChunk; k0 += 8) {
+            uint32_t ah[4], al[4];
+            split_tf32(wst[k0], ah[0], al[0]);
+            split_tf32(wst[8 * kWPitch + k0], ah[1], al[1]);
+            split_tf32(wst[k0 + 4], ah[2], al[2]);
+            split_tf32(wst[8 * kWPitch + k0 + 4], ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              if (nt < NT) {                                          // 8-joint column tiles that hold joints
+                uint32_t bh[2], bl[2];
+                split_tf32(xc[k0 * V + nt * 8], bh[0], bl[0]);
+                split_tf32(xc[(k0 + 4) * V + nt * 8], bh[1], bl[1]);
+                mma_tf32(dacc[nt], al, bh);
+                mma_tf32(dacc[nt], ah, bl);
+                mma_tf32(dacc[nt], ah, bh);
+              }
+            }
           }
         }
       }
@@ -365,7 +405,16 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
     const float inv_nm1 = 1.f / (float)(L.c_out * V - 1);
     const float rstd_o = 1.f / sqrtf(M2o * inv_nm1 + p.eps);
     const float rstd_r = 1.f / sqrtf(M2r * inv_nm1 + p.eps);
+    // The slice [Cs][V] is contiguous in every CTA's copy of the next input: it is staged locally and sent to
+    // each CTA of the cluster with ONE bulk shared::cta -> shared::cluster copy that completes on the
+    // receiver's mbarrier -- no per-element remote stores (they were uncoalesced 4-byte DSMEM writes, 8 per
+    // value) and no second cluster barrier.  Re-use is safe without further synchronisation: a peer sends
+    // layer l+1 only after exchange 1 of layer l+1, i.e. after every CTA has finished layer l, and the staging
+    // slot of a parity is rewritten two layers later, when all receivers have seen this layer's bytes.
     float *xn = xbuf[cur ^ 1];
+    float *stg = xstage + (size_t)par * (p.c_max / kNC) * V;
+    const uint32_t slice_bytes = (uint32_t)(Cs * V * sizeof(float));
+    if (tid == 0) tc::mbar_expect_tx(xbar, kNC * slice_bytes);
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int idx = tid + it * kThreads;
@@ -375,11 +424,23 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
         float y = fmaxf((oreg[it] - mean_o) * rstd_o * g1[it] + b1[it], 0.f);                 // bn_relu
         if (L.residual == 1) y = fmaxf(y + x[at], 0.f);
         else if (res_conv) y = fmaxf(y + (rreg[it] - mean_r) * rstd_r * gr[it] + br[it], 0.f);
-#pragma unroll
-        for (int rk = 0; rk < kNC; ++rk) cluster.map_shared_rank(xn, rk)[at] = y;
+        stg[cl * V + w] = y;
       }
     }
-    cluster.sync();                                       // exchange 2: the next layer's input is complete
+    tc::fence_proxy_async();                              // generic writes of the slice -> async-proxy reads
+    __syncthreads();
+    if (tid < kNC) {
+      const uint32_t src = tc::smem_u32(stg);
+      const uint32_t dst_local = tc::smem_u32(xn + (size_t)c0 * V);
+      uint32_t dst, bar;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"(tid));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(xbar), "r"(tid));
+      asm volatile(
+          "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+          "r"(src), "r"(slice_bytes), "r"(bar)
+          : "memory");
+    }
+    tc::mbar_wait(xbar, (uint32_t)(l & 1));               // all eight slices of the next input have landed here
     cur ^= 1;
     lap(4);
   }

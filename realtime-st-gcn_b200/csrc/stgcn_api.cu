@@ -1411,6 +1411,7 @@ bool rt_small_supported(const stgcn_model_desc &m, int B) {
     const stgcn_layer_desc &d = m.layers[i];
     if (d.rt != 1 || d.norm != STGCN_NORM_LAYERNORM || d.a_per_sample) return false;
     if (d.c_out % rts::kNC || d.c_in % rts::kChunk) return false;
+    if (((d.c_out / rts::kNC) * m.num_joints) % 4) return false;        // a CTA's slice travels as one 16-byte-granular bulk copy
     if (m.num_joints * (d.c_out / rts::kNC) > 4 * rts::kThreads) return false;
     if ((m.partitions + 1) * (d.c_out / rts::kNC) > 128) return false;   // rows per CTA (register tile bound)
     c_max = d.c_out > c_max ? d.c_out : c_max;
@@ -1585,6 +1586,7 @@ int rt_step(const stgcn_model_desc &m, const float *x, void *state, float *logit
     P.num_layers = m.num_layers; P.V = V; P.K = K; P.in_feat = m.in_feat; P.num_classes = m.num_classes; P.B = B;
     P.eps = kEps;
     P.period = rt_counter_period(m);
+    P.single_pass = m.math == STGCN_MATH_BF16 ? 1 : 0;
     P.x = x; P.logits = logits;
     P.norm_in_w = m.norm_in_w; P.norm_in_b = m.norm_in_b;
     P.fcn_in_w = m.fcn_in_w; P.fcn_in_b = m.fcn_in_b;

@@ -52,6 +52,15 @@ def main():
         state_bytes = 4 * sum_cout * v * 4 * b
         line = "streams=%d math=%s graph=%s p50=%.4f ms p90=%.4f ms  state %.3f GB/step -> %.1f GB/s" % (
             b, a.math, a.cuda_graph, p50, ms[int(len(ms) * 0.9)], state_bytes / 1e9, state_bytes / p50 / 1e6)
+        g = getattr(m, '_graph', None)
+        if a.cuda_graph and g is not None:                 # the captured step replayed back to back
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(200):
+                g['graph'].replay()
+            e1.record()
+            torch.cuda.synchronize()
+            line += "  back-to-back %.4f ms" % (e0.elapsed_time(e1) / 200)
         if a.profile and not a.cuda_graph:
             n = len(pkg._lib.KERNEL_CLASSES)
             cms, cn = (ctypes.c_float * n)(), (ctypes.c_longlong * n)()
