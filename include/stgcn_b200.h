@@ -34,7 +34,7 @@ enum { STGCN_NORM_LAYERNORM = 0, STGCN_NORM_BATCHNORM = 1 };
 enum { STGCN_RES_NONE = 0, STGCN_RES_IDENTITY = 1, STGCN_RES_CONV = 2 };
 /* arithmetic of the GEMM stages */
 enum {
-  STGCN_MATH_FP32 = 0,      /* fp32 CUDA-core FMA (exact reference arithmetic); the <= 16-stream
+  STGCN_MATH_FP32 = 0,      /* fp32 CUDA-core FMA (exact reference arithmetic); the <= 14-stream
                                continual step (one cluster kernel) uses 3xTF32 MMAs instead   */
   STGCN_MATH_BF16X3 = 1,    /* tcgen05 bf16 hi/lo split, 3 MMAs, fp32 accumulate (1e-4) */
   STGCN_MATH_BF16 = 2       /* tcgen05 single bf16 MMA, fp32 accumulate                 */

@@ -1400,7 +1400,9 @@ int rt_counter_period(const stgcn_model_desc &m) {
 }
 
 // few streams: the whole step as one cluster kernel (kernels_rt_small.cuh)
-constexpr int kSmallBatchMax = 16;
+// measured (back-to-back replays): 0.123-0.125 ms for 1..14 streams, 0.244 ms at 16 (the clusters no longer all
+// run at once); the batched path takes 0.19-0.20 ms from 2 to 17 streams
+constexpr int kSmallBatchMax = 14;
 bool rt_small_supported(const stgcn_model_desc &m, int B) {
   if (m.reserved & 1) return false;                      // caller opted out (tests of the batched path)
   if (B > kSmallBatchMax || m.num_layers > rts::kMaxLayers || m.num_joints > 32) return false;

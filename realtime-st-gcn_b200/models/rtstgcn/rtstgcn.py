@@ -61,7 +61,7 @@ class Model(nn.Module):
         self._state_streams = 0
         self._graph_on = False
         self._graph = None
-        # few streams (<= 16): run the whole step as ONE cluster kernel (csrc/kernels_rt_small.cuh)
+        # few streams (<= 14): run the whole step as ONE cluster kernel (csrc/kernels_rt_small.cuh)
         self.small_batch_kernel = kwargs.get('small_batch_kernel', True)
 
     def _layer_kwargs(self, i, num_joints):

@@ -518,7 +518,7 @@ def test_tsplit_emulated_ranks(pkg, syn, cuda, world, total_frames, math, tol):
 # ------------------------------------------------------------------ few-streams cluster kernel
 @pytest.mark.parametrize('tag', ['pku', 'imu'])
 def test_rt_small_batch_cluster_kernel(pkg, syn, cuda, tag):
-    """Latency path (<= 16 streams): the whole continual step in one thread-block-cluster kernel
+    """Latency path (<= 14 streams): the whole continual step in one thread-block-cluster kernel
     (fp32 FMA, distributed-shared-memory exchange per layer) vs the reference's own loop."""
     m, x, ref = _rt_case(pkg, syn, cuda, tag, 'bf16x3', small=True)
     lib = pkg._lib.load()
