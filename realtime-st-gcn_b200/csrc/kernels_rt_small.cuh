@@ -243,20 +243,13 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
     // ---- (a) this CTA's rows of the 1x1 feature transform (+ residual conv): y[j][v] ----
     // A 25-row problem cannot fill a 128-row tcgen05 tile; the shape that fits is the transposed
     // product on warp-level MMAs: D[row j][joint v] = W[j][ci] * x[ci][v], m16n8k8 TF32 with the
-    // 3xTF32 split (fp32 parity).  A warp owns a 16-row tile (<= 128 rows per CTA) and one, two or all four
+    // 3xTF32 split (fp32 parity).  Warp w owns rows 16w..16w+15 (<= 128 rows per CTA) and all four
     // 8-joint column tiles; A fragments come from the staged weight chunk, B fragments from the
     // fp32 activations in shared memory, both split into (hi, lo) on the fly.
-    // Row tiles are spread over the eight warps together with the column tiles: 64-channel layers have only
-    // 24-32 rows per CTA (2 row tiles), so four warps share a row tile and take one column tile each; 128-channel
-    // layers (3-4 row tiles): two warps per row tile, two column tiles each; 256 channels: one warp per row tile.
     const int g = lane >> 2, tq = lane & 3;
-    const int RT = (rows + 15) >> 4;
-    const int wpr = RT <= 2 ? 4 : (RT <= 4 ? 2 : 1);          // warps per row tile
-    const int ntw = 4 / wpr;                                  // column tiles per warp
-    const int nt0 = (warp % wpr) * ntw;                       // this warp's first column tile
-    const int jr = (warp / wpr) * 16;
+    const int jr = warp * 16;
+    const bool active = jr < rows;
     const int NT = (V + 7) >> 3;
-    const bool active = jr < rows && nt0 < NT;
     float dacc[4][4];
     {
       float bias0 = 0.f, bias1 = 0.f;
@@ -288,13 +281,12 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
             ah[2] = to_tf32(wst[k0 + 4]);
             ah[3] = to_tf32(wst[8 * kWPitch + k0 + 4]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int nt = nt0 + i;
-              if (i < ntw && nt < NT) {
+            for (int nt = 0; nt < 4; ++nt) {
+              if (nt < NT) {
                 uint32_t bh[2];
                 bh[0] = to_tf32(xc[k0 * V + nt * 8]);
                 bh[1] = to_tf32(xc[(k0 + 4) * V + nt * 8]);
-                mma_tf32(dacc[i], ah, bh);
+                mma_tf32(dacc[nt], ah, bh);
               }
             }
           }
@@ -307,15 +299,14 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
             split_tf32(wst[k0 + 4], ah[2], al[2]);
             split_tf32(wst[8 * kWPitch + k0 + 4], ah[3], al[3]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int nt = nt0 + i;
-              if (i < ntw && nt < NT) {                               // 8-joint column tiles that hold joints
+            for (int nt = 0; nt < 4; ++nt) {
+              if (nt < NT) {                                          // 8-joint column tiles that hold joints
                 uint32_t bh[2], bl[2];
                 split_tf32(xc[k0 * V + nt * 8], bh[0], bl[0]);
                 split_tf32(xc[(k0 + 4) * V + nt * 8], bh[1], bl[1]);
-                mma_tf32(dacc[i], al, bh);
-                mma_tf32(dacc[i], ah, bl);
-                mma_tf32(dacc[i], ah, bh);
+                mma_tf32(dacc[nt], al, bh);
+                mma_tf32(dacc[nt], ah, bl);
+                mma_tf32(dacc[nt], ah, bh);
               }
             }
           }
@@ -326,16 +317,16 @@ __global__ void __cluster_dims__(kNC, 1, 1) __launch_bounds__(kThreads, 1) k_rt_
     }
     if (active) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int col = (nt0 + i) * 8 + 2 * tq;
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = nt * 8 + 2 * tq;
         const int ja = jr + g, jb = jr + g + 8;
-        if (i < ntw && col < V) {
-          if (ja < rows) ybuf[ja * V + col] = dacc[i][0];
-          if (jb < rows) ybuf[jb * V + col] = dacc[i][2];
+        if (col < V) {
+          if (ja < rows) ybuf[ja * V + col] = dacc[nt][0];
+          if (jb < rows) ybuf[jb * V + col] = dacc[nt][2];
         }
-        if (i < ntw && col + 1 < V) {
-          if (ja < rows) ybuf[ja * V + col + 1] = dacc[i][1];
-          if (jb < rows) ybuf[jb * V + col + 1] = dacc[i][3];
+        if (col + 1 < V) {
+          if (ja < rows) ybuf[ja * V + col + 1] = dacc[nt][1];
+          if (jb < rows) ybuf[jb * V + col + 1] = dacc[nt][3];
         }
       }
     }
