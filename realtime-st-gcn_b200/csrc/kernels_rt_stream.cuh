@@ -66,6 +66,7 @@ template <int TH>
 __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) k_rt_stream(const RtUpdateArgs p) {
   extern __shared__ __align__(128) uint8_t rt_smem[];
   __shared__ float s_red[32];
+  __shared__ float4 s_pool[TH];                       // pool_out: per-thread sums over this thread's joints
   __shared__ __align__(8) unsigned long long s_bar[2 * kRtStages];
   const int tid = threadIdx.x;
   const int n = p.V * p.C, n4 = n >> 2, C4 = p.C >> 2;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) 
     const float rstd = 1.f / sqrtf(rt_block_sum<TH>(q, s_red) * inv_nm1 + p.eps);
     if (p.res_mode == 2) rstd_r = 1.f / sqrtf(rt_block_sum<TH>(qr, s_red) * inv_nm1 + p.eps);
     // ---- pass 3: out = relu( relu(LN(acc)) + res ) ----
+    float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < kRtMaxChunks; ++c)
       if (c < nch && c * TH + tid < n4) {
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) 
           v.w += (r.w - mean_r) * rstd_r * rg.w + ro.w;
         }
         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        psum.x += v.x; psum.y += v.y; psum.z += v.z; psum.w += v.w;
         if (p.out) *reinterpret_cast<float4 *>(p.out + base + 4 * i) = v;
         if (p.out_hi) {
           const uint2 h = f4_to_bf16x4(v);
@@ -238,19 +241,41 @@ __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) 
           }
         }
       }
+    if (p.pool_out) {
+      // mean over the joints (the model's AvgPool2d((1, V)), rtstgcn.py:127): TH is a multiple of C/4, so a thread's
+      // float4 always belongs to channel group tid % (C/4); the TH / (C/4) partial sums of a group are added in a
+      // fixed order.  The next stream's first block reduction separates these reads from the next writes.
+      s_pool[tid] = psum;
+      asm volatile("bar.sync 1, %0;" ::"n"(TH) : "memory");
+      if (tid < C4) {
+        float4 t = s_pool[tid];
+        for (int k = C4; k < TH; k += C4) {
+          const float4 u = s_pool[tid + k];
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        const float inv_v = 1.f / (float)p.V;
+        *reinterpret_cast<float4 *>(p.pool_out + (long long)b * p.C + 4 * tid) =
+            make_float4(t.x * inv_v, t.y * inv_v, t.z * inv_v, t.w * inv_v);
+      }
+    }
   }
 }
+// pooled output needs every thread to stay on one channel group across its chunks
+inline bool rt_stream_pool_supported(int V, int C);
 
 inline int rt_stream_threads(int V, int C) {
   const int n4 = V * C / 4;
   return n4 <= 128 * kRtMaxChunks ? 128 : (n4 <= 256 * kRtMaxChunks ? 256 : 512);
 }
 inline bool rt_stream_supported(int V, int C) { return C % 8 == 0 && V * C / 4 <= 512 * kRtMaxChunks; }
+inline bool rt_stream_pool_supported(int V, int C) {
+  return rt_stream_supported(V, C) && C % 4 == 0 && rt_stream_threads(V, C) % (C / 4) == 0;
+}
 
 template <int TH>
 int launch_rt_stream_t(const RtUpdateArgs &a, cudaStream_t st) {
   const size_t smem = (size_t)kRtStages * 4 * TH * 16;
-  int per_sm = (int)((size_t)225 * 1024 / (smem + 1024));
+  int per_sm = (int)((size_t)225 * 1024 / (smem + 1024 + TH * 16));
   const int cap = TH == 512 ? 2 : (TH == 256 ? 4 : 6);
   if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;

@@ -541,6 +541,7 @@ struct RtUpdateArgs {
   const float *r_wT, *r_bT;       // affine of the residual norm, [C/4][V][4]
   float eps;
   float *out;                     // [B*V, C]
+  float *pool_out;                // k_rt_stream only: instead of `out`, the mean over the joints [B, C] (last layer)
   int debug;                      // measurement build only (STGCN_DEBUG bits)
 };
 

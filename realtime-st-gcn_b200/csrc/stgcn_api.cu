@@ -849,7 +849,9 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
                        float *fifo, float *acc, const int *counter, int B, Bump &ws, cudaStream_t st,
                        const LayerPrep *pp = nullptr, bool use_gw = false, bool x_planes = false,
                        bool out_planes = false, bool fifo_bf16 = false, long long slot_rows = 0,
-                       int gw_smem_cap = 0, cudaEvent_t gemm_wait = nullptr, cudaEvent_t gemm_done = nullptr) {
+                       int gw_smem_cap = 0, cudaEvent_t gemm_wait = nullptr, cudaEvent_t gemm_done = nullptr,
+                       bool pool_out = false) {
+  // pool_out (per-joint-weight path, last layer): `out` receives the mean over the joints [B, c_out] instead of rows
   // slot_rows: rows (streams * V) between consecutive FIFO / accumulator slots when the call covers only a range
   // of the streams the state was laid out for (0 = the B of this call); gw_smem_cap: see GcnwParams::smem_cap
   if (check_layer(d)) return 1;
@@ -928,7 +930,11 @@ int rt_layer_step_ntvc(const stgcn_layer_desc &d, int K, int V, int math, const 
       }
       u.eps = kEps;
       if (debug_mode() & 256) { u.res_mode = 0; }                     // timing experiments only
-      if (out_planes && !(debug_mode() & 512)) {
+      if (pool_out) {
+        STGCN_REQUIRE(!out_planes && rt_stream_enabled() && rt_stream_pool_supported(V, d.c_out),
+                      "rt layer: pooled output needs the staged state kernel");
+        u.pool_out = out;
+      } else if (out_planes && !(debug_mode() & 512)) {
         u.out_hi = reinterpret_cast<__nv_bfloat16 *>(out);
         u.out_lo = planes == 2 ? u.out_hi + (size_t)rows * d.c_out : nullptr;
       } else {
@@ -1503,12 +1509,22 @@ inline int rt_overlap_mode() {
   return v;
 }
 
+// STGCN_RT_POOL=0: the last layer writes rows and the head pools them (A/B of the fused pooling)
+inline bool rt_pool_fused_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("STGCN_RT_POOL");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
 // One continual step for streams [b0, b0 + nb) of a state laid out for B streams (the many-streams path), in
 // three parts so that two ranges can be enqueued layer by layer on two CUDA streams.
 struct RtRangeCursor {
   float *buf[2] = {nullptr, nullptr};
   int cur = 0, b0 = 0, nb = 0;
   size_t prep_off = 0;            // walk through the prepared operands
+  bool pooled = false;            // the last layer wrote the mean over the joints [nb, c_last] instead of rows
 };
 int rt_step_range_begin(const stgcn_model_desc &m, const RtLayout &L, const float *x, int B, int b0, int nb,
                         bool all_gw, Bump &ws, cudaStream_t st, RtRangeCursor &c) {
@@ -1547,10 +1563,14 @@ int rt_step_range_layer(const stgcn_model_desc &m, const RtLayout &L, void *stat
     c.prep_off = pb.off;
   }
   const bool last = i + 1 == m.num_layers;
+  // last layer: the state kernel pools over the joints itself (the head then reads [nb, C] instead of [nb*V, C])
+  const bool pool = last && all_gw && rt_pool_fused_enabled() && rt_stream_enabled() &&
+                    rt_stream_pool_supported(V, d.c_out) && !(debug_mode() & 8192);
   if (rt_layer_step_ntvc(d, K, V, m.math, c.buf[c.cur], c.buf[c.cur ^ 1], fifo, acc, counter, c.nb, ws, st,
                          have ? &P : nullptr, all_gw, all_gw, all_gw && !last, fifo16 && all_gw,
-                         c.nb == B ? 0 : (long long)B * V, gw_smem_cap, gemm_wait, gemm_done))
+                         c.nb == B ? 0 : (long long)B * V, gw_smem_cap, gemm_wait, gemm_done, pool))
     return 1;
+  c.pooled = pool;
   c.cur ^= 1;
   return 0;
 }
@@ -1559,8 +1579,8 @@ int rt_step_range_end(const stgcn_model_desc &m, float *logits, int *top5, cudaS
   ProfScope ps(KC_POOL, st);
   const int spb = rt_head_streams(c.nb);
   STGCN_CUDA_OK(launch_pdl(k_rt_head, dim3(cdiv(c.nb, spb)), dim3(256),
-                           sizeof(float) * spb * (c_last + m.num_classes), st, (const float *)c.buf[c.cur], c.nb, V,
-                           c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits + (size_t)c.b0 * m.num_classes,
+                           sizeof(float) * spb * (c_last + m.num_classes), st, (const float *)c.buf[c.cur], c.nb,
+                           c.pooled ? 1 : V, c_last, m.fcn_out_w, m.fcn_out_b, m.num_classes, logits + (size_t)c.b0 * m.num_classes,
                            top5 ? top5 + (size_t)c.b0 * 5 : (int *)nullptr, spb));
   STGCN_LAUNCH_OK();
   return 0;
