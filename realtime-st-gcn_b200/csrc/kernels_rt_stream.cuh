@@ -282,6 +282,10 @@ int launch_rt_stream_t(const RtUpdateArgs &a, cudaStream_t st) {
   long long grid = (long long)tc::num_sms() * per_sm;
   if (grid > a.B) grid = a.B;
   STGCN_CUDA_OK(cudaFuncSetAttribute(k_rt_stream<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the CTAs per SM computed above need the largest shared-memory carve-out (the driver's default choice left
+  // k_rt_stream<512> at one CTA per SM once its static shared memory grew past the 196 KB configuration)
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_rt_stream<TH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
   STGCN_CUDA_OK(launch_pdl(k_rt_stream<TH>, dim3((unsigned)grid), dim3(TH + 32), (size_t)smem, st, a));
   return 0;
 }
