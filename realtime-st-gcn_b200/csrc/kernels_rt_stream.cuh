@@ -62,11 +62,14 @@ __device__ __forceinline__ float rt_block_sum(float v, float *s_red) {
 // each array: z | acc | fifo slot | residual, TH*16 B each.  The producer warp streams chunk after chunk,
 // across stream boundaries, kRtStages ahead; a compute thread keeps its (at most kRtMaxChunks) updated
 // accumulator values and residuals in registers until the stream's LayerNorm statistics are known.
-template <int TH>
+// POOL: the instantiation that also pools over the joints (last layer).  Its 8 KB scratch is kept out of the other
+// layers' kernel: with it two 512-thread CTAs no longer fit the 196 KB shared-memory configuration, and the larger
+// one leaves 28 KB of L1 for 51 KB of LayerNorm tables (ncu: 145 -> 182 us per launch).
+template <int TH, bool POOL>
 __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) k_rt_stream(const RtUpdateArgs p) {
   extern __shared__ __align__(128) uint8_t rt_smem[];
   __shared__ float s_red[32];
-  __shared__ float4 s_pool[TH];                       // pool_out: per-thread sums over this thread's joints
+  __shared__ float4 s_pool[POOL ? TH : 1];            // pool_out: per-thread sums over this thread's joints
   __shared__ __align__(8) unsigned long long s_bar[2 * kRtStages];
   const int tid = threadIdx.x;
   const int n = p.V * p.C, n4 = n >> 2, C4 = p.C >> 2;
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(TH + 32, TH == 512 ? 2 : (TH == 256 ? 4 : 6)) 
           }
         }
       }
-    if (p.pool_out) {
+    if (POOL && p.pool_out) {
       // mean over the joints (the model's AvgPool2d((1, V)), rtstgcn.py:127): TH is a multiple of C/4, so a thread's
       // float4 always belongs to channel group tid % (C/4); the TH / (C/4) partial sums of a group are added in a
       // fixed order.  The next stream's first block reduction separates these reads from the next writes.
@@ -272,30 +275,30 @@ inline bool rt_stream_pool_supported(int V, int C) {
   return rt_stream_supported(V, C) && C % 4 == 0 && rt_stream_threads(V, C) % (C / 4) == 0;
 }
 
-template <int TH>
+template <int TH, bool POOL>
 int launch_rt_stream_t(const RtUpdateArgs &a, cudaStream_t st) {
   const size_t smem = (size_t)kRtStages * 4 * TH * 16;
-  int per_sm = (int)((size_t)225 * 1024 / (smem + 1024 + TH * 16));
+  int per_sm = (int)((size_t)225 * 1024 / (smem + 1024 + (POOL ? TH * 16 : 0)));
   const int cap = TH == 512 ? 2 : (TH == 256 ? 4 : 6);
   if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)tc::num_sms() * per_sm;
   if (grid > a.B) grid = a.B;
-  STGCN_CUDA_OK(cudaFuncSetAttribute(k_rt_stream<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // the CTAs per SM computed above need the largest shared-memory carve-out (the driver's default choice left
-  // k_rt_stream<512> at one CTA per SM once its static shared memory grew past the 196 KB configuration)
-  STGCN_CUDA_OK(cudaFuncSetAttribute(k_rt_stream<TH>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     (int)cudaSharedmemCarveoutMaxShared));
-  STGCN_CUDA_OK(launch_pdl(k_rt_stream<TH>, dim3((unsigned)grid), dim3(TH + 32), (size_t)smem, st, a));
+  STGCN_CUDA_OK(cudaFuncSetAttribute(k_rt_stream<TH, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (POOL)   // two CTAs of the pooling variant need the largest carve-out
+    STGCN_CUDA_OK(cudaFuncSetAttribute(k_rt_stream<TH, POOL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+  STGCN_CUDA_OK(launch_pdl(k_rt_stream<TH, POOL>, dim3((unsigned)grid), dim3(TH + 32), (size_t)smem, st, a));
   return 0;
 }
 
 inline int launch_rt_stream(const RtUpdateArgs &a, cudaStream_t st) {
+  const bool pool = a.pool_out != nullptr;
   switch (rt_stream_threads(a.V, a.C)) {
-    case 128: return launch_rt_stream_t<128>(a, st);
-    case 256: return launch_rt_stream_t<256>(a, st);
+    case 128: return pool ? launch_rt_stream_t<128, true>(a, st) : launch_rt_stream_t<128, false>(a, st);
+    case 256: return pool ? launch_rt_stream_t<256, true>(a, st) : launch_rt_stream_t<256, false>(a, st);
   }
-  return launch_rt_stream_t<512>(a, st);
+  return pool ? launch_rt_stream_t<512, true>(a, st) : launch_rt_stream_t<512, false>(a, st);
 }
 
 }  // namespace stgcn
